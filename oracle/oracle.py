@@ -139,7 +139,10 @@ def attenuate_speaker(impulses, mic, speaker_direction, coefficient):
 
 def attenuate_hrtf(impulses, mic, table_one_ear, facing, up, channel):
     imp = np.ascontiguousarray(impulses, dtype=IMPULSE)
-    tab = np.ascontiguousarray(table_one_ear, dtype=np.float32).reshape(360 * 180, 8)
+    # elevation index 180 reads into the next azimuth row (kernel.cpp:583); for azimuth 359 that
+    # is one row past the table (undefined in the reference): defined here as a row of zeros
+    tab = np.zeros((360 * 180 + 180, 8), dtype=np.float32)
+    tab[:360 * 180] = np.asarray(table_one_ear, dtype=np.float32).reshape(360 * 180, 8)
     out = np.zeros(len(imp), dtype=ATTENUATED)
     mic, facing, up = _f3(mic), _f3(facing), _f3(up)
     lib().orc_attenuate_hrtf(_p(imp), len(imp), _p(mic), _p(tab), _p(facing), _p(up), int(channel), _p(out))

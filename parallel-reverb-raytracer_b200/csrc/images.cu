@@ -1,0 +1,158 @@
+// Image-source de-duplication on the device.
+//
+// Replaces the host loop of Raytracer::raytrace (rayverb/rayverb.cpp:654-676) and the ordered
+// walk of getRawImages (:692-706): the reference inserts, for every ray and every prefix length
+// k, the key idx[0..k) into a std::map<vector<ulong>, Impulse> unless it is already there, so
+// the FIRST (lowest-index) ray wins and the result comes out in lexicographic key order with a
+// proper prefix before its extensions.
+//
+// Here: stable-compact the candidate slots (ray-major), then LSD radix sort on the key columns
+// (column value = entry + 1, 0 = "past the end", so prefixes sort first); stability keeps the
+// lowest ray first within equal keys; then keep the head of every run of equal keys.
+#include <cub/cub.cuh>
+
+#include "rvb_internal.cuh"
+
+namespace rvb {
+
+struct CandValid {
+    const uint32_t *idx;
+    uint64_t ray_offset;
+    __device__ bool operator()(uint32_t flat) const
+    {
+        uint32_t k0 = flat % RVB_NUM_IMAGE_SOURCE;
+        if (k0 == 0) return ray_offset + flat / RVB_NUM_IMAGE_SOURCE == 0;   // only the very first ray carries key {0}
+        return idx[flat] != 0;                                               // rayverb.cpp:667
+    }
+};
+
+// column j of the key of candidate `flat`: entry+1 inside the key, 0 past its end
+__device__ __forceinline__ uint32_t key_col(const uint32_t *idx, uint32_t flat, uint32_t j)
+{
+    uint32_t k0 = flat % RVB_NUM_IMAGE_SOURCE;
+    if (j > k0) return 0u;
+    if (j == 0) return 1u;                                                   // idx[..][0] is always 0 (direct slot)
+    return idx[flat - k0 + j] + 1u;
+}
+
+__global__ void col_keys_kernel(const uint32_t *idx, const uint32_t *sel, const uint32_t *perm, uint32_t n, uint32_t j,
+                                uint32_t *keys)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) keys[p] = key_col(idx, sel[perm[p]], j);
+}
+
+__global__ void iota_kernel(uint32_t *a, uint32_t n)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) a[p] = p;
+}
+
+__global__ void head_flags_kernel(const uint32_t *idx, const uint32_t *sel, const uint32_t *perm, uint32_t n, uint8_t *head)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    bool h = (p == 0);
+    if (!h) {
+        uint32_t a = sel[perm[p]], b = sel[perm[p - 1]];
+        for (uint32_t j = 0; j < RVB_NUM_IMAGE_SOURCE && !h; ++j) h = key_col(idx, a, j) != key_col(idx, b, j);
+    }
+    head[p] = h ? 1 : 0;
+}
+
+__global__ void gather_unique_kernel(const uint32_t *idx, const uint32_t *sel, const uint32_t *perm, const uint32_t *upos,
+                                     uint32_t m, const float4 *cvA, const float4 *cvB, const float4 *cpt, float4 *ovA,
+                                     float4 *ovB, float4 *opt, uint32_t *okeys, int32_t *olen)
+{
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= m) return;
+    uint32_t flat = sel[perm[upos[u]]];
+    ovA[u] = cvA[flat]; ovB[u] = cvB[flat]; opt[u] = cpt[flat];
+    uint32_t k0 = flat % RVB_NUM_IMAGE_SOURCE;
+    olen[u] = (int32_t)k0 + 1;
+    for (uint32_t j = 0; j < RVB_NUM_IMAGE_SOURCE; ++j) okeys[u * RVB_NUM_IMAGE_SOURCE + j] = (j <= k0) ? idx[flat - k0 + j] : 0u;
+}
+
+int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 *cpt, const uint32_t *cidx)
+{
+    cudaStream_t st = lib_stream();
+    tr->n_images = 0; tr->img_keys.clear(); tr->img_len.clear(); tr->first_is_direct = false;
+    const size_t nflat64 = tr->nrays * RVB_NUM_IMAGE_SOURCE;
+    if (nflat64 == 0) return RVB_OK;
+    if (nflat64 > 0xffffffffull) return fail(RVB_ERR_UNSUPPORTED, "too many rays for one image-source pass");
+    const uint32_t nflat = (uint32_t)nflat64;
+
+    uint32_t *d_sel = nullptr, *d_nsel = nullptr;
+    RVB_TRY(dev_alloc(&d_sel, nflat));
+    RVB_TRY(dev_alloc(&d_nsel, 1));
+    CandValid pred{cidx, tr->ray_offset};
+    cub::CountingInputIterator<uint32_t> it(0);
+    size_t tmp_bytes = 0;
+    RVB_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_sel, d_nsel, (int)nflat, pred, st));
+    uint8_t *d_tmp = nullptr;
+    RVB_TRY(dev_alloc(&d_tmp, tmp_bytes));
+    RVB_CUDA(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_sel, d_nsel, (int)nflat, pred, st));
+    uint32_t n = 0;
+    RVB_CUDA(cudaMemcpyAsync(&n, d_nsel, sizeof n, cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_tmp);
+    if (n == 0) { dev_free(d_sel); dev_free(d_nsel); return RVB_OK; }
+
+    uint32_t *d_perm[2] = {nullptr, nullptr}, *d_keys[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_perm[i], n)); RVB_TRY(dev_alloc(&d_keys[i], n)); }
+    const unsigned blk = 256, grd = (n + blk - 1) / blk;
+    iota_kernel<<<grd, blk, 0, st>>>(d_perm[0], n);
+    int end_bit = 1;
+    while ((1ull << end_bit) < (unsigned long long)tr->scene->T + 2ull) ++end_bit;
+    size_t sort_bytes = 0;
+    RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys[0], d_keys[1], d_perm[0], d_perm[1], (int)n, 0, end_bit, st));
+    uint8_t *d_sort_tmp = nullptr;
+    RVB_TRY(dev_alloc(&d_sort_tmp, sort_bytes));
+    int cur = 0;
+    const uint32_t last_col = (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl);
+    for (uint32_t j = last_col; j >= 1; --j) {   // LSD over key columns; column 0 is constant
+        col_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, j, d_keys[0]);
+        RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_bytes, d_keys[0], d_keys[1], d_perm[cur], d_perm[cur ^ 1],
+                                                 (int)n, 0, end_bit, st));
+        cur ^= 1;
+    }
+    dev_free(d_sort_tmp);
+
+    uint8_t *d_head = nullptr;
+    RVB_TRY(dev_alloc(&d_head, n));
+    head_flags_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, d_head);
+    uint32_t *d_upos = d_keys[0], *d_m = d_nsel;
+    size_t fl_bytes = 0;
+    RVB_CUDA(cub::DeviceSelect::Flagged(nullptr, fl_bytes, it, d_head, d_upos, d_m, (int)n, st));
+    uint8_t *d_fl_tmp = nullptr;
+    RVB_TRY(dev_alloc(&d_fl_tmp, fl_bytes));
+    RVB_CUDA(cub::DeviceSelect::Flagged(d_fl_tmp, fl_bytes, it, d_head, d_upos, d_m, (int)n, st));
+    uint32_t m = 0;
+    RVB_CUDA(cudaMemcpyAsync(&m, d_m, sizeof m, cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_fl_tmp);
+
+    RVB_TRY(dev_alloc(&tr->d_img_volA, m));
+    RVB_TRY(dev_alloc(&tr->d_img_volB, m));
+    RVB_TRY(dev_alloc(&tr->d_img_pt, m));
+    uint32_t *d_okeys = nullptr;
+    int32_t *d_olen = nullptr;
+    RVB_TRY(dev_alloc(&d_okeys, (size_t)m * RVB_NUM_IMAGE_SOURCE));
+    RVB_TRY(dev_alloc(&d_olen, m));
+    gather_unique_kernel<<<(m + blk - 1) / blk, blk, 0, st>>>(cidx, d_sel, d_perm[cur], d_upos, m, cvA, cvB, cpt, tr->d_img_volA,
+                                                              tr->d_img_volB, tr->d_img_pt, d_okeys, d_olen);
+    RVB_CUDA(cudaGetLastError());
+    tr->img_keys.resize((size_t)m * RVB_NUM_IMAGE_SOURCE);
+    tr->img_len.resize(m);
+    RVB_CUDA(cudaMemcpyAsync(tr->img_keys.data(), d_okeys, tr->img_keys.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaMemcpyAsync(tr->img_len.data(), d_olen, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    tr->n_images = m;
+    tr->first_is_direct = (m > 0 && tr->img_len[0] == 1);   // key {0} sorts first when present
+    dev_free(d_okeys); dev_free(d_olen); dev_free(d_head);
+    for (int i = 0; i < 2; ++i) { dev_free(d_perm[i]); dev_free(d_keys[i]); }
+    dev_free(d_sel); dev_free(d_nsel);
+    return RVB_OK;
+}
+
+}  // namespace rvb

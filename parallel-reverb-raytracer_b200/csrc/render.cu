@@ -1,0 +1,810 @@
+// Fused device-resident path from trace results to the impulse response: everything
+// cmd/main.cpp:254-336 does after raytrace() --
+//   getAllRaw / getRawImages / getRawDiffuse           (rayverb.cpp:687-714)
+//   SpeakerAttenuator / HrtfAttenuator                 (kernel.cpp:506-625)
+//   fixPredelay                                        (rayverb.h:47-97)
+//   flattenImpulses                                    (rayverb.cpp:48-77)
+//   RayverbFiltering::filter, mixdown, normalize, mul, trimTail   (filters.cpp:156-306, rayverb.cpp:80-149)
+// -- without the impulses leaving the GPU.
+//
+// flattenImpulses is a serial float scatter-add in the reference.  Here it is a deterministic
+// sort-by-sample-index (LSD radix sort of (bin, impulse id) pairs, stable => fixed order inside
+// a bin) followed by a segmented reduction with a fixed lane assignment and a fixed shuffle
+// tree: no float atomics, bit-identical from run to run.
+#include <cub/cub.cuh>
+
+#include <cmath>
+
+#include "attenuate.cuh"
+#include "rvb_internal.cuh"
+
+namespace rvb {
+
+#define RVB_MAX_GROUP 4   // speaker channels reduced per pass over a bin
+
+// The impulse list seen by the attenuators: diffuse slots first, then image sources
+// (getAllRaw, rayverb.cpp:708-714).
+struct Source {
+    const float4 *volA, *volB, *pt;
+    const float *tkey;               // time if any(volume != 0) else -1
+    uint32_t n_diffuse;
+    const float4 *ivolA, *ivolB, *ipt;
+    uint32_t n_images;
+    __device__ __forceinline__ uint32_t size() const { return n_diffuse + n_images; }
+    // returns false for impulses the attenuation kernels skip (kernel.cpp:524,607)
+    __device__ __forceinline__ bool time_of(uint32_t i, float &t) const
+    {
+        if (i < n_diffuse) { t = tkey[i]; return t >= 0.0f; }
+        uint32_t j = i - n_diffuse;
+        float4 a = ivolA[j], b = ivolB[j];
+        t = ipt[j].w;
+        return a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f || b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f;
+    }
+    __device__ __forceinline__ float4 pos_time(uint32_t i) const { return i < n_diffuse ? pt[i] : ipt[i - n_diffuse]; }
+    __device__ __forceinline__ void volume(uint32_t i, float4 &a, float4 &b) const
+    {
+        if (i < n_diffuse) { a = volA[i]; b = volB[i]; } else { a = ivolA[i - n_diffuse]; b = ivolB[i - n_diffuse]; }
+    }
+};
+
+struct ChanSpec {
+    int model;          // 0 speakers, 1 hrtf, 2 none (gain 1: rvb_flatten on host arrays)
+    int nch;            // channels in this pass (speakers: <= RVB_MAX_GROUP, hrtf/none: 1)
+    f3 mic;
+    f3 sdir[RVB_MAX_GROUP];
+    float coef[RVB_MAX_GROUP];
+    f3 pointing, up, ear;
+    const float4 *table;   // one ear, padded by one row
+    unsigned long long channel;
+};
+
+__device__ __forceinline__ int ordered(float f) { int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__host__ __device__ inline float unordered(int i) { i = i ^ ((i >> 31) & 0x7fffffff); float f; memcpy(&f, &i, 4); return f; }
+
+// attenuated time of impulse i for this channel spec (before fixPredelay)
+__device__ __forceinline__ bool attenuated_time(const Source &S, const ChanSpec &C, uint32_t i, float &t)
+{
+    if (!S.time_of(i, t)) return false;
+    if (C.model == 1) {
+        float4 p = S.pos_time(i);
+        t = hrtf_time(p.w, mk3(p), C.mic, C.ear);
+    }
+    return true;
+}
+
+// min non-zero / max attenuated time (findPredelay rayverb.h:47-76, flattenImpulses rayverb.cpp:54-57)
+__global__ void times_kernel(const Source S, const ChanSpec C, int *out /* [0] ordered min nonzero, [1] ordered max */)
+{
+    float mn = __int_as_float(0x7f800000), mx = 0.0f;   // flatten's maxtime starts at 0
+    const uint32_t n = S.size();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float t;
+        if (!attenuated_time(S, C, i, t)) continue;
+        if (t != 0.0f) mn = fminf(mn, t);
+        mx = fmaxf(mx, t);
+    }
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out, ordered(mn)); atomicMax(out + 1, ordered(mx)); }
+}
+
+// fixPredelay (rayverb.h:85-89) + SAMPLE = round(time * samplerate) (rayverb.cpp:69)
+__device__ __forceinline__ uint32_t sample_index(float t, float predelay, bool fix, float sr)
+{
+    if (fix) t = t > predelay ? __fsub_rn(t, predelay) : 0.0f;
+    return (uint32_t)roundf(__fmul_rn(t, sr));
+}
+
+__global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bool fix, float sr, uint32_t L, uint32_t *keys,
+                            uint32_t *vals)
+{
+    const uint32_t n = S.size();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float t;
+        uint32_t k = L;   // sentinel: sorts behind every real bin
+        if (attenuated_time(S, C, i, t)) {
+            uint32_t s = sample_index(t, predelay, fix, sr);
+            if (s < L) k = s;
+        }
+        keys[i] = k;
+        vals[i] = i;
+    }
+}
+
+// segment bounds of every bin in the sorted key array
+__global__ void bounds_kernel(const uint32_t *keys, uint32_t n, uint32_t L, uint32_t *seg_begin, uint32_t *seg_end)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t k = keys[i];
+        if (k >= L) continue;
+        if (i == 0 || keys[i - 1] != k) seg_begin[k] = i;
+        if (i + 1 == n || keys[i + 1] != k) seg_end[k] = i + 1;
+    }
+}
+
+// One warp per bin: lane l takes entries begin+l, begin+l+32, ... in order, then a fixed
+// xor-shuffle tree combines the 32 partial sums.  hist layout: [channel][band][L].
+__global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *vals, const uint32_t *seg_begin,
+                                                     const uint32_t *seg_end, uint32_t L, float *hist, size_t chan_stride)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t bin = warp; bin < L; bin += nwarps) {
+        const uint32_t b0 = seg_begin[bin], b1 = seg_end[bin];
+        if (b0 == b1) continue;   // warp-uniform
+        float acc[RVB_MAX_GROUP][RVB_NBANDS];
+#pragma unroll
+        for (int c = 0; c < RVB_MAX_GROUP; ++c)
+#pragma unroll
+            for (int b = 0; b < RVB_NBANDS; ++b) acc[c][b] = 0.0f;
+        for (uint32_t j = b0 + lane; j < b1; j += 32) {
+            const uint32_t i = vals[j];
+            float4 va, vb;
+            S.volume(i, va, vb);
+            const float v[RVB_NBANDS] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+            if (C.model == 0) {
+                const f3 pos = mk3(S.pos_time(i));
+#pragma unroll
+                for (int c = 0; c < RVB_MAX_GROUP; ++c) {
+                    if (c < C.nch) {
+                        const float g = speaker_gain(C.mic, pos, C.sdir[c], C.coef[c]);
+#pragma unroll
+                        for (int b = 0; b < RVB_NBANDS; ++b) acc[c][b] = __fadd_rn(acc[c][b], __fmul_rn(v[b], g));
+                    }
+                }
+            } else if (C.model == 1) {
+                const f3 pos = mk3(S.pos_time(i));
+                const long idx = hrtf_index(C.pointing, C.up, normalize(pos - C.mic));
+                const float4 ga = __ldg(C.table + 2 * idx), gb = __ldg(C.table + 2 * idx + 1);
+                const float g[RVB_NBANDS] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], __fmul_rn(v[b], g[b]));
+            } else {
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], v[b]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < RVB_MAX_GROUP; ++c) {
+            if (c < C.nch) {
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) {
+                    float x = acc[c][b];
+                    for (int o = 16; o; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+                    if (lane == 0) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = x;
+                }
+            }
+        }
+    }
+}
+
+// ---- band filters (filters.cpp:156-191): TDF-II biquad, double state, float store per sample ----
+struct BiquadCoef { double b0, b1, b2, a1, a2; };
+struct RowFilter { int npass; BiquadCoef q[2]; };   // LR: q[0] lopass.twopass, q[1] hipass.twopass
+
+#define RVB_FILTER_TILE 1024
+// One warp per (channel, band) row.  The row is streamed through shared memory in tiles (all
+// lanes load/store, coalesced); lane 0 runs the recurrence.  `twopass` (forward, reverse,
+// forward, reverse) is run as a forward sweep followed by a backward sweep over the same data.
+__global__ void __launch_bounds__(32) iir_kernel(float *data, const uint32_t *row_off, const uint32_t *row_len, const RowFilter *filters,
+                                                 int mode /* 1 onepass, 2 twopass per biquad */)
+{
+    __shared__ float tile[RVB_FILTER_TILE];
+    const uint32_t row = blockIdx.x;
+    float *x = data + row_off[row];
+    const uint32_t n = row_len[row];
+    const RowFilter F = filters[row];
+    const uint32_t lane = threadIdx.x;
+    for (int p = 0; p < F.npass; ++p) {
+        const BiquadCoef q = F.q[p];
+        for (int dirn = 0; dirn < mode; ++dirn) {
+            double z1 = 0.0, z2 = 0.0;
+            for (uint32_t t0 = 0; t0 < n; t0 += RVB_FILTER_TILE) {
+                const uint32_t m = min((uint32_t)RVB_FILTER_TILE, n - t0);
+                // forward sweep reads x[t0 + k]; backward sweep reads x[n-1 - (t0 + k)]
+                for (uint32_t k = lane; k < m; k += 32) tile[k] = dirn == 0 ? x[t0 + k] : x[n - 1 - (t0 + k)];
+                __syncwarp();
+                if (lane == 0) {
+                    for (uint32_t k = 0; k < m; ++k) {
+                        const double in = (double)tile[k];
+                        const double out = __dadd_rn(__dmul_rn(in, q.b0), z1);
+                        z1 = __dsub_rn(__dadd_rn(__dmul_rn(in, q.b1), z2), __dmul_rn(q.a1, out));
+                        z2 = __dsub_rn(__dmul_rn(in, q.b2), __dmul_rn(q.a2, out));
+                        tile[k] = (float)out;
+                    }
+                }
+                __syncwarp();
+                for (uint32_t k = lane; k < m; k += 32) {
+                    if (dirn == 0) x[t0 + k] = tile[k]; else x[n - 1 - (t0 + k)] = tile[k];
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// mixdown (rayverb.cpp:80-92) + max |x| (generic_functions.h:8-24)
+__global__ void mixdown_kernel(const float *bands, uint32_t L, float *out, int *maxabs_bits)
+{
+    float m = 0.0f;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+        float s = 0.0f;
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) s = __fadd_rn(s, bands[(size_t)b * L + k]);
+        out[k] = s;
+        m = fmaxf(m, fabsf(s));
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxabs_bits, __float_as_int(m));   // m >= 0 (or NaN > inf bits: propagates)
+}
+
+__global__ void scale_kernel(float *x, uint32_t L, float f)
+{
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) x[k] = __fmul_rn(x[k], f);
+}
+
+// trimTail (rayverb.cpp:96-122): index of the last |x| >= minVol
+__global__ void last_loud_kernel(const float *x, uint32_t L, float minVol, int *last)
+{
+    int l = -1;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x)
+        if (fabsf(x[k]) >= minVol) l = (int)k;
+    for (int o = 16; o; o >>= 1) l = max(l, __shfl_xor_sync(0xffffffffu, l, o));
+    if ((threadIdx.x & 31) == 0 && l >= 0) atomicMax(last, l);
+}
+
+__global__ void aos_to_soa_kernel(const rvb_attenuated_impulse *in, uint32_t n, float4 *volA, float4 *volB, float4 *pt, float *tkey)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *s = reinterpret_cast<const float4 *>(in + i);
+    volA[i] = s[0]; volB[i] = s[1];
+    float t = s[2].x;
+    pt[i] = make_float4(0.f, 0.f, 0.f, t);
+    tkey[i] = t;   // flattenImpulses looks at every impulse, zero volume or not (rayverb.cpp:55-56,67)
+}
+
+__global__ void normalize_dirs_kernel(const float4 *in, int n, float4 *out)
+{
+    int i = threadIdx.x;
+    if (i < n) { f3 v = normalize(mk3(in[i])); out[i] = make_float4(v.x, v.y, v.z, 0.f); }
+}
+__global__ void ear_kernel(f3 pointing, f3 up, f3 mic, float4 *out)
+{
+    int ch = threadIdx.x;
+    if (ch < 2) { f3 e = hrtf_ear(pointing, up, mic, (unsigned long long)ch); out[ch] = make_float4(e.x, e.y, e.z, 0.f); }
+}
+
+static thread_local rvb_render_stats g_stats;
+
+struct Timer {
+    cudaEvent_t a, b;
+    cudaStream_t st;
+    explicit Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+static int grid_for(size_t n, int block = 256)
+{
+    size_t g = (n + block - 1) / block;
+    return (int)std::min<size_t>(std::max<size_t>(g, 1), 148 * 16);
+}
+
+// which impulses take part (cmd/main.cpp:255-269)
+static int make_source(const rvb_trace *tr, const rvb_render_config *cfg, Source &S)
+{
+    S = Source{};
+    const bool diffuse = cfg->output_mode != RVB_OUTPUT_IMAGE_ONLY;
+    const bool images = cfg->output_mode != RVB_OUTPUT_DIFFUSE_ONLY;
+    if (diffuse) {
+        size_t n = tr->nrays * tr->nrefl;
+        S.volA = tr->d_volA; S.volB = tr->d_volB; S.pt = tr->d_pt; S.tkey = tr->d_tkey; S.n_diffuse = (uint32_t)n;
+    }
+    if (images) {
+        size_t skip = (cfg->remove_direct && tr->first_is_direct) ? 1 : 0;
+        S.ivolA = tr->d_img_volA + skip; S.ivolB = tr->d_img_volB + skip; S.ipt = tr->d_img_pt + skip;
+        S.n_images = (uint32_t)(tr->n_images - skip);
+    }
+    if ((size_t)S.n_diffuse + S.n_images >= 0xffffffffull) return fail(RVB_ERR_UNSUPPORTED, "more than 2^32 impulses in one render");
+    return RVB_OK;
+}
+
+struct ChannelSetup {
+    int model = 0;
+    size_t nch = 0;
+    std::vector<ChanSpec> passes;          // one entry per (sort, reduce) pass
+    std::vector<size_t> pass_first_channel;
+    std::vector<int> pass_key_group;       // passes with the same key group share one sort
+    float4 *d_table[2] = {nullptr, nullptr};
+    ~ChannelSetup() { dev_free(d_table[0]); dev_free(d_table[1]); }
+};
+
+static int make_channels(const float mic[3], const rvb_render_config *cfg, ChannelSetup &cs)
+{
+    cudaStream_t st = lib_stream();
+    cs.model = cfg->model;
+    const f3 m = {mic[0], mic[1], mic[2]};
+    if (cfg->model == RVB_MODEL_SPEAKER) {
+        if (!cfg->speakers || cfg->nspeakers == 0) return fail(RVB_ERR_INVALID, "speaker model needs at least one speaker");
+        cs.nch = cfg->nspeakers;
+        // normalize(speaker.direction) with the device's arithmetic (kernel.cpp:511)
+        std::vector<float4> h(cs.nch);
+        for (size_t c = 0; c < cs.nch; ++c) h[c] = make_float4(cfg->speakers[c].direction.s[0], cfg->speakers[c].direction.s[1], cfg->speakers[c].direction.s[2], 0.f);
+        if (cs.nch > 1024) return fail(RVB_ERR_UNSUPPORTED, "more than 1024 speakers");
+        float4 *d = nullptr;
+        RVB_TRY(dev_alloc(&d, 2 * cs.nch));
+        RVB_CUDA(cudaMemcpyAsync(d, h.data(), cs.nch * sizeof(float4), cudaMemcpyHostToDevice, st));
+        normalize_dirs_kernel<<<1, 1024, 0, st>>>(d, (int)cs.nch, d + cs.nch);
+        RVB_CUDA(cudaMemcpyAsync(h.data(), d + cs.nch, cs.nch * sizeof(float4), cudaMemcpyDeviceToHost, st));
+        RVB_CUDA(cudaStreamSynchronize(st));
+        dev_free(d);
+        for (size_t c0 = 0; c0 < cs.nch; c0 += RVB_MAX_GROUP) {
+            ChanSpec C{};
+            C.model = 0; C.mic = m; C.nch = (int)std::min<size_t>(RVB_MAX_GROUP, cs.nch - c0);
+            for (int c = 0; c < C.nch; ++c) { C.sdir[c] = mk3(h[c0 + c]); C.coef[c] = cfg->speakers[c0 + c].coefficient; }
+            cs.passes.push_back(C); cs.pass_first_channel.push_back(c0); cs.pass_key_group.push_back(0);
+        }
+    } else if (cfg->model == RVB_MODEL_HRTF) {
+        if (!cfg->hrtf_table) return fail(RVB_ERR_INVALID, "hrtf model needs a table");
+        cs.nch = 2;
+        const size_t cells = 360 * 180;
+        float4 *d_ear = nullptr, h_ear[2];
+        RVB_TRY(dev_alloc(&d_ear, 2));
+        const f3 f = {cfg->facing[0], cfg->facing[1], cfg->facing[2]}, u = {cfg->up[0], cfg->up[1], cfg->up[2]};
+        ear_kernel<<<1, 2, 0, st>>>(f, u, m, d_ear);
+        RVB_CUDA(cudaMemcpyAsync(h_ear, d_ear, sizeof h_ear, cudaMemcpyDeviceToHost, st));
+        for (int ch = 0; ch < 2; ++ch) {
+            RVB_TRY(dev_alloc(&cs.d_table[ch], 2 * (cells + 180)));
+            RVB_CUDA(cudaMemsetAsync(cs.d_table[ch] + 2 * cells, 0, 2 * 180 * sizeof(float4), st));
+            RVB_CUDA(cudaMemcpyAsync(cs.d_table[ch], cfg->hrtf_table + (size_t)ch * cells, cells * sizeof(rvb_float8), cudaMemcpyHostToDevice, st));
+        }
+        RVB_CUDA(cudaStreamSynchronize(st));
+        dev_free(d_ear);
+        for (int ch = 0; ch < 2; ++ch) {
+            ChanSpec C{};
+            C.model = 1; C.mic = m; C.nch = 1; C.pointing = f; C.up = u; C.ear = mk3(h_ear[ch]); C.table = cs.d_table[ch]; C.channel = ch;
+            cs.passes.push_back(C); cs.pass_first_channel.push_back(ch); cs.pass_key_group.push_back(ch);
+        }
+    } else {
+        return fail(RVB_ERR_INVALID, "unknown attenuation model");
+    }
+    return RVB_OK;
+}
+
+static int times_for_spec(const Source &S, const ChanSpec &C, float &mn, float &mx)
+{
+    cudaStream_t st = lib_stream();
+    int *d = nullptr, h[2];
+    RVB_TRY(dev_alloc(&d, 2));
+    const int init[2] = {0x7f800000, 0};   // ordered(+inf), ordered(0)
+    RVB_CUDA(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, st));
+    if (S.n_diffuse + S.n_images) times_kernel<<<grid_for(S.n_diffuse + S.n_images), 256, 0, st>>>(S, C, d);
+    RVB_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d);
+    mn = unordered(h[0]); mx = unordered(h[1]);
+    if (std::isinf(mn)) mn = 0.0f;   // findPredelay: no non-zero time
+    return RVB_OK;
+}
+
+// sort + segmented reduce of one key group into hist rows
+static int histogram_passes(const Source &S, const ChannelSetup &cs, float predelay, bool fix, float sr, const size_t *lengths,
+                            float *d_hist)
+{
+    cudaStream_t st = lib_stream();
+    const uint32_t n = S.n_diffuse + S.n_images;
+    std::vector<size_t> chan_off(cs.nch + 1, 0);
+    for (size_t c = 0; c < cs.nch; ++c) chan_off[c + 1] = chan_off[c] + RVB_NBANDS * lengths[c];
+    RVB_CUDA(cudaMemsetAsync(d_hist, 0, chan_off[cs.nch] * sizeof(float), st));
+    if (n == 0) return RVB_OK;
+    uint32_t *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr}, *d_begin = nullptr, *d_end = nullptr;
+    uint8_t *d_tmp = nullptr;
+    for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_keys[i], n)); RVB_TRY(dev_alloc(&d_vals[i], n)); }
+    int last_group = -1;
+    uint32_t L = 0;
+    int cur = 0;
+    for (size_t p = 0; p < cs.passes.size(); ++p) {
+        const ChanSpec &C = cs.passes[p];
+        const size_t c0 = cs.pass_first_channel[p];
+        if (cs.model == RVB_MODEL_SPEAKER) {
+            for (int c = 1; c < C.nch; ++c)
+                if (lengths[c0 + c] != lengths[c0]) return fail(RVB_ERR_INVALID, "speaker channels must share one length");
+        }
+        if (cs.pass_key_group[p] != last_group) {
+            last_group = cs.pass_key_group[p];
+            L = (uint32_t)lengths[c0];
+            Timer tk(st);
+            keys_kernel<<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, d_keys[0], d_vals[0]);
+            g_stats.keys_ms += tk.stop();
+            Timer ts(st);
+            int end_bit = 1;
+            while ((1ull << end_bit) <= (unsigned long long)L) ++end_bit;   // keys in [0, L]
+            cub::DoubleBuffer<uint32_t> kb(d_keys[0], d_keys[1]), vb(d_vals[0], d_vals[1]);
+            size_t bytes = 0;
+            RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, 0, end_bit, st));
+            dev_free(d_tmp);
+            RVB_TRY(dev_alloc(&d_tmp, bytes));
+            RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, 0, end_bit, st));
+            cur = kb.selector;
+            if (vb.selector != cur) return fail(RVB_ERR_CUDA, "radix sort buffers diverged");
+            dev_free(d_begin); dev_free(d_end);
+            RVB_TRY(dev_alloc(&d_begin, (size_t)L + 1)); RVB_TRY(dev_alloc(&d_end, (size_t)L + 1));
+            RVB_CUDA(cudaMemsetAsync(d_begin, 0, ((size_t)L + 1) * sizeof(uint32_t), st));
+            RVB_CUDA(cudaMemsetAsync(d_end, 0, ((size_t)L + 1) * sizeof(uint32_t), st));
+            bounds_kernel<<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, L, d_begin, d_end);
+            g_stats.sort_ms += ts.stop();
+        }
+        Timer tr_(st);
+        const size_t stride = RVB_NBANDS * (size_t)L;
+        reduce_kernel<<<148 * 8, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, d_hist + chan_off[c0], stride);
+        RVB_CUDA(cudaGetLastError());
+        g_stats.reduce_ms += tr_.stop();
+    }
+    for (int i = 0; i < 2; ++i) { dev_free(d_keys[i]); dev_free(d_vals[i]); }
+    dev_free(d_begin); dev_free(d_end); dev_free(d_tmp);
+    return RVB_OK;
+}
+
+// filters.cpp:193-218
+static BiquadCoef bandpass_coef(float lo, float hi, float sr)
+{
+    const double c = std::sqrt(lo * hi);            // float overloads, as in the reference's C++
+    const double omega = 2 * M_PI * c / sr;
+    const double cs = std::cos(omega), sn = std::sin(omega);
+    const double bandwidth = std::log2(hi / lo);    // float overload
+    const double Q = sn / (std::log(2) * bandwidth * omega);
+    const double alpha = sn * std::sinh(1 / (2 * Q));
+    const double a0 = 1 + alpha, nrm = 1 / a0;
+    return BiquadCoef{nrm * alpha, nrm * 0, nrm * -alpha, nrm * (-2 * cs), nrm * (1 - alpha)};
+}
+// filters.cpp:224-260
+static double getC(double co, double sr) { const double wcT = M_PI * co / sr; return std::cos(wcT) / std::sin(wcT); }
+static void lr_coef(float l, float h, float s, BiquadCoef &lop, BiquadCoef &hip)
+{
+    {
+        const double c = getC(h, s), a0 = c * c + c * std::sqrt(2) + 1;
+        lop = BiquadCoef{1 / a0, 2 / a0, 1 / a0, (-2 * (c * c - 1)) / a0, (c * c - c * std::sqrt(2) + 1) / a0};
+    }
+    {
+        const double c = getC(l, s), a0 = c * c + c * std::sqrt(2) + 1;
+        hip = BiquadCoef{(c * c) / a0, (-2 * c * c) / a0, (c * c) / a0, (-2 * (c * c - 1)) / a0, (c * c - c * std::sqrt(2) + 1) / a0};
+    }
+}
+
+// RayverbFiltering::filter (filters.cpp:268-306) on device rows [nch][8][len_c]
+static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nch, float sr, float lo_cutoff)
+{
+    if (ft == RVB_FILTER_WINDOWED_SINC) return fail(RVB_ERR_UNSUPPORTED, "windowed-sinc filter is not implemented (SURVEY 8f rank 1)");
+    if (ft < 0 || ft > RVB_FILTER_LINKWITZ_RILEY) return fail(RVB_ERR_INVALID, "unknown filter type");
+    cudaStream_t st = lib_stream();
+    const float EDGES[9] = {lo_cutoff, 175, 350, 700, 1400, 2800, 5600, 11200, 20000};
+    const size_t nrows = nch * RVB_NBANDS;
+    std::vector<RowFilter> hf(nrows);
+    std::vector<uint32_t> off(nrows), len(nrows);
+    size_t o = 0;
+    for (size_t c = 0; c < nch; ++c)
+        for (int b = 0; b < RVB_NBANDS; ++b) {
+            RowFilter F{};
+            if (ft == RVB_FILTER_LINKWITZ_RILEY) { F.npass = 2; lr_coef(EDGES[b], EDGES[b + 1], sr, F.q[0], F.q[1]); }
+            else { F.npass = 1; F.q[0] = bandpass_coef(EDGES[b], EDGES[b + 1], sr); }
+            hf[c * RVB_NBANDS + b] = F; off[c * RVB_NBANDS + b] = (uint32_t)o; len[c * RVB_NBANDS + b] = (uint32_t)lengths[c];
+            o += lengths[c];
+        }
+    RowFilter *d_f = nullptr; uint32_t *d_off = nullptr, *d_len = nullptr;
+    RVB_TRY(dev_alloc(&d_f, nrows)); RVB_TRY(dev_alloc(&d_off, nrows)); RVB_TRY(dev_alloc(&d_len, nrows));
+    RVB_CUDA(cudaMemcpyAsync(d_f, hf.data(), nrows * sizeof(RowFilter), cudaMemcpyHostToDevice, st));
+    RVB_CUDA(cudaMemcpyAsync(d_off, off.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    RVB_CUDA(cudaMemcpyAsync(d_len, len.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    iir_kernel<<<(unsigned)nrows, 32, 0, st>>>(d_data, d_off, d_len, d_f, ft == RVB_FILTER_BIQUAD_ONEPASS ? 1 : 2);
+    RVB_CUDA(cudaGetLastError());
+    RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_f); dev_free(d_off); dev_free(d_len);
+    return RVB_OK;
+}
+
+// process (rayverb.cpp:125-149) on a device histogram; fills an Ir
+static int finish_device(const rvb_render_config *cfg, float *d_hist /* modified */, const size_t *lengths, size_t nch, Ir *ir, bool keep_bands)
+{
+    cudaStream_t st = lib_stream();
+    Timer tf(st);
+    RVB_TRY(filter_device(cfg->filter_type, d_hist, lengths, nch, cfg->sample_rate, cfg->lo_cutoff));
+    g_stats.filter_ms += tf.stop();
+    Timer tm(st);
+    size_t total = 0;
+    for (size_t c = 0; c < nch; ++c) total += lengths[c];
+    float *d_mix = nullptr; int *d_red = nullptr;
+    RVB_TRY(dev_alloc(&d_mix, total)); RVB_TRY(dev_alloc(&d_red, 2));
+    const int init[2] = {0, -1};
+    RVB_CUDA(cudaMemcpyAsync(d_red, init, sizeof init, cudaMemcpyHostToDevice, st));
+    size_t ho = 0, mo = 0;
+    for (size_t c = 0; c < nch; ++c) {
+        if (lengths[c]) mixdown_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_hist + ho, (uint32_t)lengths[c], d_mix + mo, d_red);
+        ho += RVB_NBANDS * lengths[c]; mo += lengths[c];
+    }
+    int h_red[2];
+    RVB_CUDA(cudaMemcpyAsync(h_red, d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    if (cfg->do_normalize) {   // normalize: mul(ret, 1.0 / max_amp(ret)), generic_functions.h:56-60
+        float m; memcpy(&m, &h_red[0], 4);
+        const float f = (float)(1.0 / (double)m);
+        if (total) scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, f);
+    }
+    if (cfg->volume_scale != 1) { if (total) scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, cfg->volume_scale); }
+    long trimmed = -1;
+    if (cfg->do_trim_tail) {
+        mo = 0;
+        for (size_t c = 0; c < nch; ++c) {
+            if (lengths[c]) last_loud_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_mix + mo, (uint32_t)lengths[c], 0.00001f, d_red + 1);
+            mo += lengths[c];
+        }
+        RVB_CUDA(cudaMemcpyAsync(h_red, d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
+        RVB_CUDA(cudaStreamSynchronize(st));
+        trimmed = std::max(0, h_red[1]);   // accumulate(..., 0, max(current, index)) -- the loud sample itself is dropped (Q12)
+    }
+    ir->channels.assign(nch, {});
+    ir->bands.assign(nch, {});
+    ir->band_len.assign(nch, 0);
+    mo = 0; ho = 0;
+    for (size_t c = 0; c < nch; ++c) {
+        const size_t keep = trimmed >= 0 ? std::min<size_t>((size_t)trimmed, lengths[c]) : lengths[c];
+        ir->channels[c].assign(trimmed >= 0 ? (size_t)trimmed : lengths[c], 0.0f);   // vector::resize zero-extends short channels
+        if (keep) RVB_CUDA(cudaMemcpyAsync(ir->channels[c].data(), d_mix + mo, keep * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (keep_bands) {
+            ir->bands[c].resize(RVB_NBANDS * lengths[c]);
+            ir->band_len[c] = lengths[c];
+            if (lengths[c]) RVB_CUDA(cudaMemcpyAsync(ir->bands[c].data(), d_hist + ho, RVB_NBANDS * lengths[c] * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        mo += lengths[c]; ho += RVB_NBANDS * lengths[c];
+    }
+    RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_mix); dev_free(d_red);
+    g_stats.finish_ms += tm.stop();
+    return RVB_OK;
+}
+
+static size_t flatten_length(float maxtime, float predelay, bool fix, float sr)
+{
+    float t = maxtime;
+    if (fix) t = t > predelay ? t - predelay : 0.0f;
+    return (size_t)(std::round(t * sr) + 1.0f);   // rayverb.cpp:57, float arithmetic
+}
+
+}  // namespace rvb
+
+using namespace rvb;
+
+static bool g_keep_bands = true;
+
+extern "C" {
+
+int rvb_render_get_stats(rvb_render_stats *stats)
+{
+    if (!stats) return fail(RVB_ERR_INVALID, "null argument");
+    *stats = g_stats;
+    return RVB_OK;
+}
+
+int rvb_render_times(rvb_trace *tr, const rvb_render_config *cfg, float *min_nonzero_time, float *max_time, size_t *nchannels)
+{
+    if (!tr || !cfg || !min_nonzero_time || !max_time || !nchannels) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_CUDA(cudaSetDevice(tr->scene->device));
+    Source S;
+    RVB_TRY(make_source(tr, cfg, S));
+    ChannelSetup cs;
+    RVB_TRY(make_channels(tr->mic, cfg, cs));
+    *nchannels = cs.nch;
+    int last_group = -1;
+    float mn = 0, mx = 0;
+    for (size_t p = 0; p < cs.passes.size(); ++p) {
+        if (cs.pass_key_group[p] != last_group) {
+            last_group = cs.pass_key_group[p];
+            RVB_TRY(times_for_spec(S, cs.passes[p], mn, mx));
+        }
+        for (int c = 0; c < cs.passes[p].nch; ++c) { min_nonzero_time[cs.pass_first_channel[p] + c] = mn; max_time[cs.pass_first_channel[p] + c] = mx; }
+    }
+    return RVB_OK;
+}
+
+int rvb_render_histogram(rvb_trace *tr, const rvb_render_config *cfg, float predelay, const size_t *lengths, float *d_hist)
+{
+    if (!tr || !cfg || !lengths || !d_hist) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_CUDA(cudaSetDevice(tr->scene->device));
+    g_stats = rvb_render_stats{};
+    Timer tt(lib_stream());
+    Source S;
+    RVB_TRY(make_source(tr, cfg, S));
+    ChannelSetup cs;
+    RVB_TRY(make_channels(tr->mic, cfg, cs));
+    g_stats.n_impulses = (uint64_t)S.n_diffuse + S.n_images;
+    RVB_TRY(histogram_passes(S, cs, predelay, cfg->trim_predelay != 0, cfg->sample_rate, lengths, d_hist));
+    g_stats.total_ms = tt.stop();
+    return RVB_OK;
+}
+
+int rvb_render_finish(const rvb_render_config *cfg, const float *d_hist, const size_t *lengths, size_t nchannels, rvb_ir **out)
+{
+    if (!cfg || !d_hist || !lengths || !out) return fail(RVB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    size_t total = 0;
+    for (size_t c = 0; c < nchannels; ++c) total += RVB_NBANDS * lengths[c];
+    float *d_work = nullptr;
+    RVB_TRY(dev_alloc(&d_work, total));
+    RVB_CUDA(cudaMemcpyAsync(d_work, d_hist, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    rvb_ir *ir = new rvb_ir();
+    int rc = finish_device(cfg, d_work, lengths, nchannels, ir, g_keep_bands);
+    dev_free(d_work);
+    if (rc) { delete ir; return rc; }
+    *out = ir;
+    return RVB_OK;
+}
+
+int rvb_render_ir(rvb_trace *tr, const rvb_render_config *cfg, rvb_ir **out)
+{
+    if (!tr || !cfg || !out) return fail(RVB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    RVB_CUDA(cudaSetDevice(tr->scene->device));
+    cudaStream_t st = lib_stream();
+    g_stats = rvb_render_stats{};
+    Timer tt(st);
+    Source S;
+    RVB_TRY(make_source(tr, cfg, S));
+    ChannelSetup cs;
+    RVB_TRY(make_channels(tr->mic, cfg, cs));
+    g_stats.n_impulses = (uint64_t)S.n_diffuse + S.n_images;
+    // per-channel time extrema -> predelay (min over all channels) and flatten lengths
+    std::vector<float> mn(cs.nch), mx(cs.nch);
+    int last_group = -1;
+    float a = 0, b = 0;
+    for (size_t p = 0; p < cs.passes.size(); ++p) {
+        if (cs.pass_key_group[p] != last_group) { last_group = cs.pass_key_group[p]; RVB_TRY(times_for_spec(S, cs.passes[p], a, b)); }
+        for (int c = 0; c < cs.passes[p].nch; ++c) { mn[cs.pass_first_channel[p] + c] = a; mx[cs.pass_first_channel[p] + c] = b; }
+    }
+    float predelay = 0.0f;
+    for (size_t c = 0; c < cs.nch; ++c) {   // findPredelay's fold: zeros are ignored
+        if (predelay == 0) predelay = mn[c]; else if (mn[c] != 0) predelay = std::min(predelay, mn[c]);
+    }
+    const bool fix = cfg->trim_predelay != 0;
+    std::vector<size_t> lengths(cs.nch);
+    size_t total = 0;
+    for (size_t c = 0; c < cs.nch; ++c) { lengths[c] = flatten_length(mx[c], predelay, fix, cfg->sample_rate); total += RVB_NBANDS * lengths[c]; }
+    float *d_hist = nullptr;
+    RVB_TRY(dev_alloc(&d_hist, total));
+    int rc = histogram_passes(S, cs, predelay, fix, cfg->sample_rate, lengths.data(), d_hist);
+    rvb_ir *ir = nullptr;
+    if (rc == RVB_OK) {
+        ir = new rvb_ir();
+        rc = finish_device(cfg, d_hist, lengths.data(), cs.nch, ir, g_keep_bands);
+    }
+    dev_free(d_hist);
+    if (rc) { delete ir; return rc; }
+    g_stats.total_ms = tt.stop();
+    *out = ir;
+    return RVB_OK;
+}
+
+int rvb_ir_channels(const rvb_ir *ir, size_t *n) { if (!ir || !n) return fail(RVB_ERR_INVALID, "null argument"); *n = ir->channels.size(); return RVB_OK; }
+int rvb_ir_length(const rvb_ir *ir, size_t c, size_t *n)
+{
+    if (!ir || !n || c >= ir->channels.size()) return fail(RVB_ERR_INVALID, "bad channel");
+    *n = ir->channels[c].size();
+    return RVB_OK;
+}
+int rvb_ir_copy(const rvb_ir *ir, size_t c, float *out)
+{
+    if (!ir || c >= ir->channels.size() || (!out && !ir->channels[c].empty())) return fail(RVB_ERR_INVALID, "bad channel");
+    std::copy(ir->channels[c].begin(), ir->channels[c].end(), out);
+    return RVB_OK;
+}
+int rvb_ir_band_length(const rvb_ir *ir, size_t c, size_t *n)
+{
+    if (!ir || !n || c >= ir->band_len.size()) return fail(RVB_ERR_INVALID, "bad channel");
+    *n = ir->band_len[c];
+    return RVB_OK;
+}
+int rvb_ir_copy_bands(const rvb_ir *ir, size_t c, float *out)
+{
+    if (!ir || c >= ir->bands.size() || (!out && !ir->bands[c].empty())) return fail(RVB_ERR_INVALID, "bad channel");
+    std::copy(ir->bands[c].begin(), ir->bands[c].end(), out);
+    return RVB_OK;
+}
+int rvb_ir_destroy(rvb_ir *ir) { delete ir; return RVB_OK; }
+
+// ---- host-array post-processing entry points ---------------------------------------------------
+int rvb_flatten(const rvb_attenuated_impulse *in, size_t n, float sample_rate, float **out, size_t *length)
+{
+    if (!out || !length || (n && !in)) return fail(RVB_ERR_INVALID, "null argument");
+    *out = nullptr; *length = 0;
+    RVB_TRY(ensure_device());
+    if (n >= 0xffffffffull) return fail(RVB_ERR_UNSUPPORTED, "too many impulses");
+    cudaStream_t st = lib_stream();
+    g_stats = rvb_render_stats{};
+    rvb_attenuated_impulse *d_in = nullptr;
+    float4 *vA = nullptr, *vB = nullptr, *pt = nullptr; float *tk = nullptr;
+    RVB_TRY(dev_alloc(&d_in, n)); RVB_TRY(dev_alloc(&vA, n)); RVB_TRY(dev_alloc(&vB, n)); RVB_TRY(dev_alloc(&pt, n)); RVB_TRY(dev_alloc(&tk, n));
+    if (n) {
+        RVB_CUDA(cudaMemcpyAsync(d_in, in, n * sizeof(rvb_attenuated_impulse), cudaMemcpyHostToDevice, st));
+        aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, (uint32_t)n, vA, vB, pt, tk);
+    }
+    Source S{}; S.volA = vA; S.volB = vB; S.pt = pt; S.tkey = tk; S.n_diffuse = (uint32_t)n;
+    ChannelSetup cs; cs.model = 2; cs.nch = 1;
+    ChanSpec C{}; C.model = 2; C.nch = 1;
+    cs.passes.push_back(C); cs.pass_first_channel.push_back(0); cs.pass_key_group.push_back(0);
+    float mn, mx;
+    int rc = times_for_spec(S, C, mn, mx);
+    size_t L = flatten_length(mx, 0.f, false, sample_rate);
+    float *d_hist = nullptr;
+    if (rc == RVB_OK) rc = dev_alloc(&d_hist, RVB_NBANDS * L);
+    if (rc == RVB_OK) rc = histogram_passes(S, cs, 0.f, false, sample_rate, &L, d_hist);
+    float *h = nullptr;
+    if (rc == RVB_OK) {
+        h = (float *)malloc(sizeof(float) * RVB_NBANDS * L);
+        if (!h) rc = fail(RVB_ERR_NOMEM, "host allocation failed");
+    }
+    if (rc == RVB_OK) {
+        cudaMemcpyAsync(h, d_hist, sizeof(float) * RVB_NBANDS * L, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        *out = h; *length = L;
+    }
+    dev_free(d_hist); dev_free(d_in); dev_free(vA); dev_free(vB); dev_free(pt); dev_free(tk);
+    return rc;
+}
+
+int rvb_filter(int filter_type, float *data, size_t nchannels, size_t length, float sample_rate, float lo_cutoff)
+{
+    if (!data && nchannels * length) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    const size_t total = nchannels * RVB_NBANDS * length;
+    if (total == 0) return RVB_OK;
+    float *d = nullptr;
+    RVB_TRY(dev_alloc(&d, total));
+    RVB_CUDA(cudaMemcpyAsync(d, data, total * sizeof(float), cudaMemcpyHostToDevice, st));
+    std::vector<size_t> lens(nchannels, length);
+    int rc = filter_device(filter_type, d, lens.data(), nchannels, sample_rate, lo_cutoff);
+    if (rc == RVB_OK) { cudaMemcpyAsync(data, d, total * sizeof(float), cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
+    dev_free(d);
+    return rc;
+}
+
+int rvb_process(int filter_type, float *const *data, const size_t *lengths, size_t nchannels, float sample_rate, int do_normalize,
+                float lo_cutoff, int do_trim_tail, float volume_scale, float *const *out, int64_t *out_length)
+{
+    if (!data || !lengths || !out || !out_length) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    size_t total = 0;
+    for (size_t c = 0; c < nchannels; ++c) total += RVB_NBANDS * lengths[c];
+    float *d = nullptr;
+    RVB_TRY(dev_alloc(&d, total));
+    size_t o = 0;
+    for (size_t c = 0; c < nchannels; ++c) {
+        if (lengths[c]) RVB_CUDA(cudaMemcpyAsync(d + o, data[c], RVB_NBANDS * lengths[c] * sizeof(float), cudaMemcpyHostToDevice, st));
+        o += RVB_NBANDS * lengths[c];
+    }
+    rvb_render_config cfg{};
+    cfg.filter_type = filter_type; cfg.sample_rate = sample_rate; cfg.lo_cutoff = lo_cutoff; cfg.do_normalize = do_normalize;
+    cfg.do_trim_tail = do_trim_tail; cfg.volume_scale = volume_scale;
+    Ir ir;
+    int rc = finish_device(&cfg, d, lengths, nchannels, &ir, true);
+    if (rc == RVB_OK) {
+        *out_length = do_trim_tail ? (int64_t)(nchannels ? ir.channels[0].size() : 0) : -1;
+        for (size_t c = 0; c < nchannels; ++c) {
+            // like the reference, `data` ends up filtered in place (rayverb.cpp:135)
+            std::copy(ir.bands[c].begin(), ir.bands[c].end(), data[c]);
+            size_t m = std::min(ir.channels[c].size(), lengths[c]);
+            std::copy(ir.channels[c].begin(), ir.channels[c].begin() + m, out[c]);
+        }
+    }
+    dev_free(d);
+    return rc;
+}
+
+void rvb_free(void *p) { free(p); }
+
+}  // extern "C"

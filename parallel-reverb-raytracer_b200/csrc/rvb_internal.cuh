@@ -1,0 +1,117 @@
+// Internal declarations shared by the translation units of librayverb_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rayverb_b200.h"
+#include "rvb_math.cuh"
+
+namespace rvb {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+#define RVB_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return ::rvb::fail(RVB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define RVB_TRY(call)                 \
+    do {                              \
+        int rc_ = (call);             \
+        if (rc_ != RVB_OK) return rc_; \
+    } while (0)
+
+// One library stream per device (non-blocking), created lazily; events for stage timings.
+cudaStream_t lib_stream();
+int ensure_device();   // checks that the current device exists and is sm_100; configures the mem pool
+
+// stream-ordered allocations from the device's default pool (kept warm between calls)
+template <class T>
+inline int dev_alloc(T **p, size_t n)
+{
+    *p = nullptr;
+    if (n == 0) return RVB_OK;
+    cudaError_t e = cudaMallocAsync((void **)p, n * sizeof(T), lib_stream());
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RVB_ERR_NOMEM : RVB_ERR_CUDA,
+                                      std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    return RVB_OK;
+}
+template <class T>
+inline void dev_free(T *&p)
+{
+    if (p) cudaFreeAsync((void *)p, lib_stream());
+    p = nullptr;
+}
+
+// ---- BVH node (see bvh.cu) ------------------------------------------------------------------
+// 64-byte node holding BOTH children's boxes, so one visit decides both descents.
+struct __align__(16) BvhNode {
+    float4 lo_l;   // left  box min xyz, w = bits of left  child ref
+    float4 hi_l;   // left  box max xyz, w = bits of right child ref
+    float4 lo_r;   // right box min xyz, w = unused
+    float4 hi_r;   // right box max xyz, w = unused
+};
+// child ref: >= 0 -> inner node index; < 0 -> leaf: ~ref = first position in the sorted
+// triangle order, leaf covers `leaf_count` consecutive positions (stored in the high bits)
+
+// ---- scene ----------------------------------------------------------------------------------
+struct Scene {
+    int device = 0;
+    uint32_t T = 0, S = 0;
+    int accel = RVB_ACCEL_BRUTE_FORCE;
+    float4 *d_verts = nullptr;        // [3T] v0, v1, v2 (w = 0): TriVerts of kernel.cpp:56-60, pre-gathered
+    float4 *d_tri = nullptr;          // [3T] staged intersection form: (v0.xyz,e0.x) (e0.yz,e1.xy) (e1.z,0,0,0)
+    float4 *d_nrm = nullptr;          // [T]  normalize(cross(e0,e1)) (kernel.cpp:110-116), w = surface index bits
+    rvb_surface *d_surfaces = nullptr;
+    // BVH (accel == RVB_ACCEL_BVH)
+    BvhNode *d_nodes = nullptr;       // [n_nodes]
+    uint32_t n_nodes = 0;
+    uint32_t *d_order = nullptr;      // [T] sorted position -> original triangle index
+    float4 *d_tri_sorted = nullptr;   // [3T] d_tri permuted into BVH order
+    float build_ms = 0.f;
+};
+
+// ---- trace results ----------------------------------------------------------------------------
+struct Trace {
+    Scene *scene = nullptr;
+    size_t nrays = 0, nrefl = 0;
+    uint64_t ray_offset = 0;
+    unsigned flags = 0;
+    float mic[3] = {0, 0, 0}, src[3] = {0, 0, 0};
+    // diffuse impulses, BOUNCE-major: slot = bounce * nrays + ray
+    float4 *d_volA = nullptr, *d_volB = nullptr;   // bands 0-3, 4-7
+    float4 *d_pt = nullptr;                        // position xyz, time
+    float *d_tkey = nullptr;                       // time if any(volume != 0) else -1 (kernel.cpp:524 skip rule)
+    uint32_t *d_hit = nullptr;                     // debug: hit triangle per slot
+    uint32_t *d_count = nullptr;                   // debug: reflections per ray
+    // unique image-source impulses in key order (after dedupe)
+    size_t n_images = 0;
+    float4 *d_img_volA = nullptr, *d_img_volB = nullptr, *d_img_pt = nullptr;
+    std::vector<uint32_t> img_keys;                // n_images * 10
+    std::vector<int32_t> img_len;                  // n_images
+    bool first_is_direct = false;                  // entry 0 has key {0}
+    rvb_trace_stats stats{};
+};
+
+struct Ir {
+    std::vector<std::vector<float>> channels;      // mixed-down output
+    std::vector<std::vector<float>> bands;         // [channel] -> [8][band_len] filtered, before mixdown
+    std::vector<size_t> band_len;
+};
+
+// ---- stage entry points (defined in the .cu files) ----------------------------------------------
+int scene_build_bvh(Scene *sc);                                                       // bvh.cu
+int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB,
+                 float4 *d_cand_pt, uint32_t *d_cand_idx);                            // trace.cu
+int images_dedupe(Trace *tr, const float4 *d_cand_volA, const float4 *d_cand_volB,
+                  const float4 *d_cand_pt, const uint32_t *d_cand_idx);               // images.cu
+
+}  // namespace rvb
+
+struct rvb_scene : rvb::Scene {};
+struct rvb_trace : rvb::Trace {};
+struct rvb_ir : rvb::Ir {};

@@ -1,0 +1,175 @@
+// Context, error plumbing and scene staging.
+//
+// rvb_scene_create replaces the Raytracer constructor (rayverb/rayverb.cpp:242-293): instead of
+// uploading Triangle[] / vertices[] for per-test gathers through u64 indices
+// (kernel.cpp:95-107), every triangle is gathered ONCE into
+//   d_verts  (v0, v1, v2)                       -- TriVerts for the image-source mirroring
+//   d_tri    (v0, e0 = v1-v0, e1 = v2-v0)       -- intersection form, float4-vectorised
+//   d_nrm    normalize(cross(e0, e1)), surface  -- kernel.cpp:110-116 evaluated once
+// The subtraction / normal are the same IEEE operations the reference performs per test, so the
+// staged values carry the same bits.
+#include <mutex>
+
+#include "rvb_internal.cuh"
+
+namespace rvb {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+int fail(int code, const std::string &msg) { g_error = msg; return code; }
+const char *last_error() { return g_error.c_str(); }
+
+static std::mutex g_mutex;
+static cudaStream_t g_streams[64] = {};
+static bool g_checked[64] = {};
+
+cudaStream_t lib_stream()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!g_streams[dev]) cudaStreamCreateWithFlags(&g_streams[dev], cudaStreamNonBlocking);
+    return g_streams[dev];
+}
+
+int ensure_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(RVB_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    int dev = 0;
+    RVB_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        if (g_checked[dev]) return RVB_OK;
+    }
+    cudaDeviceProp prop;
+    RVB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(RVB_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)");
+    cudaMemPool_t pool;
+    RVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;   // keep freed blocks cached: traces of the same shape re-use them
+    RVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    std::lock_guard<std::mutex> lk(g_mutex);
+    g_checked[dev] = true;
+    return RVB_OK;
+}
+
+__global__ void stage_scene_kernel(const rvb_triangle *tris, const float4 *vertices, uint32_t T, float4 *verts, float4 *tri,
+                                   float4 *nrm)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    rvb_triangle t = tris[i];
+    float4 a = vertices[t.v0], b = vertices[t.v1], c = vertices[t.v2];
+    a.w = b.w = c.w = 0.f;
+    verts[3 * i] = a; verts[3 * i + 1] = b; verts[3 * i + 2] = c;
+    f3 v0 = mk3(a), e0 = mk3(b) - mk3(a), e1 = mk3(c) - mk3(a);
+    tri[3 * i] = make_float4(v0.x, v0.y, v0.z, e0.x);
+    tri[3 * i + 1] = make_float4(e0.y, e0.z, e1.x, e1.y);
+    tri[3 * i + 2] = make_float4(e1.z, 0.f, 0.f, 0.f);
+    f3 n = normalize(cross(e0, e1));
+    nrm[i] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)t.surface));
+}
+
+}  // namespace rvb
+
+using namespace rvb;
+
+extern "C" {
+
+const char *rvb_last_error(void) { return rvb::last_error(); }
+int rvb_version(void) { return 100; }
+
+int rvb_device_count(int *count)
+{
+    if (!count) return fail(RVB_ERR_INVALID, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(RVB_ERR_CUDA, cudaGetErrorString(e)); }
+    *count = n;
+    return RVB_OK;
+}
+
+int rvb_set_device(int device)
+{
+    RVB_CUDA(cudaSetDevice(device));
+    return ensure_device();
+}
+
+int rvb_scene_create(const rvb_triangle *triangles, size_t ntriangles, const rvb_float3 *vertices, size_t nvertices,
+                     const rvb_surface *surfaces, size_t nsurfaces, int accel, rvb_scene **out)
+{
+    if (!out) return fail(RVB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!triangles || !vertices || !surfaces || ntriangles == 0 || nvertices == 0 || nsurfaces == 0)
+        return fail(RVB_ERR_INVALID, "scene needs at least one triangle, vertex and surface");
+    if (ntriangles >= (1u << 28)) return fail(RVB_ERR_UNSUPPORTED, "more than 2^28 triangles");
+    // The reference never validates indices (SceneData::valid() is dead code, rayverb.cpp:463-502)
+    // and out-of-range ones are undefined behaviour in its kernel; here they are an error.
+    for (size_t i = 0; i < ntriangles; ++i) {
+        const rvb_triangle &t = triangles[i];
+        if (t.surface >= nsurfaces || t.v0 >= nvertices || t.v1 >= nvertices || t.v2 >= nvertices)
+            return fail(RVB_ERR_INVALID, "triangle " + std::to_string(i) + " references an out-of-range vertex or surface");
+    }
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    rvb_scene *sc = new rvb_scene();
+    cudaGetDevice(&sc->device);
+    sc->T = (uint32_t)ntriangles;
+    sc->S = (uint32_t)nsurfaces;
+    rvb_triangle *d_tris = nullptr;
+    float4 *d_vertices = nullptr;
+    int rc = RVB_OK;
+    auto cleanup = [&]() { dev_free(d_tris); dev_free(d_vertices); };
+    if ((rc = dev_alloc(&d_tris, ntriangles)) || (rc = dev_alloc(&d_vertices, nvertices)) ||
+        (rc = dev_alloc(&sc->d_verts, 3 * ntriangles)) || (rc = dev_alloc(&sc->d_tri, 3 * ntriangles)) ||
+        (rc = dev_alloc(&sc->d_nrm, ntriangles)) || (rc = dev_alloc(&sc->d_surfaces, nsurfaces))) {
+        cleanup(); rvb_scene_destroy(sc); return rc;
+    }
+    cudaMemcpyAsync(d_tris, triangles, ntriangles * sizeof(rvb_triangle), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_vertices, vertices, nvertices * sizeof(rvb_float3), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(sc->d_surfaces, surfaces, nsurfaces * sizeof(rvb_surface), cudaMemcpyHostToDevice, st);
+    stage_scene_kernel<<<(unsigned)((ntriangles + 255) / 256), 256, 0, st>>>(d_tris, d_vertices, sc->T, sc->d_verts, sc->d_tri, sc->d_nrm);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) { rvb_scene_destroy(sc); return fail(RVB_ERR_CUDA, std::string("scene staging: ") + cudaGetErrorString(e)); }
+
+    const size_t smem_limit = 227 * 1024;
+    const bool fits = (size_t)3 * ntriangles * sizeof(float4) <= smem_limit;
+    if (accel == RVB_ACCEL_BRUTE_FORCE && !fits) {
+        rvb_scene_destroy(sc);
+        return fail(RVB_ERR_INVALID, "brute-force path needs the scene in shared memory (<= 4843 triangles)");
+    }
+    if (accel == RVB_ACCEL_AUTO) accel = (ntriangles <= 1024) ? RVB_ACCEL_BRUTE_FORCE : RVB_ACCEL_BVH;
+    sc->accel = accel;
+    if (accel == RVB_ACCEL_BVH) {
+        rc = scene_build_bvh(sc);
+        if (rc) { rvb_scene_destroy(sc); return rc; }
+    }
+    *out = sc;
+    return RVB_OK;
+}
+
+int rvb_scene_destroy(rvb_scene *sc)
+{
+    if (!sc) return RVB_OK;
+    cudaSetDevice(sc->device);
+    dev_free(sc->d_verts); dev_free(sc->d_tri); dev_free(sc->d_nrm); dev_free(sc->d_surfaces);
+    dev_free(sc->d_nodes); dev_free(sc->d_order); dev_free(sc->d_tri_sorted);
+    cudaStreamSynchronize(lib_stream());
+    delete sc;
+    return RVB_OK;
+}
+
+int rvb_scene_accel(const rvb_scene *scene, int *accel)
+{
+    if (!scene || !accel) return fail(RVB_ERR_INVALID, "null argument");
+    *accel = scene->accel;
+    return RVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// The bounce kernel: B200-native replacement of `kernel raytrace` (rayverb/kernel.cpp:304-503).
+//
+// One thread per ray, persistent grid-stride over rays.  The whole scene is staged once per
+// CTA in shared memory in intersection form (v0, e0, e1 -- 3 x float4 per triangle, read as
+// warp-wide broadcasts) for the brute-force path, or traversed through the GPU-built BVH
+// (bvh.cu) whose nearest-hit result -- including the lowest-index tie-break of the reference's
+// strict '<' loop (kernel.cpp:180-188) -- equals the brute-force loop.
+//
+// Output is a bounce-major SoA (slot = bounce * nrays + ray) so that the 32 lanes of a warp,
+// which sit at the same bounce, write 32 consecutive 32-byte sectors.
+#include "rvb_internal.cuh"
+
+namespace rvb {
+
+struct TraceParams {
+    const float4 *verts;      // [3T]
+    const float4 *tri;        // [3T] staged (v0,e0,e1)
+    const float4 *nrm;        // [T]
+    const rvb_surface *surfaces;
+    uint32_t T;
+    // BVH
+    const BvhNode *nodes;
+    const float4 *tri_sorted;
+    const uint32_t *order;
+    const float4 *dirs;
+    uint32_t nrays, nrefl;
+    uint64_t ray_offset;
+    float mic[3], src[3];
+    float air[RVB_NBANDS];
+    float4 *volA, *volB, *pt;
+    float *tkey;
+    uint32_t *hit, *count;
+    float4 *cand_volA, *cand_volB, *cand_pt;   // [nrays*10] image-source candidates
+    uint32_t *cand_idx;                        // [nrays*10] triangle+1, 0 = none (pre-zeroed)
+    unsigned long long *counters;              // [0] queries [1] tri tests [2] box tests [3] bounces
+    uint32_t flags;
+};
+
+struct Counters { uint32_t queries = 0, bounces = 0; unsigned long long tri = 0, box = 0; };
+
+#define RVB_NONE 0xffffffffu
+
+// ---- brute force over the shared-memory scene (kernel.cpp:167-192) ---------------------------
+struct BruteSmem {
+    const float4 *s;
+    uint32_t T;
+
+    __device__ __forceinline__ void load(uint32_t i, f3 &v0, f3 &e0, f3 &e1) const
+    {
+        float4 A = s[3 * i], B = s[3 * i + 1], C = s[3 * i + 2];
+        v0 = mk3(A.x, A.y, A.z); e0 = mk3(A.w, B.x, B.y); e1 = mk3(B.z, B.w, C.x);
+    }
+    __device__ __forceinline__ bool nearest(f3 pos, f3 dir, float &tbest, uint32_t &ibest, Counters &c) const
+    {
+        tbest = __int_as_float(0x7f800000);
+        ibest = RVB_NONE;
+#pragma unroll 4
+        for (uint32_t i = 0; i < T; ++i) {
+            f3 v0, e0, e1;
+            load(i, v0, e0, e1);
+            bool ok;
+            float t = mt_intersect_pred(v0, e0, e1, pos, dir, ok);
+            if (ok && t > RVB_EPSILON && t < tbest) { tbest = t; ibest = i; }
+        }
+        c.queries++; c.tri += T;
+        return ibest != RVB_NONE;
+    }
+    // point_intersection (kernel.cpp:274-296): visible unless some hit has EPS < t <= mag
+    __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
+    {
+        bool blocked = false;
+#pragma unroll 4
+        for (uint32_t i = 0; i < T; ++i) {
+            f3 v0, e0, e1;
+            load(i, v0, e0, e1);
+            bool ok;
+            float t = mt_intersect_pred(v0, e0, e1, pos, dir, ok);
+            blocked |= (ok && t > RVB_EPSILON && t <= mag);
+        }
+        c.queries++; c.tri += T;
+        return blocked;
+    }
+};
+
+// ---- BVH traversal ----------------------------------------------------------------------------
+// Boxes are padded at build time and the slab test carries a relative slack, so no triangle the
+// exact test would accept at (t, index) better than the current best is ever culled; candidates
+// are compared lexicographically on (t, original index) to reproduce the in-order strict '<' loop.
+struct BvhAccel {
+    const BvhNode *nodes;
+    const float4 *tri;       // sorted (v0,e0,e1)
+    const uint32_t *order;   // sorted position -> original index
+
+    __device__ __forceinline__ static bool slab(float4 lo, float4 hi, f3 o, f3 inv, float tmax, float &tnear)
+    {
+        float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
+        float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
+        float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
+        float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+        float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
+        tnear = tn;
+        // fminf/fmaxf drop NaNs (0 * inf on a face-parallel ray exactly on the slab plane), which
+        // widens the interval: conservative.  1.00001f covers the rounding of the six products.
+        return tn <= tf * 1.00001f + 1e-6f;
+    }
+
+    template <bool ANY>
+    __device__ __forceinline__ bool traverse(f3 pos, f3 dir, float tlimit, float &tbest, uint32_t &ibest, Counters &c) const
+    {
+        // 1/0 = inf is what the slab test wants for axis-parallel rays
+        f3 inv = mk3(__fdividef(1.0f, dir.x), __fdividef(1.0f, dir.y), __fdividef(1.0f, dir.z));
+        if (dir.x == 0.0f) inv.x = __int_as_float(0x7f800000);
+        if (dir.y == 0.0f) inv.y = __int_as_float(0x7f800000);
+        if (dir.z == 0.0f) inv.z = __int_as_float(0x7f800000);
+        tbest = tlimit;
+        ibest = RVB_NONE;
+        int stack[48];
+        int sp = 0;
+        int node = 0;
+        uint32_t nbox = 0, ntri = 0;
+        bool found = false;
+        while (true) {
+            if (node >= 0) {
+                const BvhNode n = nodes[node];
+                float tl, tr;
+                // candidates farther than the best are useless; equal t must still be visited (tie-break)
+                float lim = tbest * 1.00001f + 1e-6f;
+                bool hl = slab(n.lo_l, n.hi_l, pos, inv, lim, tl);
+                bool hr = slab(n.lo_r, n.hi_r, pos, inv, lim, tr);
+                nbox += 2;
+                int cl = __float_as_int(n.lo_l.w), cr = __float_as_int(n.hi_l.w);
+                if (hl && hr) {
+                    if (tr < tl) { int t_ = cl; cl = cr; cr = t_; }
+                    stack[sp++] = cr;
+                    node = cl;
+                    continue;
+                } else if (hl) { node = cl; continue; }
+                else if (hr) { node = cr; continue; }
+            } else {
+                uint32_t ref = ~(uint32_t)node;
+                uint32_t first = ref & 0x0fffffffu, cnt = (ref >> 28) + 1;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    uint32_t p = first + k;
+                    float4 A = __ldg(tri + 3 * p), B = __ldg(tri + 3 * p + 1), C = __ldg(tri + 3 * p + 2);
+                    bool ok;
+                    float t = mt_intersect_pred(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), mk3(B.z, B.w, C.x), pos, dir, ok);
+                    ++ntri;
+                    if (ok && t > RVB_EPSILON) {
+                        if (ANY) {
+                            if (t <= tlimit) { found = true; }
+                        } else {
+                            uint32_t oi = __ldg(order + p);
+                            if (t < tbest || (t == tbest && oi < ibest)) { tbest = t; ibest = oi; }
+                        }
+                    }
+                }
+                if (ANY && found) break;
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+        c.queries++; c.tri += ntri; c.box += nbox;
+        return ANY ? found : (ibest != RVB_NONE);
+    }
+    __device__ __forceinline__ bool nearest(f3 pos, f3 dir, float &tbest, uint32_t &ibest, Counters &c) const
+    {
+        return traverse<false>(pos, dir, __int_as_float(0x7f800000), tbest, ibest, c);
+    }
+    __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
+    {
+        float t; uint32_t i;
+        return traverse<true>(pos, dir, mag, t, i, c);
+    }
+};
+
+// kernel.cpp:195-214: pow(M_E, distance * AIR) * 1
+__device__ __forceinline__ void air_attenuation(float distance, const float *air, float *att)
+{
+#pragma unroll
+    for (int b = 0; b < RVB_NBANDS; ++b) att[b] = powf(RVB_M_E_F, __fmul_rn(distance, air[b]));
+}
+
+// kernel.cpp:274-296
+template <class Accel>
+__device__ __forceinline__ bool point_visible(const Accel &acc, f3 begin, f3 point, Counters &c)
+{
+    f3 btp = point - begin;
+    float mag = length(btp);
+    f3 dir = normalize(btp);
+    return !acc.occluded(begin, dir, mag, c);
+}
+
+__device__ __forceinline__ TriVerts load_verts(const float4 *verts, uint32_t i)
+{
+    TriVerts t;
+    t.v0 = mk3(__ldg(verts + 3 * i)); t.v1 = mk3(__ldg(verts + 3 * i + 1)); t.v2 = mk3(__ldg(verts + 3 * i + 2));
+    return t;
+}
+
+// kernel.cpp:243-265
+__device__ __forceinline__ void add_image(const TraceParams &P, f3 mic, f3 mic_reflection, f3 source, size_t slot,
+                                          const float *volume, uint32_t object_index)
+{
+    f3 diff = source - mic_reflection;
+    float dist = length(diff);
+    float att[RVB_NBANDS];
+    air_attenuation(dist, P.air, att);
+    float v[RVB_NBANDS];
+#pragma unroll
+    for (int b = 0; b < RVB_NBANDS; ++b) v[b] = __fmul_rn(volume[b], att[b]);
+    f3 p = mic + diff;
+    P.cand_volA[slot] = make_float4(v[0], v[1], v[2], v[3]);
+    P.cand_volB[slot] = make_float4(v[4], v[5], v[6], v[7]);
+    P.cand_pt[slot] = make_float4(p.x, p.y, p.z, __fmul_rn(RVB_SECONDS_PER_METER, dist));
+    P.cand_idx[slot] = object_index;
+}
+
+// kernel.cpp:304-503 for one ray
+template <class Accel>
+__device__ void trace_ray(const Accel &acc, const TraceParams &P, uint32_t ray, Counters &c)
+{
+    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+    const f3 source = mk3(P.src[0], P.src[1], P.src[2]);
+    f3 ray_pos = source;
+    f3 ray_dir = mk3(__ldg(P.dirs + ray));
+    float distance = 0.0f;
+    float volume[RVB_NBANDS];
+#pragma unroll
+    for (int b = 0; b < RVB_NBANDS; ++b) volume[b] = 1.0f;
+    const bool do_images = !(P.flags & RVB_TRACE_NO_IMAGES);
+    TriVerts prev[RVB_NUM_IMAGE_SOURCE - 1];
+    f3 mic_reflection = mic;
+
+    // Direct path (kernel.cpp:335-357).  Every work-item of the reference computes the same
+    // source->mic query and the host keeps the first ray's copy (rayverb.cpp:667-673); only
+    // global ray 0 needs to do it.
+    if (do_images && P.ray_offset + ray == 0) {
+        if (point_visible(acc, source, mic_reflection, c))
+            add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE, volume, 0u);
+    }
+
+    uint32_t index = 0;
+    for (; index != P.nrefl; ++index) {
+        float tclosest;
+        uint32_t prim;
+        if (!acc.nearest(ray_pos, ray_dir, tclosest, prim, c)) break;           // :363-375
+
+        if (do_images && index < RVB_NUM_IMAGE_SOURCE - 1) {                     // :379-457
+            TriVerts current = load_verts(P.verts, prim);
+            for (uint32_t k = 0; k != index; ++k) {                              // mirror_verts
+                current.v0 = mirror_point(current.v0, prev[k]);
+                current.v1 = mirror_point(current.v1, prev[k]);
+                current.v2 = mirror_point(current.v2, prev[k]);
+            }
+            prev[index] = current;
+            mic_reflection = mirror_point(mic_reflection, current);
+            const f3 DIR = normalize(mic_reflection - source);
+            bool intersects = true;
+            f3 prevI = source;
+            for (uint32_t k = 0; k != index + 1 && intersects; ++k) {
+                const float TO = mt_intersect_verts(prev[k], source, DIR);
+                if (TO <= RVB_EPSILON) { intersects = false; break; }
+                f3 Pt = madd(source, DIR, TO);
+                for (int l = (int)k - 1; l != -1; --l) Pt = mirror_point(Pt, prev[l]);
+                f3 idir = normalize(Pt - prevI);
+                float ti; uint32_t pi;
+                bool hit = acc.nearest(prevI, idir, ti, pi, c);
+                if (!hit) ti = 0.0f;                                              // Intersection{0,0,false}
+                f3 Q = madd(prevI, idir, ti);
+                intersects = hit
+                    && (__fsub_rn(Q.x, RVB_EPSILON) < Pt.x) && (__fsub_rn(Q.y, RVB_EPSILON) < Pt.y) && (__fsub_rn(Q.z, RVB_EPSILON) < Pt.z)
+                    && (Pt.x < __fadd_rn(Q.x, RVB_EPSILON)) && (Pt.y < __fadd_rn(Q.y, RVB_EPSILON)) && (Pt.z < __fadd_rn(Q.z, RVB_EPSILON));
+                prevI = Pt;
+            }
+            if (intersects) intersects = point_visible(acc, prevI, mic, c);
+            if (intersects)   // pre-bounce volume
+                add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE + index + 1, volume, prim + 1u);
+        }
+
+        const f3 X = madd(ray_pos, ray_dir, tclosest);                          // :459
+        const float newDist = __fadd_rn(distance, tclosest);
+        const float4 nrm4 = __ldg(P.nrm + prim);
+        const f3 normal = mk3(nrm4);
+        const rvb_surface *surf = P.surfaces + __float_as_uint(nrm4.w);
+        float newVol[RVB_NBANDS];
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) newVol[b] = __fmul_rn(-volume[b], __ldg(&surf->specular.s[b]));   // :461
+
+        const bool vis = point_visible(acc, X, mic, c);                          // :463
+        const float DIST = vis ? __fadd_rn(newDist, length(mic - X)) : 0.0f;     // :471
+        const float DIFF = fabsf(dot(normal, ray_dir));                          // :478
+        float out[RVB_NBANDS];
+        bool any = false;
+        if (vis) {
+            float att[RVB_NBANDS];
+            air_attenuation(DIST, P.air, att);
+#pragma unroll
+            for (int b = 0; b < RVB_NBANDS; ++b) {
+                out[b] = __fmul_rn(__fmul_rn(__fmul_rn(newVol[b], att[b]), __ldg(&surf->diffuse.s[b])), DIFF);
+                any |= (out[b] != 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < RVB_NBANDS; ++b) out[b] = 0.0f;
+        }
+        const float time = __fmul_rn(RVB_SECONDS_PER_METER, DIST);
+        const size_t slot = (size_t)index * P.nrays + ray;
+        P.volA[slot] = make_float4(out[0], out[1], out[2], out[3]);
+        P.volB[slot] = make_float4(out[4], out[5], out[6], out[7]);
+        P.pt[slot] = make_float4(X.x, X.y, X.z, time);
+        P.tkey[slot] = any ? time : -1.0f;
+        if (P.hit) P.hit[slot] = prim;
+
+        ray_dir = reflect(normal, ray_dir);                                      // :492-499
+        ray_pos = X;
+        distance = newDist;
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) volume[b] = newVol[b];
+    }
+    c.bounces += index;
+    if (P.count) P.count[ray] = index;
+    // a ray that left the mesh keeps zero impulses in its remaining slots (rayverb.cpp:601-603)
+    for (; index != P.nrefl; ++index) {
+        const size_t slot = (size_t)index * P.nrays + ray;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        P.volA[slot] = z; P.volB[slot] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
+        if (P.hit) P.hit[slot] = RVB_NONE;
+    }
+}
+
+__device__ __forceinline__ void flush_counters(const TraceParams &P, const Counters &c)
+{
+    // warp-aggregate, then one atomic per warp (integer adds: order-independent)
+    unsigned long long q = c.queries, t = c.tri, b = c.box, n = c.bounces;
+    for (int o = 16; o; o >>= 1) {
+        q += __shfl_down_sync(0xffffffffu, q, o); t += __shfl_down_sync(0xffffffffu, t, o);
+        b += __shfl_down_sync(0xffffffffu, b, o); n += __shfl_down_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(P.counters + 0, q); atomicAdd(P.counters + 1, t);
+        atomicAdd(P.counters + 2, b); atomicAdd(P.counters + 3, n);
+    }
+}
+
+__global__ void __launch_bounds__(256) trace_bruteforce_kernel(const TraceParams P)
+{
+    extern __shared__ float4 s_tri[];
+    for (uint32_t i = threadIdx.x; i < 3 * P.T; i += blockDim.x) s_tri[i] = P.tri[i];
+    __syncthreads();
+    BruteSmem acc{s_tri, P.T};
+    Counters c;
+    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x)
+        trace_ray(acc, P, ray, c);
+    flush_counters(P, c);
+}
+
+__global__ void __launch_bounds__(128) trace_bvh_kernel(const TraceParams P)
+{
+    BvhAccel acc{P.nodes, P.tri_sorted, P.order};
+    Counters c;
+    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x)
+        trace_ray(acc, P, ray, c);
+    flush_counters(P, c);
+}
+
+int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB, float4 *d_cand_pt,
+                 uint32_t *d_cand_idx)
+{
+    Scene *sc = tr->scene;
+    cudaStream_t st = lib_stream();
+    TraceParams P{};
+    P.verts = sc->d_verts; P.tri = sc->d_tri; P.nrm = sc->d_nrm; P.surfaces = sc->d_surfaces; P.T = sc->T;
+    P.nodes = sc->d_nodes; P.tri_sorted = sc->d_tri_sorted; P.order = sc->d_order;
+    P.dirs = d_dirs; P.nrays = (uint32_t)tr->nrays; P.nrefl = (uint32_t)tr->nrefl; P.ray_offset = tr->ray_offset;
+    for (int i = 0; i < 3; ++i) { P.mic[i] = tr->mic[i]; P.src[i] = tr->src[i]; }
+    // AIR_COEFFICIENT: doubles narrowed to float (rayverb.cpp:632-641)
+    const double air[RVB_NBANDS] = {0.001 * -0.1, 0.001 * -0.2, 0.001 * -0.5, 0.001 * -1.1,
+                                    0.001 * -2.7, 0.001 * -9.4, 0.001 * -29.0, 0.001 * -60.0};
+    for (int b = 0; b < RVB_NBANDS; ++b) P.air[b] = (float)air[b];
+    P.volA = tr->d_volA; P.volB = tr->d_volB; P.pt = tr->d_pt; P.tkey = tr->d_tkey;
+    P.hit = tr->d_hit; P.count = tr->d_count;
+    P.cand_volA = d_cand_volA; P.cand_volB = d_cand_volB; P.cand_pt = d_cand_pt; P.cand_idx = d_cand_idx;
+    P.flags = tr->flags;
+    unsigned long long *d_counters = nullptr;
+    RVB_TRY(dev_alloc(&d_counters, 4));
+    RVB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), st));
+    P.counters = d_counters;
+
+    cudaDeviceProp prop;
+    int dev;
+    RVB_CUDA(cudaGetDevice(&dev));
+    RVB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    cudaEvent_t e0, e1;
+    RVB_CUDA(cudaEventCreate(&e0));
+    RVB_CUDA(cudaEventCreate(&e1));
+    RVB_CUDA(cudaEventRecord(e0, st));
+    if (tr->nrays > 0) {
+        if (sc->accel == RVB_ACCEL_BRUTE_FORCE) {
+            const int block = 256;
+            size_t smem = (size_t)3 * sc->T * sizeof(float4);
+            RVB_CUDA(cudaFuncSetAttribute(trace_bruteforce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_bruteforce_kernel, block, smem));
+            if (per_sm < 1) return fail(RVB_ERR_INVALID, "scene does not fit in shared memory for the brute-force kernel");
+            size_t want = (tr->nrays + block - 1) / block;
+            size_t grid = std::min(want, (size_t)per_sm * prop.multiProcessorCount);
+            trace_bruteforce_kernel<<<(unsigned)grid, block, smem, st>>>(P);
+        } else {
+            const int block = 128;
+            int per_sm = 0;
+            RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_bvh_kernel, block, 0));
+            size_t want = (tr->nrays + block - 1) / block;
+            size_t grid = std::min(want, (size_t)std::max(per_sm, 1) * prop.multiProcessorCount);
+            trace_bvh_kernel<<<(unsigned)grid, block, 0, st>>>(P);
+        }
+        RVB_CUDA(cudaGetLastError());
+    }
+    RVB_CUDA(cudaEventRecord(e1, st));
+    unsigned long long h[4];
+    RVB_CUDA(cudaMemcpyAsync(h, d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_free(d_counters);
+    tr->stats.queries = h[0]; tr->stats.tri_tests = h[1]; tr->stats.box_tests = h[2]; tr->stats.bounces = h[3];
+    tr->stats.trace_kernel_ms = ms;
+    return RVB_OK;
+}
+
+}  // namespace rvb

@@ -1,0 +1,286 @@
+// C ABI around the bounce kernel: Raytracer::raytrace / getRawDiffuse / getRawImages / getAllRaw
+// (rayverb/rayverb.cpp:538-714).
+//
+// Unlike the reference, which loops over groups of 4096 rays with ~64 MiB of blocking
+// host<->device traffic per group (rayverb.cpp:587-684), the whole ray set is traced in one
+// launch and the results stay on the device behind the rvb_trace handle; the host copies below
+// exist for the drop-in getRaw* accessors and the parity tests.
+#include <algorithm>
+#include <map>
+
+#include "rvb_internal.cuh"
+
+namespace rvb {
+
+// bounce-major SoA -> ray-major AoS (Impulse, clstructs.h:36-42) for a range of rays
+__global__ void export_diffuse_kernel(const float4 *volA, const float4 *volB, const float4 *pt, uint32_t nrays, uint32_t nrefl,
+                                      uint32_t ray0, uint32_t nr, rvb_impulse *out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over nr*nrefl, bounce fastest
+    if (i >= (size_t)nr * nrefl) return;
+    uint32_t r = (uint32_t)(i / nrefl), b = (uint32_t)(i % nrefl);
+    size_t slot = (size_t)b * nrays + ray0 + r;
+    float4 a = volA[slot], c = volB[slot], p = pt[slot];
+    float4 *o = reinterpret_cast<float4 *>(out + i);
+    o[0] = a; o[1] = c; o[2] = make_float4(p.x, p.y, p.z, 0.f); o[3] = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+
+__global__ void export_images_kernel(const float4 *volA, const float4 *volB, const float4 *pt, uint32_t n, rvb_impulse *out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pt[i];
+    float4 *o = reinterpret_cast<float4 *>(out + i);
+    o[0] = volA[i]; o[1] = volB[i]; o[2] = make_float4(p.x, p.y, p.z, 0.f); o[3] = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+
+__global__ void import_images_kernel(const rvb_impulse *in, uint32_t n, float4 *volA, float4 *volB, float4 *pt)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 *s = reinterpret_cast<const float4 *>(in + i);
+    float4 p = s[2];
+    volA[i] = s[0]; volB[i] = s[1]; pt[i] = make_float4(p.x, p.y, p.z, s[3].x);
+}
+
+__global__ void export_hits_kernel(const uint32_t *hit, uint32_t nrays, uint32_t nrefl, uint32_t *out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nrays * nrefl) return;
+    uint32_t r = (uint32_t)(i / nrefl), b = (uint32_t)(i % nrefl);
+    out[i] = hit[(size_t)b * nrays + r];
+}
+
+static int trace_run_impl(rvb_scene *scene, const float mic[3], const float source[3], const float4 *d_dirs, size_t nrays,
+                          size_t nrefl, uint64_t ray_offset, unsigned flags, rvb_trace **out)
+{
+    cudaStream_t st = lib_stream();
+    rvb_trace *tr = new rvb_trace();
+    tr->scene = scene; tr->nrays = nrays; tr->nrefl = nrefl; tr->ray_offset = ray_offset; tr->flags = flags;
+    for (int i = 0; i < 3; ++i) { tr->mic[i] = mic[i]; tr->src[i] = source[i]; }
+    tr->stats.nrays = nrays; tr->stats.nreflections = nrefl;
+    const size_t nslots = nrays * nrefl;
+    int rc = RVB_OK;
+    float4 *cvA = nullptr, *cvB = nullptr, *cpt = nullptr;
+    uint32_t *cidx = nullptr;
+    const bool images = !(flags & RVB_TRACE_NO_IMAGES);
+    const size_t ncand = images ? nrays * RVB_NUM_IMAGE_SOURCE : 0;
+    auto bail = [&](int code) { dev_free(cvA); dev_free(cvB); dev_free(cpt); dev_free(cidx); rvb_trace_destroy(tr); return code; };
+    if ((rc = dev_alloc(&tr->d_volA, nslots)) || (rc = dev_alloc(&tr->d_volB, nslots)) || (rc = dev_alloc(&tr->d_pt, nslots)) ||
+        (rc = dev_alloc(&tr->d_tkey, nslots)))
+        return bail(rc);
+    if (flags & RVB_TRACE_DEBUG) {
+        if ((rc = dev_alloc(&tr->d_hit, nslots)) || (rc = dev_alloc(&tr->d_count, nrays))) return bail(rc);
+    }
+    if (images && ncand) {
+        if ((rc = dev_alloc(&cvA, ncand)) || (rc = dev_alloc(&cvB, ncand)) || (rc = dev_alloc(&cpt, ncand)) ||
+            (rc = dev_alloc(&cidx, ncand)))
+            return bail(rc);
+        cudaMemsetAsync(cidx, 0, ncand * sizeof(uint32_t), st);
+        // slot 0 of ray 0 is read even if the direct path is occluded (key {0} is unconditional)
+        cudaMemsetAsync(cvA, 0, sizeof(float4), st); cudaMemsetAsync(cvB, 0, sizeof(float4), st); cudaMemsetAsync(cpt, 0, sizeof(float4), st);
+    }
+    if ((rc = trace_launch(tr, d_dirs, cvA, cvB, cpt, cidx))) return bail(rc);
+    if (images && ncand) {
+        if ((rc = images_dedupe(tr, cvA, cvB, cpt, cidx))) return bail(rc);
+    }
+    dev_free(cvA); dev_free(cvB); dev_free(cpt); dev_free(cidx);
+    *out = tr;
+    return RVB_OK;
+}
+
+}  // namespace rvb
+
+using namespace rvb;
+
+extern "C" {
+
+int rvb_trace_run_device(rvb_scene *scene, const float mic[3], const float source[3], const rvb_float3 *d_directions,
+                         size_t nrays, size_t nreflections, uint64_t ray_offset, unsigned flags, rvb_trace **out)
+{
+    if (!out) return fail(RVB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!scene || !mic || !source || (!d_directions && nrays)) return fail(RVB_ERR_INVALID, "null argument");
+    if (nrays >= (1ull << 32) || nreflections >= (1ull << 32)) return fail(RVB_ERR_UNSUPPORTED, "ray or reflection count too large");
+    RVB_CUDA(cudaSetDevice(scene->device));
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    cudaEvent_t e0, e1;
+    RVB_CUDA(cudaEventCreate(&e0)); RVB_CUDA(cudaEventCreate(&e1));
+    RVB_CUDA(cudaEventRecord(e0, st));
+    int rc = trace_run_impl(scene, mic, source, reinterpret_cast<const float4 *>(d_directions), nrays, nreflections, ray_offset, flags, out);
+    if (rc == RVB_OK) {
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&(*out)->stats.total_ms, e0, e1);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+int rvb_trace_run(rvb_scene *scene, const float mic[3], const float source[3], const rvb_float3 *directions, size_t nrays,
+                  size_t nreflections, uint64_t ray_offset, unsigned flags, rvb_trace **out)
+{
+    if (!out) return fail(RVB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!scene || !mic || !source || (!directions && nrays)) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_CUDA(cudaSetDevice(scene->device));
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    cudaEvent_t e0, e1;
+    RVB_CUDA(cudaEventCreate(&e0)); RVB_CUDA(cudaEventCreate(&e1));
+    RVB_CUDA(cudaEventRecord(e0, st));
+    float4 *d_dirs = nullptr;
+    RVB_TRY(dev_alloc(&d_dirs, nrays));
+    if (nrays) RVB_CUDA(cudaMemcpyAsync(d_dirs, directions, nrays * sizeof(rvb_float3), cudaMemcpyHostToDevice, st));
+    int rc = rvb_trace_run_device(scene, mic, source, reinterpret_cast<const rvb_float3 *>(d_dirs), nrays, nreflections, ray_offset, flags, out);
+    dev_free(d_dirs);
+    if (rc == RVB_OK) {
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&(*out)->stats.total_ms, e0, e1);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+int rvb_trace_destroy(rvb_trace *tr)
+{
+    if (!tr) return RVB_OK;
+    if (tr->scene) cudaSetDevice(tr->scene->device);
+    dev_free(tr->d_volA); dev_free(tr->d_volB); dev_free(tr->d_pt); dev_free(tr->d_tkey);
+    dev_free(tr->d_hit); dev_free(tr->d_count);
+    dev_free(tr->d_img_volA); dev_free(tr->d_img_volB); dev_free(tr->d_img_pt);
+    delete tr;
+    return RVB_OK;
+}
+
+int rvb_trace_diffuse_count(const rvb_trace *tr, size_t *count)
+{
+    if (!tr || !count) return fail(RVB_ERR_INVALID, "null argument");
+    *count = tr->nrays * tr->nrefl;
+    return RVB_OK;
+}
+
+int rvb_trace_copy_diffuse(const rvb_trace *tr, rvb_impulse *out)
+{
+    if (!tr || !out) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_CUDA(cudaSetDevice(tr->scene->device));
+    cudaStream_t st = lib_stream();
+    if (tr->nrays == 0 || tr->nrefl == 0) return RVB_OK;
+    // stage through a bounded AoS buffer (<= 256 MiB)
+    size_t rays_per_chunk = std::max<size_t>(1, (256ull << 20) / (tr->nrefl * sizeof(rvb_impulse)));
+    rays_per_chunk = std::min(rays_per_chunk, tr->nrays);
+    rvb_impulse *d_stage = nullptr;
+    RVB_TRY(dev_alloc(&d_stage, rays_per_chunk * tr->nrefl));
+    for (size_t r0 = 0; r0 < tr->nrays; r0 += rays_per_chunk) {
+        size_t nr = std::min(rays_per_chunk, tr->nrays - r0);
+        size_t n = nr * tr->nrefl;
+        export_diffuse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_volA, tr->d_volB, tr->d_pt, (uint32_t)tr->nrays,
+                                                                           (uint32_t)tr->nrefl, (uint32_t)r0, (uint32_t)nr, d_stage);
+        RVB_CUDA(cudaMemcpyAsync(out + r0 * tr->nrefl, d_stage, n * sizeof(rvb_impulse), cudaMemcpyDeviceToHost, st));
+        RVB_CUDA(cudaStreamSynchronize(st));
+    }
+    dev_free(d_stage);
+    return RVB_OK;
+}
+
+int rvb_trace_image_count(const rvb_trace *tr, int remove_direct, size_t *count)
+{
+    if (!tr || !count) return fail(RVB_ERR_INVALID, "null argument");
+    *count = tr->n_images - ((remove_direct && tr->first_is_direct) ? 1 : 0);   // temp.erase({0}), rayverb.cpp:695-696
+    return RVB_OK;
+}
+
+int rvb_trace_copy_images(const rvb_trace *tr, int remove_direct, rvb_impulse *out, uint32_t *keys, int32_t *key_lengths)
+{
+    if (!tr) return fail(RVB_ERR_INVALID, "null argument");
+    const size_t skip = (remove_direct && tr->first_is_direct) ? 1 : 0;
+    const size_t n = tr->n_images - skip;
+    if (n == 0) return RVB_OK;
+    RVB_CUDA(cudaSetDevice(tr->scene->device));
+    cudaStream_t st = lib_stream();
+    if (out) {
+        rvb_impulse *d_stage = nullptr;
+        RVB_TRY(dev_alloc(&d_stage, n));
+        export_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_img_volA + skip, tr->d_img_volB + skip, tr->d_img_pt + skip, (uint32_t)n, d_stage);
+        RVB_CUDA(cudaMemcpyAsync(out, d_stage, n * sizeof(rvb_impulse), cudaMemcpyDeviceToHost, st));
+        RVB_CUDA(cudaStreamSynchronize(st));
+        dev_free(d_stage);
+    }
+    if (keys && !tr->img_keys.empty()) std::copy(tr->img_keys.begin() + skip * RVB_NUM_IMAGE_SOURCE, tr->img_keys.end(), keys);
+    if (key_lengths && !tr->img_len.empty()) std::copy(tr->img_len.begin() + skip, tr->img_len.end(), key_lengths);
+    return RVB_OK;
+}
+
+int rvb_trace_set_images(rvb_trace *tr, const rvb_impulse *images, size_t n)
+{
+    if (!tr || (!images && n)) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_CUDA(cudaSetDevice(tr->scene->device));
+    cudaStream_t st = lib_stream();
+    dev_free(tr->d_img_volA); dev_free(tr->d_img_volB); dev_free(tr->d_img_pt);
+    tr->n_images = n; tr->img_keys.clear(); tr->img_len.clear(); tr->first_is_direct = false;
+    if (n == 0) return RVB_OK;
+    rvb_impulse *d_stage = nullptr;
+    RVB_TRY(dev_alloc(&d_stage, n));
+    RVB_TRY(dev_alloc(&tr->d_img_volA, n)); RVB_TRY(dev_alloc(&tr->d_img_volB, n)); RVB_TRY(dev_alloc(&tr->d_img_pt, n));
+    RVB_CUDA(cudaMemcpyAsync(d_stage, images, n * sizeof(rvb_impulse), cudaMemcpyHostToDevice, st));
+    import_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_stage, (uint32_t)n, tr->d_img_volA, tr->d_img_volB, tr->d_img_pt);
+    RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_stage);
+    return RVB_OK;
+}
+
+// Cross-shard merge on the host: the lists are tiny (unique image sources), and the rule is the
+// reference's own map insert (rayverb.cpp:669-673): first occurrence of a key wins.
+int rvb_images_merge(const rvb_impulse *images, const uint32_t *keys, const int32_t *key_lengths, size_t n, rvb_impulse *out,
+                     uint32_t *out_keys, int32_t *out_key_lengths, size_t *nout)
+{
+    if (!nout || (n && (!images || !keys || !key_lengths || !out))) return fail(RVB_ERR_INVALID, "null argument");
+    std::map<std::vector<uint32_t>, size_t> tally;
+    for (size_t i = 0; i < n; ++i) {
+        std::vector<uint32_t> k(keys + i * RVB_NUM_IMAGE_SOURCE, keys + i * RVB_NUM_IMAGE_SOURCE + key_lengths[i]);
+        tally.emplace(std::move(k), i);   // emplace keeps the first
+    }
+    size_t m = 0;
+    for (const auto &kv : tally) {
+        out[m] = images[kv.second];
+        if (out_keys) {
+            for (int j = 0; j < RVB_NUM_IMAGE_SOURCE; ++j)
+                out_keys[m * RVB_NUM_IMAGE_SOURCE + j] = j < (int)kv.first.size() ? kv.first[j] : 0u;
+        }
+        if (out_key_lengths) out_key_lengths[m] = (int32_t)kv.first.size();
+        ++m;
+    }
+    *nout = m;
+    return RVB_OK;
+}
+
+int rvb_trace_copy_debug(const rvb_trace *tr, uint32_t *hit_triangle, uint32_t *reflection_count)
+{
+    if (!tr) return fail(RVB_ERR_INVALID, "null argument");
+    if (!tr->d_hit || !tr->d_count) return fail(RVB_ERR_INVALID, "trace was not run with RVB_TRACE_DEBUG");
+    RVB_CUDA(cudaSetDevice(tr->scene->device));
+    cudaStream_t st = lib_stream();
+    const size_t n = tr->nrays * tr->nrefl;
+    if (hit_triangle && n) {
+        uint32_t *d_stage = nullptr;
+        RVB_TRY(dev_alloc(&d_stage, n));
+        export_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_hit, (uint32_t)tr->nrays, (uint32_t)tr->nrefl, d_stage);
+        RVB_CUDA(cudaMemcpyAsync(hit_triangle, d_stage, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        RVB_CUDA(cudaStreamSynchronize(st));
+        dev_free(d_stage);
+    }
+    if (reflection_count && tr->nrays) {
+        RVB_CUDA(cudaMemcpyAsync(reflection_count, tr->d_count, tr->nrays * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        RVB_CUDA(cudaStreamSynchronize(st));
+    }
+    return RVB_OK;
+}
+
+int rvb_trace_get_stats(const rvb_trace *tr, rvb_trace_stats *stats)
+{
+    if (!tr || !stats) return fail(RVB_ERR_INVALID, "null argument");
+    *stats = tr->stats;
+    return RVB_OK;
+}
+
+}  // extern "C"
