@@ -62,6 +62,13 @@ const char *rvb_last_error(void);
 int rvb_device_count(int *count);
 int rvb_set_device(int device);          /* device used by the calling thread's later calls */
 int rvb_version(void);
+/* Run this thread's later calls on the caller's CUDA stream (e.g. torch's current stream) instead
+ * of the library's own; use = 0 switches back.  The reference has one in-order queue per object
+ * (rayverb.cpp:190-191). */
+int rvb_set_stream(void *cuda_stream, int use);
+/* number of kernels this library has launched so far in the process (CUB's sort/select passes
+ * are not counted) */
+unsigned long long rvb_launch_count(void);
 
 /* ---- scene: Raytracer::Raytracer (rayverb.h:142-148, rayverb.cpp:242-293) -------------------- */
 int rvb_scene_create(const rvb_triangle *triangles, size_t ntriangles,

@@ -95,14 +95,14 @@ int rvb_attenuate_speaker(const rvb_impulse *in, size_t n, const float mic[3], c
     // normalize(speaker.direction) once, with the device's own arithmetic (kernel.cpp:511)
     float *d_n = nullptr, h_n[3];
     RVB_TRY(dev_alloc(&d_n, 3));
-    normalize_dir_kernel<<<1, 1, 0, st>>>(mk3(speaker->direction.s[0], speaker->direction.s[1], speaker->direction.s[2]), d_n);
+    note_launch(), normalize_dir_kernel<<<1, 1, 0, st>>>(mk3(speaker->direction.s[0], speaker->direction.s[1], speaker->direction.s[2]), d_n);
     RVB_CUDA(cudaMemcpyAsync(h_n, d_n, sizeof h_n, cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
     dev_free(d_n);
     f3 m = {mic[0], mic[1], mic[2]}, sd = {h_n[0], h_n[1], h_n[2]};
     float coef = speaker->coefficient;
     return run_chunked(in, n, out, [&](const rvb_impulse *di, size_t cnt, rvb_attenuated_impulse *dout, cudaStream_t s) {
-        attenuate_speaker_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(di, cnt, m, sd, coef, dout);
+        note_launch(), attenuate_speaker_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(di, cnt, m, sd, coef, dout);
     });
 }
 
@@ -122,7 +122,7 @@ int rvb_attenuate_hrtf(const rvb_impulse *in, size_t n, const float mic[3], cons
     RVB_CUDA(cudaMemcpyAsync(d_table, table_one_ear, cells * sizeof(rvb_float8), cudaMemcpyHostToDevice, st));
     f3 m = {mic[0], mic[1], mic[2]}, f = {facing[0], facing[1], facing[2]}, u = {up[0], up[1], up[2]};
     int rc = run_chunked(in, n, out, [&](const rvb_impulse *di, size_t cnt, rvb_attenuated_impulse *dout, cudaStream_t s) {
-        attenuate_hrtf_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(di, cnt, m, d_table, f, u, (unsigned long long)channel, dout);
+        note_launch(), attenuate_hrtf_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(di, cnt, m, d_table, f, u, (unsigned long long)channel, dout);
     });
     dev_free(d_table);
     return rc;

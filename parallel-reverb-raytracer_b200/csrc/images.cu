@@ -101,7 +101,7 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     uint32_t *d_perm[2] = {nullptr, nullptr}, *d_keys[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_perm[i], n)); RVB_TRY(dev_alloc(&d_keys[i], n)); }
     const unsigned blk = 256, grd = (n + blk - 1) / blk;
-    iota_kernel<<<grd, blk, 0, st>>>(d_perm[0], n);
+    note_launch(), iota_kernel<<<grd, blk, 0, st>>>(d_perm[0], n);
     int end_bit = 1;
     while ((1ull << end_bit) < (unsigned long long)tr->scene->T + 2ull) ++end_bit;
     size_t sort_bytes = 0;
@@ -111,7 +111,7 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     int cur = 0;
     const uint32_t last_col = (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl);
     for (uint32_t j = last_col; j >= 1; --j) {   // LSD over key columns; column 0 is constant
-        col_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, j, d_keys[0]);
+        note_launch(), col_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, j, d_keys[0]);
         RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_bytes, d_keys[0], d_keys[1], d_perm[cur], d_perm[cur ^ 1],
                                                  (int)n, 0, end_bit, st));
         cur ^= 1;
@@ -120,7 +120,7 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
 
     uint8_t *d_head = nullptr;
     RVB_TRY(dev_alloc(&d_head, n));
-    head_flags_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, d_head);
+    note_launch(), head_flags_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, d_head);
     uint32_t *d_upos = d_keys[0], *d_m = d_nsel;
     size_t fl_bytes = 0;
     RVB_CUDA(cub::DeviceSelect::Flagged(nullptr, fl_bytes, it, d_head, d_upos, d_m, (int)n, st));
@@ -139,7 +139,7 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     int32_t *d_olen = nullptr;
     RVB_TRY(dev_alloc(&d_okeys, (size_t)m * RVB_NUM_IMAGE_SOURCE));
     RVB_TRY(dev_alloc(&d_olen, m));
-    gather_unique_kernel<<<(m + blk - 1) / blk, blk, 0, st>>>(cidx, d_sel, d_perm[cur], d_upos, m, cvA, cvB, cpt, tr->d_img_volA,
+    note_launch(), gather_unique_kernel<<<(m + blk - 1) / blk, blk, 0, st>>>(cidx, d_sel, d_perm[cur], d_upos, m, cvA, cvB, cpt, tr->d_img_volA,
                                                               tr->d_img_volB, tr->d_img_pt, d_okeys, d_olen);
     RVB_CUDA(cudaGetLastError());
     tr->img_keys.resize((size_t)m * RVB_NUM_IMAGE_SOURCE);

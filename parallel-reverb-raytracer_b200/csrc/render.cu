@@ -21,11 +21,12 @@
 namespace rvb {
 
 #define RVB_MAX_GROUP 4   // speaker channels reduced per pass over a bin
+#define RVB_NO_IMPULSE 0xffffffffu
 
 // The impulse list seen by the attenuators: diffuse slots first, then image sources
 // (getAllRaw, rayverb.cpp:708-714).
 struct Source {
-    const float4 *volA, *volB, *pt;
+    const float4 *vol, *pt;          // vol: 2 x float4 per impulse (one 32-B sector)
     const float *tkey;               // time if any(volume != 0) else -1
     uint32_t n_diffuse;
     const float4 *ivolA, *ivolB, *ipt;
@@ -43,7 +44,7 @@ struct Source {
     __device__ __forceinline__ float4 pos_time(uint32_t i) const { return i < n_diffuse ? pt[i] : ipt[i - n_diffuse]; }
     __device__ __forceinline__ void volume(uint32_t i, float4 &a, float4 &b) const
     {
-        if (i < n_diffuse) { a = volA[i]; b = volB[i]; } else { a = ivolA[i - n_diffuse]; b = ivolB[i - n_diffuse]; }
+        if (i < n_diffuse) { a = vol[2 * (size_t)i]; b = vol[2 * (size_t)i + 1]; } else { a = ivolA[i - n_diffuse]; b = ivolB[i - n_diffuse]; }
     }
 };
 
@@ -124,15 +125,50 @@ __global__ void bounds_kernel(const uint32_t *keys, uint32_t n, uint32_t L, uint
     }
 }
 
-// One warp per bin: lane l takes entries begin+l, begin+l+32, ... in order, then a fixed
-// xor-shuffle tree combines the 32 partial sums.  hist layout: [channel][band][L].
+// One warp per bin: lane l takes entries begin+l, begin+l+32, ... in order (four gathers in
+// flight per lane), then a fixed xor-shuffle tree combines the 32 partial sums.
+// hist layout: [channel][band][L].
+template <int MODEL, bool NEED_POS>
+__device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &C, uint32_t i, float4 va, float4 vb,
+                                               float (&acc)[RVB_MAX_GROUP][RVB_NBANDS])
+{
+    const float v[RVB_NBANDS] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    if (MODEL == 0) {
+        f3 pos = mk3(0.f, 0.f, 0.f);
+        if (NEED_POS) pos = mk3(S.pos_time(i));
+#pragma unroll
+        for (int c = 0; c < RVB_MAX_GROUP; ++c) {
+            if (c < C.nch) {
+                // coefficient 0 (omni): (1 - 0) + 0 * d == 1 exactly for every finite d, so the
+                // position is not needed
+                const float g = NEED_POS ? speaker_gain(C.mic, pos, C.sdir[c], C.coef[c]) : 1.0f;
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[c][b] = __fadd_rn(acc[c][b], __fmul_rn(v[b], g));
+            }
+        }
+    } else if (MODEL == 1) {
+        const f3 pos = mk3(S.pos_time(i));
+        const long idx = hrtf_index(C.pointing, C.up, normalize(pos - C.mic));
+        const float4 ga = __ldg(C.table + 2 * idx), gb = __ldg(C.table + 2 * idx + 1);
+        const float g[RVB_NBANDS] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], __fmul_rn(v[b], g[b]));
+    } else {
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], v[b]);
+    }
+}
+
+template <int MODEL, bool NEED_POS>
 __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *vals, const uint32_t *seg_begin,
                                                      const uint32_t *seg_end, uint32_t L, float *hist, size_t chan_stride)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t bin = warp; bin < L; bin += nwarps) {
+    // bins are handed out from the END of the response first: late bins hold the most impulses
+    for (uint32_t w = warp; w < L; w += nwarps) {
+        const uint32_t bin = L - 1 - w;
         const uint32_t b0 = seg_begin[bin], b1 = seg_end[bin];
         if (b0 == b1) continue;   // warp-uniform
         float acc[RVB_MAX_GROUP][RVB_NBANDS];
@@ -140,32 +176,17 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
         for (int c = 0; c < RVB_MAX_GROUP; ++c)
 #pragma unroll
             for (int b = 0; b < RVB_NBANDS; ++b) acc[c][b] = 0.0f;
-        for (uint32_t j = b0 + lane; j < b1; j += 32) {
-            const uint32_t i = vals[j];
-            float4 va, vb;
-            S.volume(i, va, vb);
-            const float v[RVB_NBANDS] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-            if (C.model == 0) {
-                const f3 pos = mk3(S.pos_time(i));
+        for (uint32_t j = b0 + lane; j < b1; j += 128) {
+            uint32_t idx[4];
+            float4 va[4], vb[4];
 #pragma unroll
-                for (int c = 0; c < RVB_MAX_GROUP; ++c) {
-                    if (c < C.nch) {
-                        const float g = speaker_gain(C.mic, pos, C.sdir[c], C.coef[c]);
+            for (int u = 0; u < 4; ++u) idx[u] = (j + 32 * u < b1) ? vals[j + 32 * u] : RVB_NO_IMPULSE;
 #pragma unroll
-                        for (int b = 0; b < RVB_NBANDS; ++b) acc[c][b] = __fadd_rn(acc[c][b], __fmul_rn(v[b], g));
-                    }
-                }
-            } else if (C.model == 1) {
-                const f3 pos = mk3(S.pos_time(i));
-                const long idx = hrtf_index(C.pointing, C.up, normalize(pos - C.mic));
-                const float4 ga = __ldg(C.table + 2 * idx), gb = __ldg(C.table + 2 * idx + 1);
-                const float g[RVB_NBANDS] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            for (int u = 0; u < 4; ++u)
+                if (idx[u] != RVB_NO_IMPULSE) S.volume(idx[u], va[u], vb[u]);
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], __fmul_rn(v[b], g[b]));
-            } else {
-#pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], v[b]);
-            }
+            for (int u = 0; u < 4; ++u)
+                if (idx[u] != RVB_NO_IMPULSE) accumulate_one<MODEL, NEED_POS>(S, C, idx[u], va[u], vb[u], acc);
         }
 #pragma unroll
         for (int c = 0; c < RVB_MAX_GROUP; ++c) {
@@ -185,42 +206,96 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
 struct BiquadCoef { double b0, b1, b2, a1, a2; };
 struct RowFilter { int npass; BiquadCoef q[2]; };   // LR: q[0] lopass.twopass, q[1] hipass.twopass
 
-#define RVB_FILTER_TILE 1024
-// One warp per (channel, band) row.  The row is streamed through shared memory in tiles (all
-// lanes load/store, coalesced); lane 0 runs the recurrence.  `twopass` (forward, reverse,
-// forward, reverse) is run as a forward sweep followed by a backward sweep over the same data.
-__global__ void __launch_bounds__(32) iir_kernel(float *data, const uint32_t *row_off, const uint32_t *row_len, const RowFilter *filters,
-                                                 int mode /* 1 onepass, 2 twopass per biquad */)
+#define RVB_IIR_THREADS 256
+#define RVB_IIR_CHUNK 64
+#define RVB_IIR_TILE (RVB_IIR_THREADS * RVB_IIR_CHUNK)
+
+// Biquad::onepass (filters.cpp:156-168) over one chunk held in shared memory.
+// STORE = false: only the end state is wanted.
+template <bool STORE>
+__device__ __forceinline__ void biquad_chunk(const BiquadCoef &q, float *x, double &z1, double &z2)
 {
-    __shared__ float tile[RVB_FILTER_TILE];
-    const uint32_t row = blockIdx.x;
+#pragma unroll 8
+    for (int k = 0; k < RVB_IIR_CHUNK; ++k) {
+        const double in = (double)x[k];
+        const double out = __dadd_rn(__dmul_rn(in, q.b0), z1);
+        z1 = __dsub_rn(__dadd_rn(__dmul_rn(in, q.b1), z2), __dmul_rn(q.a1, out));
+        z2 = __dsub_rn(__dmul_rn(in, q.b2), __dmul_rn(q.a2, out));
+        if (STORE) x[k] = (float)out;
+    }
+}
+
+// One CTA per (channel, band) row.  The recurrence is linear in its (z1, z2) state, so a sweep
+// is split into 256 chunks of 64 samples per shared-memory tile:
+//   pass 1  every thread runs the reference recurrence over its chunk from a ZERO state and keeps
+//           the end state e_j;
+//   scan    the true start state of chunk j is S_j = A^64 S_{j-1} + e_{j-1}  (A = homogeneous
+//           transition [[-a1, 1], [-a2, 0]], A^64 obtained by running the same recurrence on
+//           the two unit states), carried across tiles;
+//   pass 2  every thread re-runs the reference recurrence from S_j and stores (float)out.
+// Pass 2 is the reference's own arithmetic; only S_j is associated differently (double, ~1e-16
+// relative), so the float outputs equal the serial filter's except for vanishingly rare
+// last-bit rounding flips.  `twopass` = forward sweep then backward sweep (filters.cpp:185-191).
+__global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const uint32_t *row_off, const uint32_t *row_len,
+                                                              const RowFilter *filters, int mode /* 1 onepass, 2 twopass */)
+{
+    extern __shared__ float tile[];                       // RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1), padded rows
+    __shared__ double e1[RVB_IIR_THREADS], e2[RVB_IIR_THREADS], s1[RVB_IIR_THREADS], s2[RVB_IIR_THREADS];
+    __shared__ double AM[4], carry[2];
+    const uint32_t row = blockIdx.x, tid = threadIdx.x;
     float *x = data + row_off[row];
     const uint32_t n = row_len[row];
     const RowFilter F = filters[row];
-    const uint32_t lane = threadIdx.x;
+    float *mine = tile + tid * (RVB_IIR_CHUNK + 1);
     for (int p = 0; p < F.npass; ++p) {
         const BiquadCoef q = F.q[p];
+        if (tid < 2) {   // column tid of A^CHUNK: homogeneous response to the unit state
+            double z1 = tid == 0 ? 1.0 : 0.0, z2 = tid == 0 ? 0.0 : 1.0;
+            for (int k = 0; k < RVB_IIR_CHUNK; ++k) {
+                const double out = z1;
+                z1 = __dsub_rn(z2, __dmul_rn(q.a1, out));
+                z2 = -__dmul_rn(q.a2, out);
+            }
+            AM[tid] = z1; AM[2 + tid] = z2;       // AM = [[m00, m01], [m10, m11]]
+        }
         for (int dirn = 0; dirn < mode; ++dirn) {
-            double z1 = 0.0, z2 = 0.0;
-            for (uint32_t t0 = 0; t0 < n; t0 += RVB_FILTER_TILE) {
-                const uint32_t m = min((uint32_t)RVB_FILTER_TILE, n - t0);
-                // forward sweep reads x[t0 + k]; backward sweep reads x[n-1 - (t0 + k)]
-                for (uint32_t k = lane; k < m; k += 32) tile[k] = dirn == 0 ? x[t0 + k] : x[n - 1 - (t0 + k)];
-                __syncwarp();
-                if (lane == 0) {
-                    for (uint32_t k = 0; k < m; ++k) {
-                        const double in = (double)tile[k];
-                        const double out = __dadd_rn(__dmul_rn(in, q.b0), z1);
-                        z1 = __dsub_rn(__dadd_rn(__dmul_rn(in, q.b1), z2), __dmul_rn(q.a1, out));
-                        z2 = __dsub_rn(__dmul_rn(in, q.b2), __dmul_rn(q.a2, out));
-                        tile[k] = (float)out;
+            if (tid == 0) { carry[0] = 0.0; carry[1] = 0.0; }
+            __syncthreads();
+            for (uint32_t t0 = 0; t0 < n; t0 += RVB_IIR_TILE) {
+                for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
+                    const uint32_t i = t0 + k;
+                    float v = 0.0f;   // zero padding past the end never feeds a stored sample
+                    if (i < n) v = dirn == 0 ? x[i] : x[n - 1 - i];
+                    tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)] = v;
+                }
+                __syncthreads();
+                double z1 = 0.0, z2 = 0.0;
+                biquad_chunk<false>(q, mine, z1, z2);
+                e1[tid] = z1; e2[tid] = z2;
+                __syncthreads();
+                if (tid == 0) {
+                    double a = carry[0], b = carry[1];
+                    const double m00 = AM[0], m01 = AM[1], m10 = AM[2], m11 = AM[3];
+                    for (int j = 0; j < RVB_IIR_THREADS; ++j) {
+                        s1[j] = a; s2[j] = b;
+                        const double na = m00 * a + m01 * b + e1[j];
+                        const double nb = m10 * a + m11 * b + e2[j];
+                        a = na; b = nb;
+                    }
+                    carry[0] = a; carry[1] = b;
+                }
+                __syncthreads();
+                z1 = s1[tid]; z2 = s2[tid];
+                biquad_chunk<true>(q, mine, z1, z2);
+                __syncthreads();
+                for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
+                    const uint32_t i = t0 + k;
+                    if (i < n) {
+                        const float v = tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)];
+                        if (dirn == 0) x[i] = v; else x[n - 1 - i] = v;
                     }
                 }
-                __syncwarp();
-                for (uint32_t k = lane; k < m; k += 32) {
-                    if (dirn == 0) x[t0 + k] = tile[k]; else x[n - 1 - (t0 + k)] = tile[k];
-                }
-                __syncwarp();
+                __syncthreads();
             }
         }
     }
@@ -256,12 +331,12 @@ __global__ void last_loud_kernel(const float *x, uint32_t L, float minVol, int *
     if ((threadIdx.x & 31) == 0 && l >= 0) atomicMax(last, l);
 }
 
-__global__ void aos_to_soa_kernel(const rvb_attenuated_impulse *in, uint32_t n, float4 *volA, float4 *volB, float4 *pt, float *tkey)
+__global__ void aos_to_soa_kernel(const rvb_attenuated_impulse *in, uint32_t n, float4 *vol, float4 *pt, float *tkey)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 *s = reinterpret_cast<const float4 *>(in + i);
-    volA[i] = s[0]; volB[i] = s[1];
+    vol[2 * (size_t)i] = s[0]; vol[2 * (size_t)i + 1] = s[1];
     float t = s[2].x;
     pt[i] = make_float4(0.f, 0.f, 0.f, t);
     tkey[i] = t;   // flattenImpulses looks at every impulse, zero volume or not (rayverb.cpp:55-56,67)
@@ -302,7 +377,7 @@ static int make_source(const rvb_trace *tr, const rvb_render_config *cfg, Source
     const bool images = cfg->output_mode != RVB_OUTPUT_DIFFUSE_ONLY;
     if (diffuse) {
         size_t n = tr->nrays * tr->nrefl;
-        S.volA = tr->d_volA; S.volB = tr->d_volB; S.pt = tr->d_pt; S.tkey = tr->d_tkey; S.n_diffuse = (uint32_t)n;
+        S.vol = tr->d_vol; S.pt = tr->d_pt; S.tkey = tr->d_tkey; S.n_diffuse = (uint32_t)n;
     }
     if (images) {
         size_t skip = (cfg->remove_direct && tr->first_is_direct) ? 1 : 0;
@@ -338,7 +413,7 @@ static int make_channels(const float mic[3], const rvb_render_config *cfg, Chann
         float4 *d = nullptr;
         RVB_TRY(dev_alloc(&d, 2 * cs.nch));
         RVB_CUDA(cudaMemcpyAsync(d, h.data(), cs.nch * sizeof(float4), cudaMemcpyHostToDevice, st));
-        normalize_dirs_kernel<<<1, 1024, 0, st>>>(d, (int)cs.nch, d + cs.nch);
+        note_launch(), normalize_dirs_kernel<<<1, 1024, 0, st>>>(d, (int)cs.nch, d + cs.nch);
         RVB_CUDA(cudaMemcpyAsync(h.data(), d + cs.nch, cs.nch * sizeof(float4), cudaMemcpyDeviceToHost, st));
         RVB_CUDA(cudaStreamSynchronize(st));
         dev_free(d);
@@ -355,7 +430,7 @@ static int make_channels(const float mic[3], const rvb_render_config *cfg, Chann
         float4 *d_ear = nullptr, h_ear[2];
         RVB_TRY(dev_alloc(&d_ear, 2));
         const f3 f = {cfg->facing[0], cfg->facing[1], cfg->facing[2]}, u = {cfg->up[0], cfg->up[1], cfg->up[2]};
-        ear_kernel<<<1, 2, 0, st>>>(f, u, m, d_ear);
+        note_launch(), ear_kernel<<<1, 2, 0, st>>>(f, u, m, d_ear);
         RVB_CUDA(cudaMemcpyAsync(h_ear, d_ear, sizeof h_ear, cudaMemcpyDeviceToHost, st));
         for (int ch = 0; ch < 2; ++ch) {
             RVB_TRY(dev_alloc(&cs.d_table[ch], 2 * (cells + 180)));
@@ -382,7 +457,7 @@ static int times_for_spec(const Source &S, const ChanSpec &C, float &mn, float &
     RVB_TRY(dev_alloc(&d, 2));
     const int init[2] = {0x7f800000, 0};   // ordered(+inf), ordered(0)
     RVB_CUDA(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, st));
-    if (S.n_diffuse + S.n_images) times_kernel<<<grid_for(S.n_diffuse + S.n_images), 256, 0, st>>>(S, C, d);
+    if (S.n_diffuse + S.n_images) note_launch(), times_kernel<<<grid_for(S.n_diffuse + S.n_images), 256, 0, st>>>(S, C, d);
     RVB_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
     dev_free(d);
@@ -418,7 +493,7 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             last_group = cs.pass_key_group[p];
             L = (uint32_t)lengths[c0];
             Timer tk(st);
-            keys_kernel<<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, d_keys[0], d_vals[0]);
+            note_launch(), keys_kernel<<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, d_keys[0], d_vals[0]);
             g_stats.keys_ms += tk.stop();
             Timer ts(st);
             int end_bit = 1;
@@ -435,12 +510,22 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             RVB_TRY(dev_alloc(&d_begin, (size_t)L + 1)); RVB_TRY(dev_alloc(&d_end, (size_t)L + 1));
             RVB_CUDA(cudaMemsetAsync(d_begin, 0, ((size_t)L + 1) * sizeof(uint32_t), st));
             RVB_CUDA(cudaMemsetAsync(d_end, 0, ((size_t)L + 1) * sizeof(uint32_t), st));
-            bounds_kernel<<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, L, d_begin, d_end);
+            note_launch(), bounds_kernel<<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, L, d_begin, d_end);
             g_stats.sort_ms += ts.stop();
         }
         Timer tr_(st);
         const size_t stride = RVB_NBANDS * (size_t)L;
-        reduce_kernel<<<148 * 8, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, d_hist + chan_off[c0], stride);
+        {
+            const unsigned rgrid = (unsigned)sm_count() * 8;
+            float *dst = d_hist + chan_off[c0];
+            bool need_pos = false;
+            for (int c = 0; c < C.nch; ++c) need_pos |= (C.coef[c] != 0.0f);
+            note_launch();
+            if (C.model == 0 && need_pos) reduce_kernel<0, true><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
+            else if (C.model == 0) reduce_kernel<0, false><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
+            else if (C.model == 1) reduce_kernel<1, true><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
+            else reduce_kernel<2, false><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
+        }
         RVB_CUDA(cudaGetLastError());
         g_stats.reduce_ms += tr_.stop();
     }
@@ -499,7 +584,9 @@ static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nc
     RVB_CUDA(cudaMemcpyAsync(d_f, hf.data(), nrows * sizeof(RowFilter), cudaMemcpyHostToDevice, st));
     RVB_CUDA(cudaMemcpyAsync(d_off, off.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     RVB_CUDA(cudaMemcpyAsync(d_len, len.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    iir_kernel<<<(unsigned)nrows, 32, 0, st>>>(d_data, d_off, d_len, d_f, ft == RVB_FILTER_BIQUAD_ONEPASS ? 1 : 2);
+    const size_t iir_smem = (size_t)RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1) * sizeof(float);
+    RVB_CUDA(cudaFuncSetAttribute(iir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iir_smem));
+    note_launch(), iir_kernel<<<(unsigned)nrows, RVB_IIR_THREADS, iir_smem, st>>>(d_data, d_off, d_len, d_f, ft == RVB_FILTER_BIQUAD_ONEPASS ? 1 : 2);
     RVB_CUDA(cudaGetLastError());
     RVB_CUDA(cudaStreamSynchronize(st));
     dev_free(d_f); dev_free(d_off); dev_free(d_len);
@@ -522,7 +609,7 @@ static int finish_device(const rvb_render_config *cfg, float *d_hist /* modified
     RVB_CUDA(cudaMemcpyAsync(d_red, init, sizeof init, cudaMemcpyHostToDevice, st));
     size_t ho = 0, mo = 0;
     for (size_t c = 0; c < nch; ++c) {
-        if (lengths[c]) mixdown_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_hist + ho, (uint32_t)lengths[c], d_mix + mo, d_red);
+        if (lengths[c]) note_launch(), mixdown_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_hist + ho, (uint32_t)lengths[c], d_mix + mo, d_red);
         ho += RVB_NBANDS * lengths[c]; mo += lengths[c];
     }
     int h_red[2];
@@ -531,14 +618,14 @@ static int finish_device(const rvb_render_config *cfg, float *d_hist /* modified
     if (cfg->do_normalize) {   // normalize: mul(ret, 1.0 / max_amp(ret)), generic_functions.h:56-60
         float m; memcpy(&m, &h_red[0], 4);
         const float f = (float)(1.0 / (double)m);
-        if (total) scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, f);
+        if (total) note_launch(), scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, f);
     }
-    if (cfg->volume_scale != 1) { if (total) scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, cfg->volume_scale); }
+    if (cfg->volume_scale != 1) { if (total) note_launch(), scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, cfg->volume_scale); }
     long trimmed = -1;
     if (cfg->do_trim_tail) {
         mo = 0;
         for (size_t c = 0; c < nch; ++c) {
-            if (lengths[c]) last_loud_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_mix + mo, (uint32_t)lengths[c], 0.00001f, d_red + 1);
+            if (lengths[c]) note_launch(), last_loud_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_mix + mo, (uint32_t)lengths[c], 0.00001f, d_red + 1);
             mo += lengths[c];
         }
         RVB_CUDA(cudaMemcpyAsync(h_red, d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
@@ -651,12 +738,17 @@ int rvb_render_ir(rvb_trace *tr, const rvb_render_config *cfg, rvb_ir **out)
     RVB_CUDA(cudaSetDevice(tr->scene->device));
     cudaStream_t st = lib_stream();
     g_stats = rvb_render_stats{};
+    StageTimer t_all("render.total");
     Timer tt(st);
     Source S;
-    RVB_TRY(make_source(tr, cfg, S));
     ChannelSetup cs;
-    RVB_TRY(make_channels(tr->mic, cfg, cs));
+    {
+        StageTimer t_s("render.setup");
+        RVB_TRY(make_source(tr, cfg, S));
+        RVB_TRY(make_channels(tr->mic, cfg, cs));
+    }
     g_stats.n_impulses = (uint64_t)S.n_diffuse + S.n_images;
+    StageTimer *t_t = new StageTimer("render.times");
     // per-channel time extrema -> predelay (min over all channels) and flatten lengths
     std::vector<float> mn(cs.nch), mx(cs.nch);
     int last_group = -1;
@@ -673,11 +765,17 @@ int rvb_render_ir(rvb_trace *tr, const rvb_render_config *cfg, rvb_ir **out)
     std::vector<size_t> lengths(cs.nch);
     size_t total = 0;
     for (size_t c = 0; c < cs.nch; ++c) { lengths[c] = flatten_length(mx[c], predelay, fix, cfg->sample_rate); total += RVB_NBANDS * lengths[c]; }
+    delete t_t;
     float *d_hist = nullptr;
     RVB_TRY(dev_alloc(&d_hist, total));
-    int rc = histogram_passes(S, cs, predelay, fix, cfg->sample_rate, lengths.data(), d_hist);
+    int rc;
+    {
+        StageTimer t_h("render.histogram");
+        rc = histogram_passes(S, cs, predelay, fix, cfg->sample_rate, lengths.data(), d_hist);
+    }
     rvb_ir *ir = nullptr;
     if (rc == RVB_OK) {
+        StageTimer t_fi("render.finish(filter+mix)");
         ir = new rvb_ir();
         rc = finish_device(cfg, d_hist, lengths.data(), cs.nch, ir, g_keep_bands);
     }
@@ -725,13 +823,13 @@ int rvb_flatten(const rvb_attenuated_impulse *in, size_t n, float sample_rate, f
     cudaStream_t st = lib_stream();
     g_stats = rvb_render_stats{};
     rvb_attenuated_impulse *d_in = nullptr;
-    float4 *vA = nullptr, *vB = nullptr, *pt = nullptr; float *tk = nullptr;
-    RVB_TRY(dev_alloc(&d_in, n)); RVB_TRY(dev_alloc(&vA, n)); RVB_TRY(dev_alloc(&vB, n)); RVB_TRY(dev_alloc(&pt, n)); RVB_TRY(dev_alloc(&tk, n));
+    float4 *vA = nullptr, *pt = nullptr; float *tk = nullptr;
+    RVB_TRY(dev_alloc(&d_in, n)); RVB_TRY(dev_alloc(&vA, 2 * n)); RVB_TRY(dev_alloc(&pt, n)); RVB_TRY(dev_alloc(&tk, n));
     if (n) {
         RVB_CUDA(cudaMemcpyAsync(d_in, in, n * sizeof(rvb_attenuated_impulse), cudaMemcpyHostToDevice, st));
-        aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, (uint32_t)n, vA, vB, pt, tk);
+        note_launch(), aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, (uint32_t)n, vA, pt, tk);
     }
-    Source S{}; S.volA = vA; S.volB = vB; S.pt = pt; S.tkey = tk; S.n_diffuse = (uint32_t)n;
+    Source S{}; S.vol = vA; S.pt = pt; S.tkey = tk; S.n_diffuse = (uint32_t)n;
     ChannelSetup cs; cs.model = 2; cs.nch = 1;
     ChanSpec C{}; C.model = 2; C.nch = 1;
     cs.passes.push_back(C); cs.pass_first_channel.push_back(0); cs.pass_key_group.push_back(0);
@@ -751,7 +849,7 @@ int rvb_flatten(const rvb_attenuated_impulse *in, size_t n, float sample_rate, f
         cudaStreamSynchronize(st);
         *out = h; *length = L;
     }
-    dev_free(d_hist); dev_free(d_in); dev_free(vA); dev_free(vB); dev_free(pt); dev_free(tk);
+    dev_free(d_hist); dev_free(d_in); dev_free(vA); dev_free(pt); dev_free(tk);
     return rc;
 }
 

@@ -27,6 +27,17 @@ int fail(int code, const std::string &msg);
 
 // One library stream per device (non-blocking), created lazily; events for stage timings.
 cudaStream_t lib_stream();
+void note_launch();    // counts kernels launched by this library (rvb_launch_count)
+int sm_count();        // multiprocessor count of the current device (cached)
+
+// RVB_TIMING=1: host wall-clock per stage (stream-synchronised at scope exit), printed to stderr
+struct StageTimer {
+    const char *name;
+    double t0;
+    bool on;
+    explicit StageTimer(const char *n);
+    ~StageTimer();
+};
 int ensure_device();   // checks that the current device exists and is sm_100; configures the mem pool
 
 // stream-ordered allocations from the device's default pool (kept warm between calls)
@@ -83,7 +94,7 @@ struct Trace {
     unsigned flags = 0;
     float mic[3] = {0, 0, 0}, src[3] = {0, 0, 0};
     // diffuse impulses, BOUNCE-major: slot = bounce * nrays + ray
-    float4 *d_volA = nullptr, *d_volB = nullptr;   // bands 0-3, 4-7
+    float4 *d_vol = nullptr;                        // [2*slots]: bands 0-3 at 2*slot, 4-7 at 2*slot+1 (one 32-B sector)
     float4 *d_pt = nullptr;                        // position xyz, time
     float *d_tkey = nullptr;                       // time if any(volume != 0) else -1 (kernel.cpp:524 skip rule)
     uint32_t *d_hit = nullptr;                     // debug: hit triangle per slot

@@ -8,6 +8,10 @@
 //   d_nrm    normalize(cross(e0, e1)), surface  -- kernel.cpp:110-116 evaluated once
 // The subtraction / normal are the same IEEE operations the reference performs per test, so the
 // staged values carry the same bits.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <mutex>
 
 #include "rvb_internal.cuh"
@@ -23,13 +27,49 @@ static std::mutex g_mutex;
 static cudaStream_t g_streams[64] = {};
 static bool g_checked[64] = {};
 
+static thread_local cudaStream_t g_user_stream = nullptr;
+static thread_local bool g_has_user_stream = false;
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 cudaStream_t lib_stream()
 {
+    if (g_has_user_stream) return g_user_stream;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_mutex);
     if (!g_streams[dev]) cudaStreamCreateWithFlags(&g_streams[dev], cudaStreamNonBlocking);
     return g_streams[dev];
+}
+
+static int g_sm_count[64] = {};
+int sm_count()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!g_sm_count[dev]) cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    return g_sm_count[dev];
+}
+
+static bool timing_on()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("RVB_TIMING"); on = (e && *e && *e != '0') ? 1 : 0; }
+    return on == 1;
+}
+static double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+StageTimer::StageTimer(const char *n) : name(n), t0(0), on(timing_on())
+{
+    if (on) { cudaStreamSynchronize(lib_stream()); t0 = now_ms(); }
+}
+StageTimer::~StageTimer()
+{
+    if (on) { cudaStreamSynchronize(lib_stream()); fprintf(stderr, "[rvb] %-28s %8.3f ms\n", name, now_ms() - t0); }
 }
 
 int ensure_device()
@@ -94,6 +134,15 @@ int rvb_device_count(int *count)
     return RVB_OK;
 }
 
+int rvb_set_stream(void *cuda_stream, int use)
+{
+    g_user_stream = (cudaStream_t)cuda_stream;
+    g_has_user_stream = use != 0;
+    return RVB_OK;
+}
+
+unsigned long long rvb_launch_count(void) { return g_launches.load(); }
+
 int rvb_set_device(int device)
 {
     RVB_CUDA(cudaSetDevice(device));
@@ -133,7 +182,7 @@ int rvb_scene_create(const rvb_triangle *triangles, size_t ntriangles, const rvb
     cudaMemcpyAsync(d_tris, triangles, ntriangles * sizeof(rvb_triangle), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_vertices, vertices, nvertices * sizeof(rvb_float3), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(sc->d_surfaces, surfaces, nsurfaces * sizeof(rvb_surface), cudaMemcpyHostToDevice, st);
-    stage_scene_kernel<<<(unsigned)((ntriangles + 255) / 256), 256, 0, st>>>(d_tris, d_vertices, sc->T, sc->d_verts, sc->d_tri, sc->d_nrm);
+    note_launch(), stage_scene_kernel<<<(unsigned)((ntriangles + 255) / 256), 256, 0, st>>>(d_tris, d_vertices, sc->T, sc->d_verts, sc->d_tri, sc->d_nrm);
     cudaError_t e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess) { rvb_scene_destroy(sc); return fail(RVB_ERR_CUDA, std::string("scene staging: ") + cudaGetErrorString(e)); }

@@ -27,7 +27,7 @@ struct TraceParams {
     uint64_t ray_offset;
     float mic[3], src[3];
     float air[RVB_NBANDS];
-    float4 *volA, *volB, *pt;
+    float4 *vol, *pt;      // vol: 2 x float4 per slot
     float *tkey;
     uint32_t *hit, *count;
     float4 *cand_volA, *cand_volB, *cand_pt;   // [nrays*10] image-source candidates
@@ -305,8 +305,8 @@ __device__ void trace_ray(const Accel &acc, const TraceParams &P, uint32_t ray, 
         }
         const float time = __fmul_rn(RVB_SECONDS_PER_METER, DIST);
         const size_t slot = (size_t)index * P.nrays + ray;
-        P.volA[slot] = make_float4(out[0], out[1], out[2], out[3]);
-        P.volB[slot] = make_float4(out[4], out[5], out[6], out[7]);
+        P.vol[2 * slot] = make_float4(out[0], out[1], out[2], out[3]);
+        P.vol[2 * slot + 1] = make_float4(out[4], out[5], out[6], out[7]);
         P.pt[slot] = make_float4(X.x, X.y, X.z, time);
         P.tkey[slot] = any ? time : -1.0f;
         if (P.hit) P.hit[slot] = prim;
@@ -323,7 +323,7 @@ __device__ void trace_ray(const Accel &acc, const TraceParams &P, uint32_t ray, 
     for (; index != P.nrefl; ++index) {
         const size_t slot = (size_t)index * P.nrays + ray;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        P.volA[slot] = z; P.volB[slot] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
+        P.vol[2 * slot] = z; P.vol[2 * slot + 1] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
         if (P.hit) P.hit[slot] = RVB_NONE;
     }
 }
@@ -377,7 +377,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     const double air[RVB_NBANDS] = {0.001 * -0.1, 0.001 * -0.2, 0.001 * -0.5, 0.001 * -1.1,
                                     0.001 * -2.7, 0.001 * -9.4, 0.001 * -29.0, 0.001 * -60.0};
     for (int b = 0; b < RVB_NBANDS; ++b) P.air[b] = (float)air[b];
-    P.volA = tr->d_volA; P.volB = tr->d_volB; P.pt = tr->d_pt; P.tkey = tr->d_tkey;
+    P.vol = tr->d_vol; P.pt = tr->d_pt; P.tkey = tr->d_tkey;
     P.hit = tr->d_hit; P.count = tr->d_count;
     P.cand_volA = d_cand_volA; P.cand_volB = d_cand_volB; P.cand_pt = d_cand_pt; P.cand_idx = d_cand_idx;
     P.flags = tr->flags;
@@ -386,10 +386,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     RVB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), st));
     P.counters = d_counters;
 
-    cudaDeviceProp prop;
-    int dev;
-    RVB_CUDA(cudaGetDevice(&dev));
-    RVB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int nsm = sm_count();
     cudaEvent_t e0, e1;
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
@@ -403,15 +400,15 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
             RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_bruteforce_kernel, block, smem));
             if (per_sm < 1) return fail(RVB_ERR_INVALID, "scene does not fit in shared memory for the brute-force kernel");
             size_t want = (tr->nrays + block - 1) / block;
-            size_t grid = std::min(want, (size_t)per_sm * prop.multiProcessorCount);
-            trace_bruteforce_kernel<<<(unsigned)grid, block, smem, st>>>(P);
+            size_t grid = std::min(want, (size_t)per_sm * nsm);
+            note_launch(), trace_bruteforce_kernel<<<(unsigned)grid, block, smem, st>>>(P);
         } else {
             const int block = 128;
             int per_sm = 0;
             RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_bvh_kernel, block, 0));
             size_t want = (tr->nrays + block - 1) / block;
-            size_t grid = std::min(want, (size_t)std::max(per_sm, 1) * prop.multiProcessorCount);
-            trace_bvh_kernel<<<(unsigned)grid, block, 0, st>>>(P);
+            size_t grid = std::min(want, (size_t)std::max(per_sm, 1) * nsm);
+            note_launch(), trace_bvh_kernel<<<(unsigned)grid, block, 0, st>>>(P);
         }
         RVB_CUDA(cudaGetLastError());
     }

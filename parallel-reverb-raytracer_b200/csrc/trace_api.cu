@@ -13,14 +13,14 @@
 namespace rvb {
 
 // bounce-major SoA -> ray-major AoS (Impulse, clstructs.h:36-42) for a range of rays
-__global__ void export_diffuse_kernel(const float4 *volA, const float4 *volB, const float4 *pt, uint32_t nrays, uint32_t nrefl,
+__global__ void export_diffuse_kernel(const float4 *vol, const float4 *pt, uint32_t nrays, uint32_t nrefl,
                                       uint32_t ray0, uint32_t nr, rvb_impulse *out)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over nr*nrefl, bounce fastest
     if (i >= (size_t)nr * nrefl) return;
     uint32_t r = (uint32_t)(i / nrefl), b = (uint32_t)(i % nrefl);
     size_t slot = (size_t)b * nrays + ray0 + r;
-    float4 a = volA[slot], c = volB[slot], p = pt[slot];
+    float4 a = vol[2 * slot], c = vol[2 * slot + 1], p = pt[slot];
     float4 *o = reinterpret_cast<float4 *>(out + i);
     o[0] = a; o[1] = c; o[2] = make_float4(p.x, p.y, p.z, 0.f); o[3] = make_float4(p.w, 0.f, 0.f, 0.f);
 }
@@ -65,8 +65,11 @@ static int trace_run_impl(rvb_scene *scene, const float mic[3], const float sour
     uint32_t *cidx = nullptr;
     const bool images = !(flags & RVB_TRACE_NO_IMAGES);
     const size_t ncand = images ? nrays * RVB_NUM_IMAGE_SOURCE : 0;
+    StageTimer t_all("trace.total");
     auto bail = [&](int code) { dev_free(cvA); dev_free(cvB); dev_free(cpt); dev_free(cidx); rvb_trace_destroy(tr); return code; };
-    if ((rc = dev_alloc(&tr->d_volA, nslots)) || (rc = dev_alloc(&tr->d_volB, nslots)) || (rc = dev_alloc(&tr->d_pt, nslots)) ||
+    {
+    StageTimer t_alloc("trace.alloc");
+    if ((rc = dev_alloc(&tr->d_vol, 2 * nslots)) || (rc = dev_alloc(&tr->d_pt, nslots)) ||
         (rc = dev_alloc(&tr->d_tkey, nslots)))
         return bail(rc);
     if (flags & RVB_TRACE_DEBUG) {
@@ -80,10 +83,16 @@ static int trace_run_impl(rvb_scene *scene, const float mic[3], const float sour
         // slot 0 of ray 0 is read even if the direct path is occluded (key {0} is unconditional)
         cudaMemsetAsync(cvA, 0, sizeof(float4), st); cudaMemsetAsync(cvB, 0, sizeof(float4), st); cudaMemsetAsync(cpt, 0, sizeof(float4), st);
     }
-    if ((rc = trace_launch(tr, d_dirs, cvA, cvB, cpt, cidx))) return bail(rc);
+    }
+    {
+        StageTimer t_k("trace.kernel");
+        if ((rc = trace_launch(tr, d_dirs, cvA, cvB, cpt, cidx))) return bail(rc);
+    }
     if (images && ncand) {
+        StageTimer t_d("trace.dedupe");
         if ((rc = images_dedupe(tr, cvA, cvB, cpt, cidx))) return bail(rc);
     }
+    StageTimer t_f("trace.free");
     dev_free(cvA); dev_free(cvB); dev_free(cpt); dev_free(cidx);
     *out = tr;
     return RVB_OK;
@@ -146,7 +155,7 @@ int rvb_trace_destroy(rvb_trace *tr)
 {
     if (!tr) return RVB_OK;
     if (tr->scene) cudaSetDevice(tr->scene->device);
-    dev_free(tr->d_volA); dev_free(tr->d_volB); dev_free(tr->d_pt); dev_free(tr->d_tkey);
+    dev_free(tr->d_vol); dev_free(tr->d_pt); dev_free(tr->d_tkey);
     dev_free(tr->d_hit); dev_free(tr->d_count);
     dev_free(tr->d_img_volA); dev_free(tr->d_img_volB); dev_free(tr->d_img_pt);
     delete tr;
@@ -174,7 +183,7 @@ int rvb_trace_copy_diffuse(const rvb_trace *tr, rvb_impulse *out)
     for (size_t r0 = 0; r0 < tr->nrays; r0 += rays_per_chunk) {
         size_t nr = std::min(rays_per_chunk, tr->nrays - r0);
         size_t n = nr * tr->nrefl;
-        export_diffuse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_volA, tr->d_volB, tr->d_pt, (uint32_t)tr->nrays,
+        note_launch(), export_diffuse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_vol, tr->d_pt, (uint32_t)tr->nrays,
                                                                            (uint32_t)tr->nrefl, (uint32_t)r0, (uint32_t)nr, d_stage);
         RVB_CUDA(cudaMemcpyAsync(out + r0 * tr->nrefl, d_stage, n * sizeof(rvb_impulse), cudaMemcpyDeviceToHost, st));
         RVB_CUDA(cudaStreamSynchronize(st));
@@ -201,7 +210,7 @@ int rvb_trace_copy_images(const rvb_trace *tr, int remove_direct, rvb_impulse *o
     if (out) {
         rvb_impulse *d_stage = nullptr;
         RVB_TRY(dev_alloc(&d_stage, n));
-        export_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_img_volA + skip, tr->d_img_volB + skip, tr->d_img_pt + skip, (uint32_t)n, d_stage);
+        note_launch(), export_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_img_volA + skip, tr->d_img_volB + skip, tr->d_img_pt + skip, (uint32_t)n, d_stage);
         RVB_CUDA(cudaMemcpyAsync(out, d_stage, n * sizeof(rvb_impulse), cudaMemcpyDeviceToHost, st));
         RVB_CUDA(cudaStreamSynchronize(st));
         dev_free(d_stage);
@@ -223,7 +232,7 @@ int rvb_trace_set_images(rvb_trace *tr, const rvb_impulse *images, size_t n)
     RVB_TRY(dev_alloc(&d_stage, n));
     RVB_TRY(dev_alloc(&tr->d_img_volA, n)); RVB_TRY(dev_alloc(&tr->d_img_volB, n)); RVB_TRY(dev_alloc(&tr->d_img_pt, n));
     RVB_CUDA(cudaMemcpyAsync(d_stage, images, n * sizeof(rvb_impulse), cudaMemcpyHostToDevice, st));
-    import_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_stage, (uint32_t)n, tr->d_img_volA, tr->d_img_volB, tr->d_img_pt);
+    note_launch(), import_images_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_stage, (uint32_t)n, tr->d_img_volA, tr->d_img_volB, tr->d_img_pt);
     RVB_CUDA(cudaStreamSynchronize(st));
     dev_free(d_stage);
     return RVB_OK;
@@ -264,7 +273,7 @@ int rvb_trace_copy_debug(const rvb_trace *tr, uint32_t *hit_triangle, uint32_t *
     if (hit_triangle && n) {
         uint32_t *d_stage = nullptr;
         RVB_TRY(dev_alloc(&d_stage, n));
-        export_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_hit, (uint32_t)tr->nrays, (uint32_t)tr->nrefl, d_stage);
+        note_launch(), export_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tr->d_hit, (uint32_t)tr->nrays, (uint32_t)tr->nrefl, d_stage);
         RVB_CUDA(cudaMemcpyAsync(hit_triangle, d_stage, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         RVB_CUDA(cudaStreamSynchronize(st));
         dev_free(d_stage);

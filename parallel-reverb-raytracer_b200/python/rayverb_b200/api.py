@@ -48,7 +48,7 @@ class RenderConfig(C.Structure):
 
 # every symbol include/rayverb_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "rvb_last_error", "rvb_device_count", "rvb_set_device", "rvb_version",
+    "rvb_last_error", "rvb_device_count", "rvb_set_device", "rvb_version", "rvb_set_stream", "rvb_launch_count",
     "rvb_scene_create", "rvb_scene_destroy", "rvb_scene_accel",
     "rvb_trace_run", "rvb_trace_run_device", "rvb_trace_destroy", "rvb_trace_diffuse_count", "rvb_trace_copy_diffuse",
     "rvb_trace_image_count", "rvb_trace_copy_images", "rvb_trace_set_images", "rvb_images_merge",
@@ -73,9 +73,11 @@ def lib():
         L.rvb_last_error.restype = C.c_char_p
         for name in EXPORTS:
             fn = getattr(L, name)
-            if name not in ("rvb_last_error", "rvb_free"):
+            if name not in ("rvb_last_error", "rvb_free", "rvb_launch_count"):
                 fn.restype = C.c_int
         L.rvb_free.restype = None
+        L.rvb_launch_count.restype = C.c_ulonglong
+        L.rvb_set_stream.argtypes = [C.c_void_p, C.c_int]
         L.rvb_free.argtypes = [C.c_void_p]
         vp, sz, u64, f32, i32, u32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_float, C.c_int, C.c_uint
         L.rvb_device_count.argtypes = [vp]
@@ -135,6 +137,18 @@ def device_count():
 
 def set_device(dev):
     _check(lib().rvb_set_device(int(dev)))
+
+
+def set_stream(cuda_stream_ptr):
+    """Run this thread's calls on the given CUDA stream (None: the library's own stream)."""
+    if cuda_stream_ptr is None:
+        _check(lib().rvb_set_stream(None, 0))
+    else:
+        _check(lib().rvb_set_stream(C.c_void_p(int(cuda_stream_ptr)), 1))
+
+
+def launch_count():
+    return int(lib().rvb_launch_count())
 
 
 def _filter_id(ft):

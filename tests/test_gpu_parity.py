@@ -28,6 +28,17 @@ def rel_l2(a, b):
     return np.linalg.norm(a - b) / d if d > 0 else np.linalg.norm(a)
 
 
+def assert_filter_close(got, want, what):
+    """The chunk-parallel IIR runs the reference's own double recurrence inside every chunk; only
+    the chunk start states are associated differently (~1e-16 relative in double), so the float
+    outputs are bit-identical except for very rare last-bit rounding flips."""
+    got = np.asarray(got, np.float32); want = np.asarray(want, np.float32)
+    mism = bits(got) != bits(want)
+    assert mism.mean() <= 1e-4, (what, mism.mean())
+    scale = np.abs(want).max()
+    assert np.abs(got.astype(np.float64) - want).max() <= 2e-7 * scale, what
+
+
 def check_trace_against_oracle(orc, tri, vtx, srf, mic, src, dirs, nrefl, accel):
     rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
     tr = rt.raytrace(mic, src, dirs, flags=api.TRACE_DEBUG)
@@ -214,8 +225,9 @@ def test_host_array_postprocessing_vs_oracle(orc):
     for ft in ("onepass", "twopass", "linkwitz_riley"):
         g = api.filter_bands(ft, rf[None], sr, 45.0)[0]
         rg = orc.filter_channel(ft, rf, sr, 45.0)
-        assert np.array_equal(bits(g), bits(rg)), ft    # same double recurrence, unfused: bit exact
+        assert_filter_close(g, rg, ft)
     out = api.process("linkwitz_riley", [rf, rf[:, :9000]], sr, True, 45.0, True, 1.0)
     ref = orc.process("linkwitz_riley", [rf, rf[:, :9000]], sr, True, 45.0, True, 1.0)
     for a, b in zip(out, ref):
-        assert len(a) == len(b) and np.array_equal(bits(a), bits(b))
+        assert len(a) == len(b)
+        assert_filter_close(a, b, "process")
