@@ -40,21 +40,23 @@ struct StageTimer {
 };
 int ensure_device();   // checks that the current device exists and is sm_100; configures the mem pool
 
-// stream-ordered allocations from the device's default pool (kept warm between calls)
+// Device allocations.  Small blocks come from the device's stream-ordered pool; blocks of 1 MiB
+// and more go through an exact-size cache (a trace of the same shape re-uses the very same
+// blocks on the next call instead of paying cudaMalloc / pool growth -- the reference allocates
+// its cl::Buffers once per Raytracer for the same reason, rayverb.cpp:252-274).
+int alloc_bytes(void **p, size_t bytes);
+void free_bytes(void *p);
 template <class T>
 inline int dev_alloc(T **p, size_t n)
 {
     *p = nullptr;
     if (n == 0) return RVB_OK;
-    cudaError_t e = cudaMallocAsync((void **)p, n * sizeof(T), lib_stream());
-    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RVB_ERR_NOMEM : RVB_ERR_CUDA,
-                                      std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
-    return RVB_OK;
+    return alloc_bytes((void **)p, n * sizeof(T));
 }
 template <class T>
 inline void dev_free(T *&p)
 {
-    if (p) cudaFreeAsync((void *)p, lib_stream());
+    if (p) free_bytes((void *)p);
     p = nullptr;
 }
 

@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 
 #include "rvb_internal.cuh"
 
@@ -40,6 +42,89 @@ cudaStream_t lib_stream()
     std::lock_guard<std::mutex> lk(g_mutex);
     if (!g_streams[dev]) cudaStreamCreateWithFlags(&g_streams[dev], cudaStreamNonBlocking);
     return g_streams[dev];
+}
+
+// ---- exact-size block cache ----------------------------------------------------------------------
+struct CachedBlock { void *p; cudaStream_t stream; };
+static std::multimap<size_t, CachedBlock> g_free_blocks[64];
+static std::unordered_map<void *, size_t> g_live_blocks[64];
+static size_t g_cached_bytes[64] = {};
+static const size_t kCacheThreshold = (size_t)1 << 20;
+static const size_t kCacheLimit = (size_t)48 << 30;   // beyond this, idle blocks go back to the driver
+
+int alloc_bytes(void **p, size_t bytes)
+{
+    cudaStream_t st = lib_stream();
+    if (bytes < kCacheThreshold) {
+        cudaError_t e = cudaMallocAsync(p, bytes, st);
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RVB_ERR_NOMEM : RVB_ERR_CUDA,
+                                          std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        return RVB_OK;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        auto it = g_free_blocks[dev].find(bytes);
+        if (it != g_free_blocks[dev].end()) {
+            CachedBlock b = it->second;
+            g_free_blocks[dev].erase(it);
+            g_cached_bytes[dev] -= bytes;
+            g_live_blocks[dev][b.p] = bytes;
+            *p = b.p;
+            if (b.stream != st) cudaStreamSynchronize(b.stream);   // freed on another stream: wait for its last use
+            return RVB_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {   // give cached blocks back and retry once
+        cudaGetLastError();
+        std::vector<void *> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_mutex);
+            for (auto &kv : g_free_blocks[dev]) drop.push_back(kv.second.p);
+            g_free_blocks[dev].clear();
+            g_cached_bytes[dev] = 0;
+        }
+        cudaDeviceSynchronize();
+        for (void *q : drop) cudaFree(q);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RVB_ERR_NOMEM : RVB_ERR_CUDA,
+                                      std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lk(g_mutex);
+    g_live_blocks[dev][*p] = bytes;
+    return RVB_OK;
+}
+
+void free_bytes(void *p)
+{
+    cudaStream_t st = lib_stream();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::vector<void *> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        auto it = g_live_blocks[dev].find(p);
+        if (it == g_live_blocks[dev].end()) {
+            cudaFreeAsync(p, st);
+            return;
+        }
+        const size_t bytes = it->second;
+        g_live_blocks[dev].erase(it);
+        g_free_blocks[dev].emplace(bytes, CachedBlock{p, st});
+        g_cached_bytes[dev] += bytes;
+        while (g_cached_bytes[dev] > kCacheLimit && !g_free_blocks[dev].empty()) {
+            auto big = std::prev(g_free_blocks[dev].end());
+            drop.push_back(big->second.p);
+            g_cached_bytes[dev] -= big->first;
+            g_free_blocks[dev].erase(big);
+        }
+    }
+    if (!drop.empty()) {
+        cudaDeviceSynchronize();
+        for (void *q : drop) cudaFree(q);
+    }
 }
 
 static int g_sm_count[64] = {};

@@ -1,10 +1,20 @@
-// The bounce kernel: B200-native replacement of `kernel raytrace` (rayverb/kernel.cpp:304-503).
+// The bounce kernels: B200-native replacement of `kernel raytrace` (rayverb/kernel.cpp:304-503).
 //
-// One thread per ray, persistent grid-stride over rays.  The whole scene is staged once per
-// CTA in shared memory in intersection form (v0, e0, e1 -- 3 x float4 per triangle, read as
-// warp-wide broadcasts) for the brute-force path, or traversed through the GPU-built BVH
-// (bvh.cu) whose nearest-hit result -- including the lowest-index tie-break of the reference's
-// strict '<' loop (kernel.cpp:180-188) -- equals the brute-force loop.
+// One thread per ray, persistent grid-stride over rays, in two kernels:
+//
+//   image phase    reflections 0..8: the part of the reference loop that carries the image-source
+//                  branch (kernel.cpp:379-457: mirrored triangles, validation queries, add_image).
+//                  Heavy, divergent, 7 % of the reflections.
+//   steady phase   reflections 9..: nearest hit -> visibility -> emit -> reflect, one inlined copy
+//                  of each query loop so the hot code stays instruction-cache resident and the
+//                  lanes of a warp stay in lock step.
+//
+// The ray state (position, direction, path length, 8-band volume) passes between them through a
+// 64-byte record per ray.  The scene is staged once per CTA in shared memory in intersection form
+// (v0, e0, e1 -- 3 x float4 per triangle, read as warp-wide broadcasts) for the brute-force path,
+// or traversed through the GPU-built BVH (bvh.cu) whose nearest-hit result -- including the
+// lowest-index tie-break of the reference's strict '<' loop (kernel.cpp:180-188) -- equals the
+// brute-force loop.
 //
 // Output is a bounce-major SoA (slot = bounce * nrays + ray) so that the 32 lanes of a warp,
 // which sit at the same bounce, write 32 consecutive 32-byte sectors.
@@ -24,12 +34,14 @@ struct TraceParams {
     const uint32_t *order;
     const float4 *dirs;
     uint32_t nrays, nrefl;
+    uint32_t first, last;     // reflections [first, last) handled by this launch
     uint64_t ray_offset;
     float mic[3], src[3];
     float air[RVB_NBANDS];
-    float4 *vol, *pt;      // vol: 2 x float4 per slot
+    float4 *vol, *pt;         // vol: 2 x float4 per slot
     float *tkey;
     uint32_t *hit, *count;
+    float4 *state;            // [4*nrays] (pos, distance) (dir, alive) volA volB
     float4 *cand_volA, *cand_volB, *cand_pt;   // [nrays*10] image-source candidates
     uint32_t *cand_idx;                        // [nrays*10] triangle+1, 0 = none (pre-zeroed)
     unsigned long long *counters;              // [0] queries [1] tri tests [2] box tests [3] bounces
@@ -39,6 +51,7 @@ struct TraceParams {
 struct Counters { uint32_t queries = 0, bounces = 0; unsigned long long tri = 0, box = 0; };
 
 #define RVB_NONE 0xffffffffu
+#define RVB_INF __int_as_float(0x7f800000)
 
 // ---- brute force over the shared-memory scene (kernel.cpp:167-192) ---------------------------
 struct BruteSmem {
@@ -52,7 +65,7 @@ struct BruteSmem {
     }
     __device__ __forceinline__ bool nearest(f3 pos, f3 dir, float &tbest, uint32_t &ibest, Counters &c) const
     {
-        tbest = __int_as_float(0x7f800000);
+        tbest = RVB_INF;
         ibest = RVB_NONE;
 #pragma unroll 4
         for (uint32_t i = 0; i < T; ++i) {
@@ -109,9 +122,9 @@ struct BvhAccel {
     {
         // 1/0 = inf is what the slab test wants for axis-parallel rays
         f3 inv = mk3(__fdividef(1.0f, dir.x), __fdividef(1.0f, dir.y), __fdividef(1.0f, dir.z));
-        if (dir.x == 0.0f) inv.x = __int_as_float(0x7f800000);
-        if (dir.y == 0.0f) inv.y = __int_as_float(0x7f800000);
-        if (dir.z == 0.0f) inv.z = __int_as_float(0x7f800000);
+        if (dir.x == 0.0f) inv.x = RVB_INF;
+        if (dir.y == 0.0f) inv.y = RVB_INF;
+        if (dir.z == 0.0f) inv.z = RVB_INF;
         tbest = tlimit;
         ibest = RVB_NONE;
         int stack[48];
@@ -164,7 +177,7 @@ struct BvhAccel {
     }
     __device__ __forceinline__ bool nearest(f3 pos, f3 dir, float &tbest, uint32_t &ibest, Counters &c) const
     {
-        return traverse<false>(pos, dir, __int_as_float(0x7f800000), tbest, ibest, c);
+        return traverse<false>(pos, dir, RVB_INF, tbest, ibest, c);
     }
     __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
     {
@@ -173,11 +186,28 @@ struct BvhAccel {
     }
 };
 
-// kernel.cpp:195-214: pow(M_E, distance * AIR) * 1
+// kernel.cpp:195-214: pow(M_E, distance * AIR) * 1, with M_E narrowed to float.
+// pow(e_f, x) = 2^(x * log2(e_f)): the product is formed in double-float (hi + lo) so the
+// argument reduction is exact to ~2e-8, then ex2.approx on |r| <= 0.5 (max relative error
+// 2^-22).  Total error <= 2.6e-7 relative, i.e. ~2 ulp -- the same class as powf itself
+// (CUDA documents 4 ulp for powf); volumes are compared with a 2e-6 relative tolerance.
+__device__ __forceinline__ float pow_e(float x)
+{
+    const float L_HI = 1.4426950216293335f;        // float(log2((float)M_E))
+    const float L_LO = -2.4551930266625277e-08f;   // log2((float)M_E) - L_HI
+    const float p_hi = __fmul_rn(x, L_HI);
+    if (!(p_hi > -120.0f && p_hi < 120.0f)) return powf(RVB_M_E_F, x);   // under/overflow range, NaN: library path
+    const float p_lo = __fadd_rn(__fmaf_rn(x, L_HI, -p_hi), __fmul_rn(x, L_LO));
+    const float n = rintf(p_hi);
+    const float r = __fadd_rn(__fsub_rn(p_hi, n), p_lo);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r));
+    return __fmul_rn(e, __int_as_float(((int)n + 127) << 23));
+}
 __device__ __forceinline__ void air_attenuation(float distance, const float *air, float *att)
 {
 #pragma unroll
-    for (int b = 0; b < RVB_NBANDS; ++b) att[b] = powf(RVB_M_E_F, __fmul_rn(distance, air[b]));
+    for (int b = 0; b < RVB_NBANDS; ++b) att[b] = pow_e(__fmul_rn(distance, air[b]));
 }
 
 // kernel.cpp:274-296
@@ -190,11 +220,16 @@ __device__ __forceinline__ bool point_visible(const Accel &acc, f3 begin, f3 poi
     return !acc.occluded(begin, dir, mag, c);
 }
 
-__device__ __forceinline__ TriVerts load_verts(const float4 *verts, uint32_t i)
+// TriVerts with its normal cached: triangle_verts_normal (kernel.cpp:110-116) is a pure function
+// of the three vertices, so evaluating it once per mirrored triangle gives the bits the
+// reference recomputes on every mirror_point call (kernel.cpp:219).
+struct MirrorTri { f3 v0, v1, v2, n; };
+
+// kernel.cpp:217-221: *p += -n * dot(n, *p - t->v0) * 2
+__device__ __forceinline__ f3 mirror_point(f3 p, const MirrorTri &t)
 {
-    TriVerts t;
-    t.v0 = mk3(__ldg(verts + 3 * i)); t.v1 = mk3(__ldg(verts + 3 * i + 1)); t.v2 = mk3(__ldg(verts + 3 * i + 2));
-    return t;
+    const float d = dot(t.n, p - t.v0);
+    return p + ((-t.n) * d) * 2.0f;
 }
 
 // kernel.cpp:243-265
@@ -215,117 +250,183 @@ __device__ __forceinline__ void add_image(const TraceParams &P, f3 mic, f3 mic_r
     P.cand_idx[slot] = object_index;
 }
 
-// kernel.cpp:304-503 for one ray
-template <class Accel>
-__device__ void trace_ray(const Accel &acc, const TraceParams &P, uint32_t ray, Counters &c)
-{
-    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
-    const f3 source = mk3(P.src[0], P.src[1], P.src[2]);
-    f3 ray_pos = source;
-    f3 ray_dir = mk3(__ldg(P.dirs + ray));
-    float distance = 0.0f;
+struct RayState {
+    f3 pos, dir;
+    float distance;
     float volume[RVB_NBANDS];
+};
+
+// kernel.cpp:459-501: everything a reflection does after the nearest hit is known
+template <class Accel>
+__device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceParams &P, f3 mic, uint32_t ray, uint32_t index,
+                                                  float tclosest, uint32_t prim, RayState &R, Counters &c)
+{
+    const f3 X = madd(R.pos, R.dir, tclosest);                               // :459
+    const float newDist = __fadd_rn(R.distance, tclosest);
+    const float4 nrm4 = __ldg(P.nrm + prim);
+    const f3 normal = mk3(nrm4);
+    const float4 *surf = reinterpret_cast<const float4 *>(P.surfaces + __float_as_uint(nrm4.w));
+    const float4 s0 = __ldg(surf), s1 = __ldg(surf + 1), d0 = __ldg(surf + 2), d1 = __ldg(surf + 3);
+    const float spec[RVB_NBANDS] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float diff[RVB_NBANDS] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float newVol[RVB_NBANDS];
 #pragma unroll
-    for (int b = 0; b < RVB_NBANDS; ++b) volume[b] = 1.0f;
-    const bool do_images = !(P.flags & RVB_TRACE_NO_IMAGES);
-    TriVerts prev[RVB_NUM_IMAGE_SOURCE - 1];
-    f3 mic_reflection = mic;
+    for (int b = 0; b < RVB_NBANDS; ++b) newVol[b] = __fmul_rn(-R.volume[b], spec[b]);     // :461
 
-    // Direct path (kernel.cpp:335-357).  Every work-item of the reference computes the same
-    // source->mic query and the host keeps the first ray's copy (rayverb.cpp:667-673); only
-    // global ray 0 needs to do it.
-    if (do_images && P.ray_offset + ray == 0) {
-        if (point_visible(acc, source, mic_reflection, c))
-            add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE, volume, 0u);
-    }
-
-    uint32_t index = 0;
-    for (; index != P.nrefl; ++index) {
-        float tclosest;
-        uint32_t prim;
-        if (!acc.nearest(ray_pos, ray_dir, tclosest, prim, c)) break;           // :363-375
-
-        if (do_images && index < RVB_NUM_IMAGE_SOURCE - 1) {                     // :379-457
-            TriVerts current = load_verts(P.verts, prim);
-            for (uint32_t k = 0; k != index; ++k) {                              // mirror_verts
-                current.v0 = mirror_point(current.v0, prev[k]);
-                current.v1 = mirror_point(current.v1, prev[k]);
-                current.v2 = mirror_point(current.v2, prev[k]);
-            }
-            prev[index] = current;
-            mic_reflection = mirror_point(mic_reflection, current);
-            const f3 DIR = normalize(mic_reflection - source);
-            bool intersects = true;
-            f3 prevI = source;
-            for (uint32_t k = 0; k != index + 1 && intersects; ++k) {
-                const float TO = mt_intersect_verts(prev[k], source, DIR);
-                if (TO <= RVB_EPSILON) { intersects = false; break; }
-                f3 Pt = madd(source, DIR, TO);
-                for (int l = (int)k - 1; l != -1; --l) Pt = mirror_point(Pt, prev[l]);
-                f3 idir = normalize(Pt - prevI);
-                float ti; uint32_t pi;
-                bool hit = acc.nearest(prevI, idir, ti, pi, c);
-                if (!hit) ti = 0.0f;                                              // Intersection{0,0,false}
-                f3 Q = madd(prevI, idir, ti);
-                intersects = hit
-                    && (__fsub_rn(Q.x, RVB_EPSILON) < Pt.x) && (__fsub_rn(Q.y, RVB_EPSILON) < Pt.y) && (__fsub_rn(Q.z, RVB_EPSILON) < Pt.z)
-                    && (Pt.x < __fadd_rn(Q.x, RVB_EPSILON)) && (Pt.y < __fadd_rn(Q.y, RVB_EPSILON)) && (Pt.z < __fadd_rn(Q.z, RVB_EPSILON));
-                prevI = Pt;
-            }
-            if (intersects) intersects = point_visible(acc, prevI, mic, c);
-            if (intersects)   // pre-bounce volume (SURVEY Q1)
-                add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE + index + 1, volume, prim + 1u);
+    const bool vis = point_visible(acc, X, mic, c);                          // :463
+    const float DIST = vis ? __fadd_rn(newDist, length(mic - X)) : 0.0f;     // :471
+    const float DIFF = fabsf(dot(normal, R.dir));                            // :478
+    float out[RVB_NBANDS];
+    bool any = false;
+    if (vis) {
+        float att[RVB_NBANDS];
+        air_attenuation(DIST, P.air, att);
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) {
+            out[b] = __fmul_rn(__fmul_rn(__fmul_rn(newVol[b], att[b]), diff[b]), DIFF);     // :481-485
+            any |= (out[b] != 0.0f);
         }
-
-        const f3 X = madd(ray_pos, ray_dir, tclosest);                          // :459
-        const float newDist = __fadd_rn(distance, tclosest);
-        const float4 nrm4 = __ldg(P.nrm + prim);
-        const f3 normal = mk3(nrm4);
-        const rvb_surface *surf = P.surfaces + __float_as_uint(nrm4.w);
-        float newVol[RVB_NBANDS];
+    } else {
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) newVol[b] = __fmul_rn(-volume[b], __ldg(&surf->specular.s[b]));   // :461
-
-        const bool vis = point_visible(acc, X, mic, c);                          // :463
-        const float DIST = vis ? __fadd_rn(newDist, length(mic - X)) : 0.0f;     // :471
-        const float DIFF = fabsf(dot(normal, ray_dir));                          // :478
-        float out[RVB_NBANDS];
-        bool any = false;
-        if (vis) {
-            float att[RVB_NBANDS];
-            air_attenuation(DIST, P.air, att);
-#pragma unroll
-            for (int b = 0; b < RVB_NBANDS; ++b) {
-                out[b] = __fmul_rn(__fmul_rn(__fmul_rn(newVol[b], att[b]), __ldg(&surf->diffuse.s[b])), DIFF);
-                any |= (out[b] != 0.0f);
-            }
-        } else {
-#pragma unroll
-            for (int b = 0; b < RVB_NBANDS; ++b) out[b] = 0.0f;
-        }
-        const float time = __fmul_rn(RVB_SECONDS_PER_METER, DIST);
-        const size_t slot = (size_t)index * P.nrays + ray;
-        P.vol[2 * slot] = make_float4(out[0], out[1], out[2], out[3]);
-        P.vol[2 * slot + 1] = make_float4(out[4], out[5], out[6], out[7]);
-        P.pt[slot] = make_float4(X.x, X.y, X.z, time);
-        P.tkey[slot] = any ? time : -1.0f;
-        if (P.hit) P.hit[slot] = prim;
-
-        ray_dir = reflect(normal, ray_dir);                                      // :492-499
-        ray_pos = X;
-        distance = newDist;
-#pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) volume[b] = newVol[b];
+        for (int b = 0; b < RVB_NBANDS; ++b) out[b] = 0.0f;
     }
-    c.bounces += index;
-    if (P.count) P.count[ray] = index;
-    // a ray that left the mesh keeps zero impulses in its remaining slots (rayverb.cpp:601-603)
+    const float time = __fmul_rn(RVB_SECONDS_PER_METER, DIST);               // :489
+    const size_t slot = (size_t)index * P.nrays + ray;
+    P.vol[2 * slot] = make_float4(out[0], out[1], out[2], out[3]);
+    P.vol[2 * slot + 1] = make_float4(out[4], out[5], out[6], out[7]);
+    P.pt[slot] = make_float4(X.x, X.y, X.z, time);
+    P.tkey[slot] = any ? time : -1.0f;
+    if (P.hit) P.hit[slot] = prim;
+
+    R.dir = reflect(normal, R.dir);                                          // :492-499
+    R.pos = X;
+    R.distance = newDist;
+#pragma unroll
+    for (int b = 0; b < RVB_NBANDS; ++b) R.volume[b] = newVol[b];
+}
+
+// a ray that left the mesh keeps zero impulses in its remaining slots (rayverb.cpp:601-603)
+__device__ __forceinline__ void zero_fill(const TraceParams &P, uint32_t ray, uint32_t index)
+{
     for (; index != P.nrefl; ++index) {
         const size_t slot = (size_t)index * P.nrays + ray;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         P.vol[2 * slot] = z; P.vol[2 * slot + 1] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
         if (P.hit) P.hit[slot] = RVB_NONE;
     }
+}
+
+__device__ __forceinline__ void store_state(const TraceParams &P, uint32_t ray, const RayState &R, bool alive)
+{
+    float4 *s = P.state + 4 * (size_t)ray;
+    s[0] = make_float4(R.pos.x, R.pos.y, R.pos.z, R.distance);
+    s[1] = make_float4(R.dir.x, R.dir.y, R.dir.z, alive ? 1.0f : 0.0f);
+    s[2] = make_float4(R.volume[0], R.volume[1], R.volume[2], R.volume[3]);
+    s[3] = make_float4(R.volume[4], R.volume[5], R.volume[6], R.volume[7]);
+}
+
+// Reflections [0, P.last) WITH the image-source branch (kernel.cpp:379-457); P.last <= 9.
+template <class Accel>
+__device__ void image_phase_ray(const Accel &acc, const TraceParams &P, uint32_t ray, Counters &c)
+{
+    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+    const f3 source = mk3(P.src[0], P.src[1], P.src[2]);
+    RayState R;
+    R.pos = source;
+    R.dir = mk3(__ldg(P.dirs + ray));
+    R.distance = 0.0f;
+#pragma unroll
+    for (int b = 0; b < RVB_NBANDS; ++b) R.volume[b] = 1.0f;
+    MirrorTri prev[RVB_NUM_IMAGE_SOURCE - 1];
+    f3 mic_reflection = mic;
+
+    // Direct path (kernel.cpp:335-357).  Every work-item of the reference computes the same
+    // source->mic query and the host keeps the first ray's copy (rayverb.cpp:667-673); only
+    // global ray 0 needs to do it.
+    if (P.ray_offset + ray == 0) {
+        if (point_visible(acc, source, mic_reflection, c))
+            add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE, R.volume, 0u);
+    }
+
+    uint32_t index = 0;
+    bool alive = true;
+    for (; index != P.last; ++index) {
+        float tclosest;
+        uint32_t prim;
+        if (!acc.nearest(R.pos, R.dir, tclosest, prim, c)) { alive = false; break; }   // :363-375
+
+        {   // index < NUM_IMAGE_SOURCE - 1 holds for every reflection of this kernel (:379)
+            MirrorTri cur;
+            cur.v0 = mk3(__ldg(P.verts + 3 * prim)); cur.v1 = mk3(__ldg(P.verts + 3 * prim + 1)); cur.v2 = mk3(__ldg(P.verts + 3 * prim + 2));
+            for (uint32_t k = 0; k != index; ++k) {                              // mirror_verts, :387-390
+                cur.v0 = mirror_point(cur.v0, prev[k]);
+                cur.v1 = mirror_point(cur.v1, prev[k]);
+                cur.v2 = mirror_point(cur.v2, prev[k]);
+            }
+            cur.n = normalize(cross(cur.v1 - cur.v0, cur.v2 - cur.v0));
+            prev[index] = cur;
+            mic_reflection = mirror_point(mic_reflection, cur);                  // :394
+            const f3 DIR = normalize(mic_reflection - source);                   // :396
+            bool intersects = true;
+            f3 prevI = source;
+            for (uint32_t k = 0; k != index + 1 && intersects; ++k) {            // :401
+                const MirrorTri &pk = prev[k];
+                const float TO = mt_intersect(pk.v0, pk.v1 - pk.v0, pk.v2 - pk.v0, source, DIR);
+                if (TO <= RVB_EPSILON) { intersects = false; break; }            // :405
+                f3 Pt = madd(source, DIR, TO);                                   // :411
+                for (int l = (int)k - 1; l != -1; --l) Pt = mirror_point(Pt, prev[l]);
+                f3 idir = normalize(Pt - prevI);                                 // :417
+                float ti; uint32_t pi;
+                bool hit = acc.nearest(prevI, idir, ti, pi, c);
+                if (!hit) ti = 0.0f;                                             // Intersection{0,0,false}
+                f3 Q = madd(prevI, idir, ti);                                    // :425
+                intersects = hit
+                    && (__fsub_rn(Q.x, RVB_EPSILON) < Pt.x) && (__fsub_rn(Q.y, RVB_EPSILON) < Pt.y) && (__fsub_rn(Q.z, RVB_EPSILON) < Pt.z)
+                    && (Pt.x < __fadd_rn(Q.x, RVB_EPSILON)) && (Pt.y < __fadd_rn(Q.y, RVB_EPSILON)) && (Pt.z < __fadd_rn(Q.z, RVB_EPSILON));
+                prevI = Pt;
+            }
+            if (intersects) intersects = point_visible(acc, prevI, mic, c);      // :431
+            if (intersects)   // pre-bounce volume (SURVEY Q1)
+                add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE + index + 1, R.volume, prim + 1u);
+        }
+        shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c);
+    }
+    c.bounces += index;
+    if (P.count) P.count[ray] = index;
+    if (!alive) zero_fill(P, ray, index);
+    if (P.last < P.nrefl) store_state(P, ray, R, alive);
+}
+
+// Reflections [P.first, P.last) without image sources: the steady state of the reference loop.
+template <class Accel>
+__device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TraceParams &P, uint32_t ray, Counters &c)
+{
+    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+    RayState R;
+    if (P.first == 0) {
+        R.pos = mk3(P.src[0], P.src[1], P.src[2]);
+        R.dir = mk3(__ldg(P.dirs + ray));
+        R.distance = 0.0f;
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) R.volume[b] = 1.0f;
+    } else {
+        const float4 *s = P.state + 4 * (size_t)ray;
+        const float4 a = s[0], d = s[1], va = s[2], vb = s[3];
+        if (d.w == 0.0f) return;   // left the mesh during the image phase (slots already zero-filled)
+        R.pos = mk3(a); R.distance = a.w; R.dir = mk3(d);
+        R.volume[0] = va.x; R.volume[1] = va.y; R.volume[2] = va.z; R.volume[3] = va.w;
+        R.volume[4] = vb.x; R.volume[5] = vb.y; R.volume[6] = vb.z; R.volume[7] = vb.w;
+    }
+    uint32_t index = P.first;
+    for (; index != P.last; ++index) {
+        float tclosest;
+        uint32_t prim;
+        if (!acc.nearest(R.pos, R.dir, tclosest, prim, c)) break;                // :363-375
+        shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c);
+    }
+    c.bounces += index - P.first;
+    if (P.count) P.count[ray] = (P.first ? P.count[ray] : 0u) + (index - P.first);
+    if (index != P.last) zero_fill(P, ray, index);
 }
 
 __device__ __forceinline__ void flush_counters(const TraceParams &P, const Counters &c)
@@ -342,25 +443,48 @@ __device__ __forceinline__ void flush_counters(const TraceParams &P, const Count
     }
 }
 
+__device__ __forceinline__ void stage_scene(float4 *s_tri, const TraceParams &P)
+{
+    for (uint32_t i = threadIdx.x; i < 3 * P.T; i += blockDim.x) s_tri[i] = P.tri[i];
+    __syncthreads();
+}
+
+template <bool IMAGES>
 __global__ void __launch_bounds__(256) trace_bruteforce_kernel(const TraceParams P)
 {
     extern __shared__ float4 s_tri[];
-    for (uint32_t i = threadIdx.x; i < 3 * P.T; i += blockDim.x) s_tri[i] = P.tri[i];
-    __syncthreads();
+    stage_scene(s_tri, P);
     BruteSmem acc{s_tri, P.T};
     Counters c;
-    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x)
-        trace_ray(acc, P, ray, c);
+    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x) {
+        if (IMAGES) image_phase_ray(acc, P, ray, c); else steady_phase_ray(acc, P, ray, c);
+    }
     flush_counters(P, c);
 }
 
+template <bool IMAGES>
 __global__ void __launch_bounds__(128) trace_bvh_kernel(const TraceParams P)
 {
     BvhAccel acc{P.nodes, P.tri_sorted, P.order};
     Counters c;
-    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x)
-        trace_ray(acc, P, ray, c);
+    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x) {
+        if (IMAGES) image_phase_ray(acc, P, ray, c); else steady_phase_ray(acc, P, ray, c);
+    }
     flush_counters(P, c);
+}
+
+template <class K>
+static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, cudaStream_t st)
+{
+    RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    if (per_sm < 1) return fail(RVB_ERR_INVALID, "scene does not fit in shared memory for the brute-force kernel");
+    const size_t want = ((size_t)P.nrays + block - 1) / block;
+    const size_t grid = std::min(want, (size_t)per_sm * sm_count());
+    note_launch(), kernel<<<(unsigned)grid, block, smem, st>>>(P);
+    RVB_CUDA(cudaGetLastError());
+    return RVB_OK;
 }
 
 int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB, float4 *d_cand_pt,
@@ -386,31 +510,34 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     RVB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), st));
     P.counters = d_counters;
 
-    const int nsm = sm_count();
+    const bool images = !(tr->flags & RVB_TRACE_NO_IMAGES);
+    const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
+    float4 *d_state = nullptr;
+    if (split > 0 && split < tr->nrefl) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
+    P.state = d_state;
+    const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
+    const size_t smem = brute ? (size_t)3 * sc->T * sizeof(float4) : 0;
+
     cudaEvent_t e0, e1;
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
     RVB_CUDA(cudaEventRecord(e0, st));
-    if (tr->nrays > 0) {
-        if (sc->accel == RVB_ACCEL_BRUTE_FORCE) {
-            const int block = 256;
-            size_t smem = (size_t)3 * sc->T * sizeof(float4);
-            RVB_CUDA(cudaFuncSetAttribute(trace_bruteforce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0;
-            RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_bruteforce_kernel, block, smem));
-            if (per_sm < 1) return fail(RVB_ERR_INVALID, "scene does not fit in shared memory for the brute-force kernel");
-            size_t want = (tr->nrays + block - 1) / block;
-            size_t grid = std::min(want, (size_t)per_sm * nsm);
-            note_launch(), trace_bruteforce_kernel<<<(unsigned)grid, block, smem, st>>>(P);
-        } else {
-            const int block = 128;
-            int per_sm = 0;
-            RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_bvh_kernel, block, 0));
-            size_t want = (tr->nrays + block - 1) / block;
-            size_t grid = std::min(want, (size_t)std::max(per_sm, 1) * nsm);
-            note_launch(), trace_bvh_kernel<<<(unsigned)grid, block, 0, st>>>(P);
+    if (tr->nrays > 0 && tr->nrefl > 0) {
+        if (split > 0) {
+            P.first = 0; P.last = split;
+            if (brute) RVB_TRY(launch_phase(trace_bruteforce_kernel<true>, P, 256, smem, st));
+            else RVB_TRY(launch_phase(trace_bvh_kernel<true>, P, 128, 0, st));
         }
-        RVB_CUDA(cudaGetLastError());
+        if (split < tr->nrefl) {
+            P.first = split; P.last = (uint32_t)tr->nrefl;
+            if (brute) RVB_TRY(launch_phase(trace_bruteforce_kernel<false>, P, 256, smem, st));
+            else RVB_TRY(launch_phase(trace_bvh_kernel<false>, P, 128, 0, st));
+        }
+    } else if (tr->nrays > 0 && images && tr->ray_offset == 0) {
+        // zero reflections: the reference still computes the direct path for ray 0
+        P.first = 0; P.last = 0;
+        if (brute) RVB_TRY(launch_phase(trace_bruteforce_kernel<true>, P, 256, smem, st));
+        else RVB_TRY(launch_phase(trace_bvh_kernel<true>, P, 128, 0, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
     unsigned long long h[4];
@@ -420,6 +547,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     dev_free(d_counters);
+    dev_free(d_state);
     tr->stats.queries = h[0]; tr->stats.tri_tests = h[1]; tr->stats.box_tests = h[2]; tr->stats.bounces = h[3];
     tr->stats.trace_kernel_ms = ms;
     return RVB_OK;
