@@ -127,7 +127,7 @@ struct BvhAccel {
         if (dir.z == 0.0f) inv.z = RVB_INF;
         tbest = tlimit;
         ibest = RVB_NONE;
-        int stack[48];
+        int stack[64];
         int sp = 0;
         int node = 0;
         uint32_t nbox = 0, ntri = 0;

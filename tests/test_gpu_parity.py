@@ -231,3 +231,49 @@ def test_host_array_postprocessing_vs_oracle(orc):
     for a, b in zip(out, ref):
         assert len(a) == len(b)
         assert_filter_close(a, b, "process")
+
+
+# ---- BVH path: must equal the brute-force loop (kernel.cpp:167-192) including its tie-break -----
+def test_bvh_small_room_vs_oracle(orc):
+    tri, vtx = scenes.displaced_box(8.0, 3.0, 5.0, 700, amp=0.08, fan=0.2, nsurfaces=4)
+    srf = scenes.hall_surfaces()
+    dirs = scenes.sphere_directions(1500, seed=9)
+    check_trace_against_oracle(orc, tri, vtx, srf, (5.5, 1.2, 3.5), (2, 1.5, 2), dirs, 24, api.ACCEL_BVH)
+
+
+def test_bvh_shoebox_and_diamond_vs_oracle(orc):
+    """Large axis-aligned triangles (boxes as big as the scene, rays parallel to faces)."""
+    tri, vtx, srf = scenes.shoebox()
+    check_trace_against_oracle(orc, tri, vtx, srf, (7, 2, 4), (2, 1.5, 2), scenes.sphere_directions(2000, seed=1), 30, api.ACCEL_BVH)
+    tri, vtx, srf = scenes.diamond_room()
+    check_trace_against_oracle(orc, tri, vtx, srf, (0, 2, 0), (0, 2, 2), kat_directions(300), 20, api.ACCEL_BVH)
+
+
+def test_bvh_equals_bruteforce_kernel_4k_triangles():
+    """GPU brute force (shared-memory scene) is the intermediate oracle at sizes the CPU cannot
+    sweep: same hits, counts, positions, times and bit-identical volumes (same device arithmetic)."""
+    tri, vtx = scenes.displaced_box(20.0, 8.0, 14.0, 4400, amp=0.1, fan=0.25, nsurfaces=4)
+    assert len(tri) <= 4843
+    srf = scenes.hall_surfaces()
+    dirs = scenes.sphere_directions(20000, seed=21)
+    out = {}
+    for name, accel in (("bf", api.ACCEL_BRUTE_FORCE), ("bvh", api.ACCEL_BVH)):
+        rt = api.Raytracer(48, tri, vtx, srf, accel=accel)
+        tr = rt.raytrace((12, 1.5, 9), (6, 2, 3), dirs, flags=api.TRACE_DEBUG)
+        out[name] = (tr.debug(), tr.raw_diffuse(), tr.raw_images(with_keys=True), tr.stats())
+        rt.close()
+    (hit_a, cnt_a), d_a, (img_a, k_a, l_a), st_a = out["bf"]
+    (hit_b, cnt_b), d_b, (img_b, k_b, l_b), st_b = out["bvh"]
+    assert np.array_equal(cnt_a, cnt_b) and np.array_equal(hit_a, hit_b)
+    assert d_a.tobytes() == d_b.tobytes()
+    assert np.array_equal(k_a, k_b) and np.array_equal(l_a, l_b) and img_a.tobytes() == img_b.tobytes()
+    assert st_b["tri_tests"] < st_a["tri_tests"] / 20          # the BVH actually culls
+    assert st_a["queries"] == st_b["queries"]
+
+
+def test_bvh_hall_100k_subsample_vs_oracle(orc):
+    """C3 mesh (~100k triangles): a ray subsample against the CPU brute-force oracle."""
+    tri, vtx, srf = scenes.concert_hall()
+    assert 95_000 < len(tri) < 105_000
+    dirs = scenes.sphere_directions(48, seed=2015)
+    check_trace_against_oracle(orc, tri, vtx, srf, (24, 1.5, 18), (20, 2.0, 4), dirs, 12, api.ACCEL_AUTO)
