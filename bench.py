@@ -159,7 +159,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from rayverb_b200 import api, scenes
+    from rayverb_b200 import api, scenes, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,25 +198,8 @@ def main():
             state["render"] = api.render_stats()
             return ir
         # ---- sharded: global predelay/lengths, cross-shard image merge, one NCCL reduce ----------
-        mn, mx = tr.render_times(cfg)
-        t = torch.tensor([[(x if x != 0 else math.inf) for x in mn], [-x for x in mx]], device="cuda", dtype=torch.float32)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        gmx = (-t[1]).tolist()
-        # round(maxtime * sr) + 1 in float arithmetic, half away from zero (rayverb.cpp:57)
-        lengths = [int(math.floor(float(np.float32(m) * np.float32(44100.0)) + 0.5)) + 1 for m in gmx]
-        img, keys, klen = tr.raw_images(with_keys=True)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (img, keys, klen))
-        if rank == 0:
-            merged, _, _ = api.images_merge(np.concatenate([g[0] for g in gathered]), np.concatenate([g[1] for g in gathered]),
-                                            np.concatenate([g[2] for g in gathered]))
-            tr.set_images(merged)
-        else:
-            tr.set_images(np.zeros(0, dtype=api.IMPULSE))
-        hist = torch.empty(sum(8 * l for l in lengths), device="cuda", dtype=torch.float32)
-        tr.render_histogram(cfg, 0.0, lengths, hist.data_ptr())
+        hist, lengths, _ = sharding.sharded_histogram(tr, cfg, rank, world, "cuda", 44100.0, False)
         state["render"] = api.render_stats()
-        dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
         if rank == 0:
             return api.render_finish(cfg, hist.data_ptr(), lengths)
         return None

@@ -189,7 +189,10 @@ int rvb_render_finish(const rvb_render_config *cfg, const float *d_hist, const s
 int rvb_ir_channels(const rvb_ir *ir, size_t *nchannels);
 int rvb_ir_length(const rvb_ir *ir, size_t channel, size_t *length);
 int rvb_ir_copy(const rvb_ir *ir, size_t channel, float *out);
-/* per-band data before mixdown, [8][band_length] for `channel` (parity checks) */
+/* per-band data before mixdown, [8][band_length] for `channel` (parity checks); only kept when
+ * rvb_render_keep_bands(1) was called on this thread before the render (default off: it costs a
+ * device-to-host copy of 8x the IR) */
+int rvb_render_keep_bands(int on);
 int rvb_ir_band_length(const rvb_ir *ir, size_t channel, size_t *length);
 int rvb_ir_copy_bands(const rvb_ir *ir, size_t channel, float *out);
 int rvb_ir_destroy(rvb_ir *ir);

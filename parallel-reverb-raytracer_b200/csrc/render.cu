@@ -664,9 +664,15 @@ static size_t flatten_length(float maxtime, float predelay, bool fix, float sr)
 
 using namespace rvb;
 
-static bool g_keep_bands = true;
+static thread_local bool g_keep_bands = false;
 
 extern "C" {
+
+int rvb_render_keep_bands(int on)
+{
+    g_keep_bands = on != 0;
+    return RVB_OK;
+}
 
 int rvb_render_get_stats(rvb_render_stats *stats)
 {

@@ -57,7 +57,7 @@ EXPORTS = [
     "rvb_flatten", "rvb_filter", "rvb_process", "rvb_free",
     "rvb_render_ir", "rvb_render_times", "rvb_render_histogram", "rvb_render_finish",
     "rvb_ir_channels", "rvb_ir_length", "rvb_ir_copy", "rvb_ir_band_length", "rvb_ir_copy_bands", "rvb_ir_destroy",
-    "rvb_render_get_stats",
+    "rvb_render_get_stats", "rvb_render_keep_bands",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def lib():
         L.rvb_ir_copy_bands.argtypes = [vp, sz, vp]
         L.rvb_ir_destroy.argtypes = [vp]
         L.rvb_render_get_stats.argtypes = [vp]
+        L.rvb_render_keep_bands.argtypes = [i32]
         _lib = L
     return _lib
 
@@ -262,8 +263,10 @@ class Trace:
 
     def render_ir(self, **kw):
         """Fused attenuate -> fixPredelay -> flattenImpulses -> process on the device."""
+        keep_bands = kw.pop("keep_bands", False)
         cfg, keep = make_render_config(**kw)
         h = C.c_void_p()
+        lib().rvb_render_keep_bands(int(keep_bands))
         _check(lib().rvb_render_ir(self._h, C.byref(cfg), C.byref(h)))
         del keep
         return Ir(h)
@@ -284,6 +287,7 @@ class Trace:
 def render_finish(cfg, d_hist_ptr, lengths):
     ln = np.asarray(lengths, dtype=np.uint64)
     h = C.c_void_p()
+    lib().rvb_render_keep_bands(0)
     _check(lib().rvb_render_finish(C.byref(cfg), C.c_void_p(d_hist_ptr), _p(ln), len(ln), C.byref(h)))
     return Ir(h)
 

@@ -165,7 +165,7 @@ def test_trace_displaced_room_vs_oracle(orc):
 def _render_case(orc, tri, vtx, srf, mic, src, dirs, nrefl, accel, **kw):
     rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
     tr = rt.raytrace(mic, src, dirs)
-    ir = tr.render_ir(**kw)
+    ir = tr.render_ir(keep_bands=True, **kw)
     okw = dict(kw)
     ref, flat, bands = orc.render_ir(tri, vtx, srf, mic, src, dirs, nrefl, return_bands=True, **okw)
     assert len(ir.channels) == len(ref)
