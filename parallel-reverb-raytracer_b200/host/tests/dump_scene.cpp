@@ -1,0 +1,28 @@
+// dump_scene <model.obj> <materials.json> <out.bin>: runs the host scene loader and writes
+// T, V, S (u64) followed by Triangle[T], cl_float3[V], Surface[S].  CPU only; used by the tests to
+// compare the C++ loader with the Python one.
+#include "rayverb.h"
+
+#include <fstream>
+
+int main (int argc, char ** argv)
+{
+    if (argc != 4) return 2;
+    try
+    {
+        std::vector <Triangle> t; std::vector <cl_float3> v; std::vector <Surface> s;
+        loadScene (argv [1], argv [2], false, t, v, s);
+        std::ofstream f (argv [3], std::ios::binary);
+        const uint64_t hdr [3] = {t.size(), v.size(), s.size()};
+        f.write ((const char *) hdr, sizeof hdr);
+        f.write ((const char *) t.data(), t.size() * sizeof (Triangle));
+        f.write ((const char *) v.data(), v.size() * sizeof (cl_float3));
+        f.write ((const char *) s.data(), s.size() * sizeof (Surface));
+    }
+    catch (const std::exception & e)
+    {
+        std::cerr << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

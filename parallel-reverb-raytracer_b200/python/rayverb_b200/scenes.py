@@ -178,8 +178,7 @@ def _ear_clip(poly3d):
         a, b = p[i], p[(i + 1) % n]
         nrm += np.array([(a[1] - b[1]) * (a[2] + b[2]), (a[2] - b[2]) * (a[0] + b[0]), (a[0] - b[0]) * (a[1] + b[1])])
     ax = int(np.argmax(np.abs(nrm)))
-    keep = [i for i in range(3) if i != ax]
-    q = p[:, keep]
+    q = p[:, [(ax + 1) % 3, (ax + 2) % 3]]     # cyclic order keeps the polygon's orientation
     if nrm[ax] < 0:
         q = q[:, ::-1]
 
@@ -193,7 +192,8 @@ def _ear_clip(poly3d):
         guard += 1
         m = len(idx)
         clipped = False
-        for k in range(m):
+        for kk in range(m):
+            k = (kk + 1) % m     # start at corner 1: a convex polygon comes out as a fan around vertex 0
             i0, i1, i2 = idx[(k - 1) % m], idx[k], idx[(k + 1) % m]
             if cross2(q[i0], q[i1], q[i2]) <= 1e-12:
                 continue
