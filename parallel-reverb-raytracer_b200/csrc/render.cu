@@ -114,37 +114,39 @@ __global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bo
     }
 }
 
-// segment bounds of every bin in the sorted key array
-__global__ void bounds_kernel(const uint32_t *keys, uint32_t n, uint32_t L, uint32_t *seg_begin, uint32_t *seg_end)
+// The sort may ignore the low `shift` bits of the sample index (one radix pass fewer): a segment
+// then holds 2^shift adjacent bins, interleaved in impulse order, and the reduction separates them
+// by the key's low bits.  Segment bounds in the sorted key array:
+__global__ void bounds_kernel(const uint32_t *keys, uint32_t n, uint32_t nseg, uint32_t shift, uint32_t *seg_begin, uint32_t *seg_end)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t k = keys[i];
-        if (k >= L) continue;
-        if (i == 0 || keys[i - 1] != k) seg_begin[k] = i;
-        if (i + 1 == n || keys[i + 1] != k) seg_end[k] = i + 1;
+        const uint32_t sg = keys[i] >> shift;
+        if (sg >= nseg) continue;   // sentinel-only tail
+        if (i == 0 || (keys[i - 1] >> shift) != sg) seg_begin[sg] = i;
+        if (i + 1 == n || (keys[i + 1] >> shift) != sg) seg_end[sg] = i + 1;
     }
 }
 
-// One warp per bin: lane l takes entries begin+l, begin+l+32, ... in order (four gathers in
-// flight per lane), then a fixed xor-shuffle tree combines the 32 partial sums.
-// hist layout: [channel][band][L].
-template <int MODEL, bool NEED_POS>
-__device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &C, uint32_t i, float4 va, float4 vb,
-                                               float (&acc)[RVB_MAX_GROUP][RVB_NBANDS])
+// One warp per segment: lane l takes entries begin+l, begin+l+32, ... in order (four gathers in
+// flight per lane), then a fixed xor-shuffle tree combines the 32 partial sums of every
+// (sub-bin, channel, band).  hist layout: [channel][band][L].
+// NSUB sub-bins x MAXC channels <= RVB_MAX_GROUP accumulator sets.
+template <int MODEL, bool NEED_POS, int NSUB, int MAXC>
+__device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &C, uint32_t i, uint32_t sub, float4 va, float4 vb,
+                                               float (&acc)[NSUB][MAXC][RVB_NBANDS])
 {
     const float v[RVB_NBANDS] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    float term[MAXC][RVB_NBANDS];
     if (MODEL == 0) {
         f3 pos = mk3(0.f, 0.f, 0.f);
         if (NEED_POS) pos = mk3(S.pos_time(i));
 #pragma unroll
-        for (int c = 0; c < RVB_MAX_GROUP; ++c) {
-            if (c < C.nch) {
-                // coefficient 0 (omni): (1 - 0) + 0 * d == 1 exactly for every finite d, so the
-                // position is not needed
-                const float g = NEED_POS ? speaker_gain(C.mic, pos, C.sdir[c], C.coef[c]) : 1.0f;
+        for (int c = 0; c < MAXC; ++c) {
+            // coefficient 0 (omni): (1 - 0) + 0 * d == 1 exactly for every finite d, so the
+            // position is not needed
+            const float g = (NEED_POS && c < C.nch) ? speaker_gain(C.mic, pos, C.sdir[c], C.coef[c]) : 1.0f;
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[c][b] = __fadd_rn(acc[c][b], __fmul_rn(v[b], g));
-            }
+            for (int b = 0; b < RVB_NBANDS; ++b) term[c][b] = __fmul_rn(v[b], g);
         }
     } else if (MODEL == 1) {
         const f3 pos = mk3(S.pos_time(i));
@@ -152,54 +154,86 @@ __device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &
         const float4 ga = __ldg(C.table + 2 * idx), gb = __ldg(C.table + 2 * idx + 1);
         const float g[RVB_NBANDS] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], __fmul_rn(v[b], g[b]));
+        for (int b = 0; b < RVB_NBANDS; ++b) term[0][b] = __fmul_rn(v[b], g[b]);
     } else {
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) acc[0][b] = __fadd_rn(acc[0][b], v[b]);
+        for (int b = 0; b < RVB_NBANDS; ++b) term[0][b] = v[b];
     }
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s)
+        if (NSUB == 1 || s == (int)sub) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = __fadd_rn(acc[s][c][b], term[c][b]);
+        }
 }
 
-template <int MODEL, bool NEED_POS>
-__global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *vals, const uint32_t *seg_begin,
-                                                     const uint32_t *seg_end, uint32_t L, float *hist, size_t chan_stride)
+template <int MODEL, bool NEED_POS, int NSUB, int MAXC>
+__global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *keys, const uint32_t *vals,
+                                                     const uint32_t *seg_begin, const uint32_t *seg_end, uint32_t nseg, uint32_t L,
+                                                     float *hist, size_t chan_stride)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    // bins are handed out from the END of the response first: late bins hold the most impulses
-    for (uint32_t w = warp; w < L; w += nwarps) {
-        const uint32_t bin = L - 1 - w;
-        const uint32_t b0 = seg_begin[bin], b1 = seg_end[bin];
+    // segments are handed out from the END of the response first: late bins hold the most impulses
+    for (uint32_t w = warp; w < nseg; w += nwarps) {
+        const uint32_t seg = nseg - 1 - w;
+        const uint32_t b0 = seg_begin[seg], b1 = seg_end[seg];
         if (b0 == b1) continue;   // warp-uniform
-        float acc[RVB_MAX_GROUP][RVB_NBANDS];
+        float acc[NSUB][MAXC][RVB_NBANDS];
 #pragma unroll
-        for (int c = 0; c < RVB_MAX_GROUP; ++c)
+        for (int s = 0; s < NSUB; ++s)
 #pragma unroll
-            for (int b = 0; b < RVB_NBANDS; ++b) acc[c][b] = 0.0f;
+            for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0f;
         for (uint32_t j = b0 + lane; j < b1; j += 128) {
-            uint32_t idx[4];
+            uint32_t idx[4], sub[4];
             float4 va[4], vb[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) idx[u] = (j + 32 * u < b1) ? vals[j + 32 * u] : RVB_NO_IMPULSE;
+            for (int u = 0; u < 4; ++u) {
+                idx[u] = RVB_NO_IMPULSE; sub[u] = 0;
+                if (j + 32 * u < b1) {
+                    idx[u] = vals[j + 32 * u];
+                    if (NSUB > 1) {
+                        const uint32_t k = keys[j + 32 * u];
+                        if (k >= L) idx[u] = RVB_NO_IMPULSE;   // skipped impulses share the last segment
+                        sub[u] = k & (NSUB - 1);
+                    }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (idx[u] != RVB_NO_IMPULSE) S.volume(idx[u], va[u], vb[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (idx[u] != RVB_NO_IMPULSE) accumulate_one<MODEL, NEED_POS>(S, C, idx[u], va[u], vb[u], acc);
+                if (idx[u] != RVB_NO_IMPULSE) accumulate_one<MODEL, NEED_POS, NSUB, MAXC>(S, C, idx[u], sub[u], va[u], vb[u], acc);
         }
 #pragma unroll
-        for (int c = 0; c < RVB_MAX_GROUP; ++c) {
-            if (c < C.nch) {
+        for (int s = 0; s < NSUB; ++s) {
+            const uint32_t bin = seg * NSUB + s;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
 #pragma unroll
                 for (int b = 0; b < RVB_NBANDS; ++b) {
-                    float x = acc[c][b];
+                    float x = acc[s][c][b];
                     for (int o = 16; o; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
-                    if (lane == 0) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = x;
+                    if (lane == 0 && c < C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = x;
                 }
             }
         }
     }
+}
+
+template <int MODEL, bool NEED_POS>
+static void launch_reduce(int nsub, unsigned grid, cudaStream_t st, const Source &S, const ChanSpec &C, const uint32_t *keys,
+                          const uint32_t *vals, const uint32_t *b, const uint32_t *e, uint32_t nseg, uint32_t L, float *dst, size_t stride)
+{
+    if (nsub == 4) reduce_kernel<MODEL, NEED_POS, 4, 1><<<grid, 256, 0, st>>>(S, C, keys, vals, b, e, nseg, L, dst, stride);
+    else if (nsub == 2) reduce_kernel<MODEL, NEED_POS, 2, 2><<<grid, 256, 0, st>>>(S, C, keys, vals, b, e, nseg, L, dst, stride);
+    else reduce_kernel<MODEL, NEED_POS, 1, RVB_MAX_GROUP><<<grid, 256, 0, st>>>(S, C, keys, vals, b, e, nseg, L, dst, stride);
 }
 
 // ---- band filters (filters.cpp:156-191): TDF-II biquad, double state, float store per sample ----
@@ -480,8 +514,8 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
     uint8_t *d_tmp = nullptr;
     for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_keys[i], n)); RVB_TRY(dev_alloc(&d_vals[i], n)); }
     int last_group = -1;
-    uint32_t L = 0;
-    int cur = 0;
+    uint32_t L = 0, nseg = 0;
+    int cur = 0, shift = 0;
     for (size_t p = 0; p < cs.passes.size(); ++p) {
         const ChanSpec &C = cs.passes[p];
         const size_t c0 = cs.pass_first_channel[p];
@@ -498,19 +532,25 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             Timer ts(st);
             int end_bit = 1;
             while ((1ull << end_bit) <= (unsigned long long)L) ++end_bit;   // keys in [0, L]
+            // drop low key bits from the sort when that saves an 8-bit radix pass (see bounds_kernel)
+            const int max_shift = C.nch == 1 ? 2 : (C.nch == 2 ? 1 : 0);
+            shift = 0;
+            for (int sft = 1; sft <= max_shift; ++sft)
+                if ((end_bit - sft + 7) / 8 < (end_bit + 7) / 8) { shift = sft; break; }
+            nseg = ((L - 1) >> shift) + 1;
             cub::DoubleBuffer<uint32_t> kb(d_keys[0], d_keys[1]), vb(d_vals[0], d_vals[1]);
             size_t bytes = 0;
-            RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, 0, end_bit, st));
+            RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, shift, end_bit, st));
             dev_free(d_tmp);
             RVB_TRY(dev_alloc(&d_tmp, bytes));
-            RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, 0, end_bit, st));
+            RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, shift, end_bit, st));
             cur = kb.selector;
             if (vb.selector != cur) return fail(RVB_ERR_CUDA, "radix sort buffers diverged");
             dev_free(d_begin); dev_free(d_end);
-            RVB_TRY(dev_alloc(&d_begin, (size_t)L + 1)); RVB_TRY(dev_alloc(&d_end, (size_t)L + 1));
-            RVB_CUDA(cudaMemsetAsync(d_begin, 0, ((size_t)L + 1) * sizeof(uint32_t), st));
-            RVB_CUDA(cudaMemsetAsync(d_end, 0, ((size_t)L + 1) * sizeof(uint32_t), st));
-            note_launch(), bounds_kernel<<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, L, d_begin, d_end);
+            RVB_TRY(dev_alloc(&d_begin, (size_t)nseg)); RVB_TRY(dev_alloc(&d_end, (size_t)nseg));
+            RVB_CUDA(cudaMemsetAsync(d_begin, 0, (size_t)nseg * sizeof(uint32_t), st));
+            RVB_CUDA(cudaMemsetAsync(d_end, 0, (size_t)nseg * sizeof(uint32_t), st));
+            note_launch(), bounds_kernel<<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, nseg, (uint32_t)shift, d_begin, d_end);
             g_stats.sort_ms += ts.stop();
         }
         Timer tr_(st);
@@ -521,10 +561,11 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             bool need_pos = false;
             for (int c = 0; c < C.nch; ++c) need_pos |= (C.coef[c] != 0.0f);
             note_launch();
-            if (C.model == 0 && need_pos) reduce_kernel<0, true><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
-            else if (C.model == 0) reduce_kernel<0, false><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
-            else if (C.model == 1) reduce_kernel<1, true><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
-            else reduce_kernel<2, false><<<rgrid, 256, 0, st>>>(S, C, d_vals[cur], d_begin, d_end, L, dst, stride);
+            const int nsub = 1 << shift;
+            if (C.model == 0 && need_pos) launch_reduce<0, true>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else if (C.model == 0) launch_reduce<0, false>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else if (C.model == 1) launch_reduce<1, true>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else launch_reduce<2, false>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
         }
         RVB_CUDA(cudaGetLastError());
         g_stats.reduce_ms += tr_.stop();

@@ -443,10 +443,35 @@ __device__ __forceinline__ void flush_counters(const TraceParams &P, const Count
     }
 }
 
+// Stage the whole scene (48 B per triangle, 16-byte aligned, a multiple of 16 bytes) into shared
+// memory with the TMA bulk-copy engine: one elected thread issues cp.async.bulk in <= 32 KiB
+// pieces that all complete on one mbarrier; everybody waits on its phase.  (UBLKCP in SASS.)
 __device__ __forceinline__ void stage_scene(float4 *s_tri, const TraceParams &P)
 {
-    for (uint32_t i = threadIdx.x; i < 3 * P.T; i += blockDim.x) s_tri[i] = P.tri[i];
+    __shared__ __align__(8) unsigned long long bar;
+    const uint32_t bytes = 3u * P.T * (uint32_t)sizeof(float4);
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tri);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+        const char *src = reinterpret_cast<const char *>(P.tri);
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t n = min(32768u, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + off), "l"(src + off), "r"(n), "r"(bar_addr) : "memory");
+        }
+    }
+    // phase 0 completes when all bytes have landed
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+    }
 }
 
 template <bool IMAGES>

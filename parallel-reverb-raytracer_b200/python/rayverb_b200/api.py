@@ -218,7 +218,10 @@ class Trace:
 
     def close(self):
         if self._h:
-            lib().rvb_trace_destroy(self._h)
+            try:
+                lib().rvb_trace_destroy(self._h)
+            except TypeError:   # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     __del__ = close
@@ -334,7 +337,10 @@ class Raytracer:
             self.trace.close()
             self.trace = None
         if self._h:
-            lib().rvb_scene_destroy(self._h)
+            try:
+                lib().rvb_scene_destroy(self._h)
+            except TypeError:
+                pass
             self._h = None
 
     __del__ = close
