@@ -2,24 +2,25 @@
 """bench.py -- rays x bounces / s of the rayverb hot path on B200 (BASELINE.json metric).
 
 A "step" is one pass of the whole hot path over one batch of synthetic rays:
-  bounce kernel (nearest hit, specular bounces, diffuse + image-source emission, 8-band air
-  attenuation) -> image-source dedupe -> speaker attenuation -> deterministic flatten (radix sort
-  by sample index + segmented reduction) -> Linkwitz-Riley band filters -> mixdown/normalize/trim.
+  bounce kernels (nearest hit, specular bounces, diffuse + image-source emission, 8-band air
+  attenuation) -> image-source dedupe -> speaker / HRTF attenuation -> deterministic flatten (radix
+  sort by sample index + segmented reduction) -> Linkwitz-Riley band filters -> mixdown / normalize /
+  trim.
 
   value : whole-job rays*bounces/s with the directions already resident in HBM (CUDA events on
           the launching stream, max over ranks)
   e2e   : the same metric through the public C-ABI calls with HOST buffers: pinned-host
           directions -> device inside the timed region, final IR read back to the host
-  N > 1 : rays are sharded (weak scaling: every GPU traces the full per-GPU ray count of its own
-          contiguous slice of the direction set); per-GPU histograms are summed with one NCCL
-          reduce, rank 0 filters.
+  N > 1 : rays are sharded; per-GPU histograms are summed with one NCCL reduce, rank 0 filters.
+          The default workload (C2) scales weakly (every GPU traces the full per-GPU ray count of
+          its own contiguous slice of the direction set); C3/C4 keep the total ray count fixed
+          (strong); C5 shards independent source/receiver pairs with no collective.
 
 `--impl reference` times the CPU restatement of the reference's own algorithm (oracle/) on the
 host cores -- the reference's OpenCL build cannot run in this image (no OpenCL ICD).
 """
 import argparse
 import json
-import math
 import os
 import sys
 import threading
@@ -34,6 +35,7 @@ import numpy as np  # noqa: E402
 FLOP_PER_TEST = 52           # Moller-Trumbore, rayverb/kernel.cpp:63-88
 SM_COUNT = 148
 FP32_LANES = 128
+SR = 44100.0
 
 
 def load_peaks():
@@ -44,14 +46,32 @@ def load_peaks():
     return 6650.0, 1965.0, "fallback"
 
 
+def _pairs_grid():
+    """C5: 8 x 8 grid of (mic, source) positions on two planes of the hall."""
+    jobs = []
+    for i in range(8):
+        for j in range(8):
+            jobs.append(((8.0 + 3.0 * i, 1.5, 16.0 + 0.8 * j), (14.0 + 1.5 * j, 2.0, 3.0 + 0.6 * i)))
+    return jobs
+
+
+# scaling: "weak"   rays = per GPU        (total grows with N)
+#          "strong" rays = total          (sharded over N)
+#          "jobs"   independent (mic, src) pairs sharded over N, `rays` per pair
 WORKLOADS = {
-    # name: (scene builder, mic, source, rays per GPU, reflections, speakers)
-    "C2_shoebox_12tri_1Mx128_omni": dict(scene="shoebox", mic=(7, 2, 4), src=(2, 1.5, 2), rays=1 << 20, refl=128,
+    "C2_shoebox_12tri_1Mx128_omni": dict(scene="shoebox", jobs=[((7, 2, 4), (2, 1.5, 2))], rays=1 << 20, refl=128, scaling="weak",
                                          speakers=[((0, 0, 1), 0.0)], seed=2015),
-    "C1_small_room_1024x64": dict(scene="room700", mic=(5.5, 1.2, 3.5), src=(2, 1.5, 2), rays=1024, refl=64,
-                                  speakers=[((0, 0, -1), 0.0)], seed=2015),
-    "C3_hall_100ktri_1Mx128_stereo": dict(scene="hall", mic=(24, 1.5, 18), src=(20, 2.0, 4), rays=1 << 20, refl=128,
+    "C1_vault_like_room_1024x64": dict(scene="room700", jobs=[((5.5, 1.2, 3.5), (2, 1.5, 2))], rays=1024, refl=64, scaling="weak",
+                                       speakers=[((0, 0, -1), 0.0)], seed=2015),
+    "C3_hall_100ktri_1Mx128_stereo": dict(scene="hall", jobs=[((24, 1.5, 18), (20, 2.0, 4))], rays=1 << 20, refl=128, scaling="strong",
                                           speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], seed=2015),
+    "C4_cathedral_1Mtri_4Mx256_hrtf": dict(scene="cathedral", jobs=[((15, 1.7, 60), (15, 2.0, 10))], rays=1 << 22, refl=256, scaling="strong",
+                                           hrtf=dict(facing=(0, 0, -1), up=(0, 1, 0)), seed=2016),
+    "C5_hall_64pairs_16kx128": dict(scene="hall", jobs=_pairs_grid(), rays=1 << 14, refl=128, scaling="jobs",
+                                    speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], seed=2015),
+    # the brute-force intersector at a size where the tests dominate (roofline of the kernel proper)
+    "X_room_4ktri_303kx64_bruteforce": dict(scene="room4k", jobs=[((12, 1.5, 9), (6, 2, 3))], rays=148 * 2048, refl=64, scaling="weak",
+                                           speakers=[((0, 0, 1), 0.0)], seed=2015, accel=1),
 }
 
 
@@ -62,9 +82,24 @@ def build_scene(name):
     if name == "room700":
         tri, vtx = scenes.displaced_box(8.0, 3.0, 5.0, 700, amp=0.08, fan=0.2, nsurfaces=4)
         return tri, vtx, scenes.hall_surfaces()
+    if name == "room4k":
+        tri, vtx = scenes.displaced_box(20.0, 8.0, 14.0, 4400, amp=0.1, fan=0.25, nsurfaces=4)
+        return tri, vtx, scenes.hall_surfaces()
     if name == "hall":
         return scenes.concert_hall()
+    if name == "cathedral":
+        return scenes.cathedral()
     raise KeyError(name)
+
+
+def render_kwargs(wl):
+    from rayverb_b200 import scenes
+    kw = dict(sr=SR, ft="linkwitz_riley", lo_cutoff=45.0)
+    if "hrtf" in wl:
+        kw["hrtf"] = dict(table=scenes.synthetic_hrtf_table(), facing=wl["hrtf"]["facing"], up=wl["hrtf"]["up"])
+    else:
+        kw["speakers"] = wl["speakers"]
+    return kw
 
 
 class ClockSampler(threading.Thread):
@@ -102,37 +137,49 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_pipeline(wl, tri, vtx, srf, dirs):
+def cpu_sample_rays(wl):
+    """Bounded ray sample of the workload for the CPU legs (brute force over T triangles)."""
+    T = {"shoebox": 12, "room700": 700, "room4k": 4400, "hall": 100_000, "cathedral": 1_000_000}[wl["scene"]]
+    budget = 2.0e9   # ray-triangle tests per step: a few seconds on ~16 cores
+    return int(max(16, min(wl["rays"], budget / (2.3 * wl["refl"] * T))))
+
+
+def cpu_pipeline(wl, tri, vtx, srf, dirs, job):
     """The reference's CLI pipeline (cmd/main.cpp:241-336) on the CPU oracle."""
     from oracle import oracle as orc
-    return orc.render_ir(tri, vtx, srf, wl["mic"], wl["src"], dirs, wl["refl"], speakers=wl["speakers"], sr=44100.0,
-                         ft="linkwitz_riley", lo_cutoff=45.0)
+    mic, src = job
+    return orc.render_ir(tri, vtx, srf, mic, src, dirs, wl["refl"], **render_kwargs(wl))
+
+
+def cpu_leg(wl, tri, vtx, srf, steps, warmup):
+    from oracle import oracle as orc
+    from rayverb_b200 import scenes
+    orc.build()
+    n = cpu_sample_rays(wl)
+    dirs = scenes.sphere_directions(n, seed=wl["seed"])
+    job = wl["jobs"][0]
+    for _ in range(warmup):
+        cpu_pipeline(wl, tri, vtx, srf, dirs[:max(1, n // 8)], job)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pipeline(wl, tri, vtx, srf, dirs, job)
+    dt = (time.perf_counter() - t0) / steps
+    sample = (f"{n} rays x {wl['refl']} reflections of the workload per step, full pipeline "
+              f"(trace+dedupe+attenuate+flatten+filter), {dt:.2f} s")
+    return n * wl["refl"] / dt, dt, orc.num_threads(), sample
 
 
 def run_reference(args, wl_name, wl):
     """--impl reference: the CPU restatement of the reference's algorithm on the host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import oracle as orc
-    from rayverb_b200 import scenes
-    orc.build()
     tri, vtx, srf = build_scene(wl["scene"])
-    sample_rays = min(wl["rays"], 32768 if wl["scene"] == "shoebox" else 256)
-    dirs = scenes.sphere_directions(sample_rays, seed=wl["seed"])
-    for _ in range(args.warmup):
-        cpu_pipeline(wl, tri, vtx, srf, dirs[:max(1, sample_rays // 8)])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_pipeline(wl, tri, vtx, srf, dirs)
-    dt = (time.perf_counter() - t0) / args.steps
-    value = sample_rays * wl["refl"] / dt
-    cores = orc.num_threads()
-    sample = f"{sample_rays} rays x {wl['refl']} reflections of the workload per step, full pipeline (trace+dedupe+attenuate+flatten+filter)"
+    value, dt, cores, sample = cpu_leg(wl, tri, vtx, srf, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "rays_x_bounces_per_s", "value": value, "unit": "rays*bounces/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl_name, "note": "CPU oracle port of rayverb/kernel.cpp + host pipeline; the reference's OpenCL build has no ICD here"},
+            "config": {"workload": wl_name,
+                       "note": "CPU oracle port of rayverb/kernel.cpp + host pipeline (OpenMP over rays); the reference's OpenCL build has no ICD here"},
             "cpu_baseline": {"value": value, "unit": "rays*bounces/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays*bounces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -146,9 +193,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2_shoebox_12tri_1Mx128_omni", choices=sorted(WORKLOADS))
-    ap.add_argument("--rays", type=int, default=None, help="override rays per GPU (testing)")
+    ap.add_argument("--rays", type=int, default=None, help="override the workload's ray count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--accel", type=int, default=0)
+    ap.add_argument("--accel", type=int, default=None, help="0 auto, 1 brute force, 2 BVH")
     args = ap.parse_args()
     wl_name = args.workload
     wl = dict(WORKLOADS[wl_name])
@@ -174,49 +221,65 @@ def main():
     api.set_stream(stream.cuda_stream)
 
     tri, vtx, srf = build_scene(wl["scene"])
-    nrays, nrefl = wl["rays"], wl["refl"]
-    # one global direction set of world*nrays rays; rank r owns the contiguous slice [r*nrays, (r+1)*nrays)
-    all_dirs = scenes.sphere_directions(world * nrays, seed=wl["seed"])
-    h_dirs = torch.from_numpy(all_dirs[rank * nrays:(rank + 1) * nrays].copy()).pin_memory()
+    nrefl, scaling = wl["refl"], wl["scaling"]
+    # ray set and the slice this rank owns
+    if scaling == "weak":
+        total_rays = world * wl["rays"]
+        lo, hi = rank * wl["rays"], (rank + 1) * wl["rays"]
+        jobs = wl["jobs"]
+    elif scaling == "strong":
+        total_rays = wl["rays"]
+        lo, hi = sharding.shard_slice(total_rays, rank, world)
+        jobs = wl["jobs"]
+    else:   # independent pairs: every rank traces ALL rays of its own pairs, no collective
+        total_rays = wl["rays"]
+        lo, hi = 0, total_rays
+        jobs = wl["jobs"][rank::world]
+    sharded = world > 1 and scaling != "jobs"
+    all_dirs = scenes.sphere_directions(total_rays, seed=wl["seed"])
+    nrays = hi - lo
+    h_dirs = torch.from_numpy(all_dirs[lo:hi].copy()).pin_memory()
     d_dirs = h_dirs.to("cuda", non_blocking=False)
-    rt = api.Raytracer(nrefl, tri, vtx, srf, accel=args.accel)
-    render_kw = dict(speakers=wl["speakers"], sr=44100.0, ft="linkwitz_riley", lo_cutoff=45.0)
+    accel = args.accel if args.accel is not None else wl.get("accel", 0)
+    rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
+    render_kw = render_kwargs(wl)
     cfg, keep = api.make_render_config(**render_kw)
-    nch = len(wl["speakers"])
-    h2d_bytes = h_dirs.numel() * 4
-    state = {}
+    nch = 2 if "hrtf" in wl else len(wl["speakers"])
+    h2d_bytes = h_dirs.numel() * 4 * len(jobs)
+    state = {"trace": [], "render": []}
 
     def step(resident):
-        """One pass of the hot path on this rank's ray shard.  Returns the IR on rank 0."""
-        if resident:
-            tr = rt.raytrace(wl["mic"], wl["src"], None, ray_offset=rank * nrays, device_ptr=d_dirs.data_ptr(), nrays=nrays)
-        else:
-            tr = rt.raytrace(wl["mic"], wl["src"], h_dirs.numpy(), ray_offset=rank * nrays)
-        state["trace"] = tr.stats()
-        if world == 1:
-            ir = tr.render_ir(**render_kw)
-            state["render"] = api.render_stats()
-            return ir
-        # ---- sharded: global predelay/lengths, cross-shard image merge, one NCCL reduce ----------
-        hist, lengths, _ = sharding.sharded_histogram(tr, cfg, rank, world, "cuda", 44100.0, False)
-        state["render"] = api.render_stats()
-        if rank == 0:
-            return api.render_finish(cfg, hist.data_ptr(), lengths)
-        return None
+        """One pass of the hot path over this rank's work.  Returns the IR(s) this rank produced."""
+        irs = []
+        for mic, src in jobs:
+            if resident:
+                tr = rt.raytrace(mic, src, None, ray_offset=lo, device_ptr=d_dirs.data_ptr(), nrays=nrays)
+            else:
+                tr = rt.raytrace(mic, src, h_dirs.numpy(), ray_offset=lo)
+            state["trace"].append(tr.stats())
+            if not sharded:
+                irs.append(tr.render_ir(**render_kw))
+                state["render"].append(api.render_stats())
+                continue
+            # sharded: global predelay/lengths, cross-shard image merge, ONE NCCL reduce of the histogram
+            hist, lengths, _ = sharding.sharded_histogram(tr, cfg, rank, world, "cuda", SR, False)
+            state["render"].append(api.render_stats())
+            if rank == 0:
+                irs.append(api.render_finish(cfg, hist.data_ptr(), lengths))
+        return irs
 
     def timed(resident, steps):
+        state["trace"].clear()
+        state["render"].clear()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0, d2h = api.launch_count(), 0
         e0.record(stream)
-        kern_ms, launches0, d2h, tests = [], api.launch_count(), 0, 0
         for _ in range(steps):
-            ir = step(resident)
-            kern_ms.append(state["trace"]["trace_kernel_ms"])
-            tests = state["trace"]["tri_tests"]
-            if ir is not None:
-                d2h = sum(c.nbytes for c in ir.channels)
+            irs = step(resident)
+            d2h = sum(c.nbytes for ir in irs for c in ir.channels)
         e1.record(stream)
         if world > 1:
             dist.barrier()
@@ -226,62 +289,75 @@ def main():
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, float(np.mean(kern_ms)), api.launch_count() - launches0, d2h, tests
+        return ms, api.launch_count() - launches0, d2h
 
     for _ in range(max(args.warmup, 3)):
         step(True)
     sampler = ClockSampler(local)
     sampler.start()
-    ms, kern_ms, launches, d2h_bytes, tests = timed(True, args.steps)
-    render = dict(state["render"])
-    trace_stats = dict(state["trace"])
+    ms, launches, _ = timed(True, args.steps)
+    tstats = [dict(s) for s in state["trace"]]
+    rstats = [dict(s) for s in state["render"]]
     step(False)  # warm the host-buffer path (pinned H2D)
-    e2e_ms, _, _, d2h_bytes, _ = timed(False, args.steps)
+    e2e_ms, _, d2h_bytes = timed(False, args.steps)
     clocks = sampler.stop()
 
     if rank == 0:
         hbm_gbs, sm_max_mhz, peak_src = load_peaks()
-        total_rb = world * nrays * nrefl
+        njobs_total = len(wl["jobs"])
+        total_rb = total_rays * nrefl * (njobs_total if scaling == "jobs" else 1)
         fp32_peak_tf = SM_COUNT * FP32_LANES * 2 * sm_max_mhz * 1e6 / 1e12
-        achieved_tf = tests * FLOP_PER_TEST / (kern_ms * 1e-3) / 1e12
-        # emission bytes of the bounce kernel: 48 useful bytes per impulse + 4 B sort key time
-        emit_gbs = nrays * nrefl * 52 / (kern_ms * 1e-3) / 1e9
+
+        def mean(k, ss):
+            return float(np.mean([s[k] for s in ss])) if ss else 0.0
+
+        steady_ms, image_ms = mean("steady_phase_ms", tstats), mean("image_phase_ms", tstats)
+        steady_tests = mean("steady_tri_tests", tstats)
+        all_tests = mean("tri_tests", tstats)
+        brute = rt.accel == api.ACCEL_BRUTE_FORCE
+        achieved_tf = steady_tests * FLOP_PER_TEST / (steady_ms * 1e-3) / 1e12 if steady_ms > 0 else 0.0
+        split = min(9, nrefl)
+        emit_gbs = nrays * (nrefl - split) * 52 / (steady_ms * 1e-3) / 1e9 if steady_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if brute and os.path.exists(tp):   # DRAM bytes per ray*bounce of the steady kernel, from the committed ncu --set full capture
+            traffic = json.load(open(tp))["steady_phase_dram_bytes_per_ray_bounce"] * nrays * (nrefl - split)
+        both_ms = steady_ms + image_ms
         line = {
             "metric": "rays_x_bounces_per_s", "value": total_rb / (ms * 1e-3), "unit": "rays*bounces/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl_name, "triangles": int(len(tri)), "rays_per_gpu": nrays, "reflections": nrefl,
-                       "channels": nch, "sample_rate": 44100, "filter": "linkwitz_riley",
-                       "accel": "brute_force_smem" if rt.accel == api.ACCEL_BRUTE_FORCE else "bvh",
-                       "sharding": f"rays/{world}" if world > 1 else "none",
-                       "l2": "inputs_larger_than_L2 (per-step working set %.1f GB)" % (nrays * nrefl * 52 / 1e9)},
+            "higher_is_better": True, "scaling": "strong" if scaling == "strong" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "triangles": int(len(tri)), "rays_total": int(total_rays), "rays_this_gpu": int(nrays),
+                       "reflections": nrefl, "source_receiver_pairs": njobs_total, "channels": nch, "sample_rate": int(SR),
+                       "attenuation": "hrtf" if "hrtf" in wl else "speakers", "filter": "linkwitz_riley",
+                       "accel": "brute_force_smem" if brute else "bvh",
+                       "sharding": ("pairs/%d" % world if scaling == "jobs" else "rays/%d" % world) if world > 1 else "none",
+                       "l2": "inputs_larger_than_L2 (per-step working set %.2f GB per GPU)" % (nrays * nrefl * 52 / 1e9)},
             "e2e": {"value": total_rb / (e2e_ms * 1e-3), "unit": "rays*bounces/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes)},
-            "ir_wall_ms": e2e_ms,
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+            "ir_wall_ms": e2e_ms / max(1, len(jobs)),
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "trace_bruteforce_kernel" if rt.accel == api.ACCEL_BRUTE_FORCE else "trace_bvh_kernel",
+            "roofline": {"kernel": ("trace_bruteforce_kernel<false>" if brute else "trace_bvh_kernel<false>")
+                         + " (steady phase, reflections %d..%d)" % (split, nrefl - 1),
                          "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp32_peak_tf, "traffic": None,
+                         "frac": achieved_tf / fp32_peak_tf, "traffic": traffic,
                          "peak_source": f"148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz ({peak_src} clock)",
-                         "kernel_ms": kern_ms, "tests_per_launch": int(tests), "flop_per_test": FLOP_PER_TEST,
+                         "kernel_ms": steady_ms, "tests_per_launch": int(steady_tests), "flop_per_test": FLOP_PER_TEST,
+                         "all_bounce_kernels": {"ms": both_ms, "tests": int(all_tests),
+                                                "achieved": all_tests * FLOP_PER_TEST / (both_ms * 1e-3) / 1e12 if both_ms > 0 else 0.0},
                          "hbm_view": {"achieved": emit_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": emit_gbs / hbm_gbs,
                                       "bytes_per_impulse": 52}},
-            "stages_ms": {"trace_kernel": kern_ms, "trace_total": trace_stats["total_ms"], "keys": render["keys_ms"],
-                          "sort": render["sort_ms"], "reduce": render["reduce_ms"], "filter": render["filter_ms"],
-                          "finish": render["finish_ms"]},
+            "stages_ms": {"image_phase": image_ms, "steady_phase": steady_ms, "trace_total": mean("total_ms", tstats),
+                          "keys": mean("keys_ms", rstats), "sort": mean("sort_ms", rstats), "reduce": mean("reduce_ms", rstats),
+                          "filter": mean("filter_ms", rstats), "finish": mean("finish_ms", rstats)},
         }
+        if not brute:
+            line["roofline"]["box_tests_per_launch"] = int(mean("steady_box_tests", tstats))
         if not args.no_cpu_baseline:
-            from oracle import oracle as orc
-            orc.build()
-            sample_rays = min(nrays, 32768 if wl["scene"] == "shoebox" else 256)
-            d = all_dirs[:sample_rays]
-            t0 = time.perf_counter()
-            cpu_pipeline(wl, tri, vtx, srf, d)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": sample_rays * nrefl / dt, "unit": "rays*bounces/s", "cores": orc.num_threads(),
-                                    "kind": "port",
-                                    "sample": f"{sample_rays} rays x {nrefl} reflections of the same workload, full pipeline, {dt:.1f} s"}
+            v, dt, cores, sample = cpu_leg(wl, tri, vtx, srf, 1, 0)
+            line["cpu_baseline"] = {"value": v, "unit": "rays*bounces/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     rt.close()
     if world > 1:

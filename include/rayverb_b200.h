@@ -122,6 +122,10 @@ typedef struct {
     uint64_t bounces;          /* reflections actually executed (<= nrays*nreflections)         */
     float trace_kernel_ms;     /* CUDA-event time of the bounce kernel(s)                       */
     float total_ms;            /* CUDA-event time of rvb_trace_run incl. H2D + image dedupe     */
+    float image_phase_ms;      /* reflections 0..8 (image-source branch), 0 when skipped        */
+    float steady_phase_ms;     /* reflections 9.. (the dominant kernel)                         */
+    uint64_t steady_tri_tests; /* ray-triangle tests executed by the steady-phase kernel        */
+    uint64_t steady_box_tests;
 } rvb_trace_stats;
 int rvb_trace_get_stats(const rvb_trace *trace, rvb_trace_stats *stats);
 

@@ -67,7 +67,7 @@ struct BruteSmem {
     {
         tbest = RVB_INF;
         ibest = RVB_NONE;
-#pragma unroll 4
+#pragma unroll 6
         for (uint32_t i = 0; i < T; ++i) {
             f3 v0, e0, e1;
             load(i, v0, e0, e1);
@@ -82,7 +82,7 @@ struct BruteSmem {
     __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
     {
         bool blocked = false;
-#pragma unroll 4
+#pragma unroll 6
         for (uint32_t i = 0; i < T; ++i) {
             f3 v0, e0, e1;
             load(i, v0, e0, e1);
@@ -474,8 +474,11 @@ __device__ __forceinline__ void stage_scene(float4 *s_tri, const TraceParams &P)
     }
 }
 
-template <bool IMAGES>
-__global__ void __launch_bounds__(256) trace_bruteforce_kernel(const TraceParams P)
+// BLOCK = 256 for small scenes (several CTAs per SM); when the shared-memory scene leaves room for
+// only one CTA per SM the launcher switches to 1024 (steady phase) / 512 (image phase) threads so
+// that the schedulers still have 8 / 4 warps each.
+template <bool IMAGES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TraceParams P)
 {
     extern __shared__ float4 s_tri[];
     stage_scene(s_tri, P);
@@ -499,17 +502,41 @@ __global__ void __launch_bounds__(128) trace_bvh_kernel(const TraceParams P)
 }
 
 template <class K>
-static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, cudaStream_t st)
+static int occupancy_of(K kernel, int block, size_t smem, int &per_sm)
 {
     RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
     RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    return RVB_OK;
+}
+
+template <class K>
+static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, cudaStream_t st)
+{
+    int per_sm = 0;
+    RVB_TRY(occupancy_of(kernel, block, smem, per_sm));
     if (per_sm < 1) return fail(RVB_ERR_INVALID, "scene does not fit in shared memory for the brute-force kernel");
     const size_t want = ((size_t)P.nrays + block - 1) / block;
     const size_t grid = std::min(want, (size_t)per_sm * sm_count());
     note_launch(), kernel<<<(unsigned)grid, block, smem, st>>>(P);
     RVB_CUDA(cudaGetLastError());
     return RVB_OK;
+}
+
+// brute force: the CTA size with the most resident threads per SM
+template <bool IMAGES>
+static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
+{
+    int small = 0, big = 0;
+    RVB_TRY(occupancy_of(trace_bruteforce_kernel<IMAGES, 256>, 256, smem, small));
+    constexpr int BIG = IMAGES ? 512 : 1024;
+    RVB_TRY(occupancy_of(trace_bruteforce_kernel<IMAGES, BIG>, BIG, smem, big));
+    // threads that would actually be busy with this many rays (small CTAs spread few rays over more SMs)
+    const size_t nsm = (size_t)sm_count();
+    const size_t busy_small = std::min<size_t>(P.nrays, (size_t)small * 256 * nsm);
+    const size_t busy_big = std::min<size_t>(P.nrays, (size_t)big * BIG * nsm);
+    const bool spread = (size_t)P.nrays >= nsm * BIG;   // enough rays to give every SM a big CTA
+    if (spread && busy_big > busy_small) return launch_phase(trace_bruteforce_kernel<IMAGES, BIG>, P, BIG, smem, st);
+    return launch_phase(trace_bruteforce_kernel<IMAGES, 256>, P, 256, smem, st);
 }
 
 int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB, float4 *d_cand_pt,
@@ -543,34 +570,43 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
     const size_t smem = brute ? (size_t)3 * sc->T * sizeof(float4) : 0;
 
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0, e1, em;
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
+    RVB_CUDA(cudaEventCreate(&em));
+    unsigned long long hm[4] = {0, 0, 0, 0};
     RVB_CUDA(cudaEventRecord(e0, st));
+    RVB_CUDA(cudaEventRecord(em, st));
     if (tr->nrays > 0 && tr->nrefl > 0) {
         if (split > 0) {
             P.first = 0; P.last = split;
-            if (brute) RVB_TRY(launch_phase(trace_bruteforce_kernel<true>, P, 256, smem, st));
+            if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
             else RVB_TRY(launch_phase(trace_bvh_kernel<true>, P, 128, 0, st));
+            RVB_CUDA(cudaEventRecord(em, st));
+            RVB_CUDA(cudaMemcpyAsync(hm, d_counters, sizeof hm, cudaMemcpyDeviceToHost, st));
         }
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
-            if (brute) RVB_TRY(launch_phase(trace_bruteforce_kernel<false>, P, 256, smem, st));
+            if (brute) RVB_TRY(launch_bruteforce<false>(P, smem, st));
             else RVB_TRY(launch_phase(trace_bvh_kernel<false>, P, 128, 0, st));
         }
     } else if (tr->nrays > 0 && images && tr->ray_offset == 0) {
         // zero reflections: the reference still computes the direct path for ray 0
         P.first = 0; P.last = 0;
-        if (brute) RVB_TRY(launch_phase(trace_bruteforce_kernel<true>, P, 256, smem, st));
+        if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
         else RVB_TRY(launch_phase(trace_bvh_kernel<true>, P, 128, 0, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
     unsigned long long h[4];
     RVB_CUDA(cudaMemcpyAsync(h, d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
-    float ms = 0.f;
+    float ms = 0.f, ms_image = 0.f, ms_steady = 0.f;
     RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    RVB_CUDA(cudaEventElapsedTime(&ms_image, e0, em));
+    RVB_CUDA(cudaEventElapsedTime(&ms_steady, em, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(em);
+    tr->stats.image_phase_ms = ms_image; tr->stats.steady_phase_ms = ms_steady;
+    tr->stats.steady_tri_tests = h[1] - hm[1]; tr->stats.steady_box_tests = h[2] - hm[2];
     dev_free(d_counters);
     dev_free(d_state);
     tr->stats.queries = h[0]; tr->stats.tri_tests = h[1]; tr->stats.box_tests = h[2]; tr->stats.bounces = h[3];

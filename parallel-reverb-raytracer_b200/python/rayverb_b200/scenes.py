@@ -254,3 +254,15 @@ def load_obj(obj_path, materials_path):
                     sids.append(current)
     tri, vtx = _pack(verts, faces, sids)
     return tri, vtx, surfaces
+
+
+def synthetic_hrtf_table():
+    """Smooth synthetic [2, 360, 180, 8] HRTF table (the reference's rayverb/hrtf.cpp, generated from
+    the IRCAM Listen recordings, is not available): positive, ear-asymmetric, band-dependent.  Same
+    formula as the C++ host's built-in table (host/rayverb.cpp: fillSynthetic)."""
+    a = np.deg2rad(np.arange(360, dtype=np.float64))[None, :, None, None]
+    e = np.deg2rad(np.arange(180, dtype=np.float64))[None, None, :, None]
+    b = np.arange(8, dtype=np.float64)[None, None, None, :]
+    ear = np.array([-1.0, 1.0])[:, None, None, None]
+    t = 0.55 + 0.35 * ear * np.sin(a) * np.sin(e) * (0.3 + 0.1 * b) + 0.08 * np.cos(2 * a + 0.3 * b) * np.sin(e)
+    return np.ascontiguousarray(t, dtype=np.float32)

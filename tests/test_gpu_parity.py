@@ -277,3 +277,20 @@ def test_bvh_hall_100k_subsample_vs_oracle(orc):
     assert 95_000 < len(tri) < 105_000
     dirs = scenes.sphere_directions(48, seed=2015)
     check_trace_against_oracle(orc, tri, vtx, srf, (24, 1.5, 18), (20, 2.0, 4), dirs, 12, api.ACCEL_AUTO)
+
+
+def test_c4_cathedral_1m_triangles_hrtf_subsample(orc):
+    """C4 mesh (~1M triangles, BVH path) with HRTF output: a ray subsample end to end against the
+    CPU brute-force oracle (hits bit-exact, IR within 1e-4 relative L2 per band)."""
+    tri, vtx, srf = scenes.cathedral()
+    assert 950_000 < len(tri) < 1_050_000
+    dirs = scenes.sphere_directions(24, seed=2016)
+    mic, src = (15, 1.7, 60), (15, 2.0, 10)
+    ref = check_trace_against_oracle(orc, tri, vtx, srf, mic, src, dirs, 6, api.ACCEL_AUTO)
+    assert ref["refl_count"].min() >= 1
+    _render_case(orc, tri, vtx, srf, mic, src, dirs, 6, api.ACCEL_AUTO,
+                 hrtf=dict(table=scenes.synthetic_hrtf_table(), facing=(0, 0, -1), up=(0, 1, 0)))
+
+
+def test_synthetic_table_matches_test_helper():
+    assert np.array_equal(scenes.synthetic_hrtf_table(), smooth_table())
