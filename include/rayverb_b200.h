@@ -146,7 +146,14 @@ int rvb_attenuate_hrtf(const rvb_impulse *in, size_t n, const float mic[3],
 int rvb_flatten(const rvb_attenuated_impulse *in, size_t n, float sample_rate, float **out, size_t *length);
 /* RayverbFiltering::filter (filters.cpp:268-306) on [nchannels][8][length], in place */
 int rvb_filter(int filter_type, float *data, size_t nchannels, size_t length, float sample_rate, float lo_cutoff);
+/* BandpassWindowedSinc (filters.cpp:100-131, FILTER_TYPE_WINDOWED_SINC): out of place because the
+ * data GROWS -- in [nchannels][8][length] -> out [nchannels][8][29 + length - 1], scaled by the FFT
+ * length like the reference's un-normalised FFTW round trip. */
+#define RVB_SINC_KERNEL_LENGTH 29
+int rvb_filter_sinc(const float *in, size_t nchannels, size_t length, float sample_rate, float lo_cutoff, float *out);
 /* process (rayverb.cpp:125-149): filter + mixdown + normalize + scale + trimTail.
+ * With RVB_FILTER_WINDOWED_SINC every out[c] must hold 29 + lengths[0] - 1 samples and `data` is
+ * left untouched (the filtered rows no longer fit).
  * data: nchannels pointers to [8][lengths[c]] (modified like the reference does);
  * out: nchannels pointers to lengths[c] floats; *out_length = trimmed common length or -1. */
 int rvb_process(int filter_type, float *const *data, const size_t *lengths, size_t nchannels,

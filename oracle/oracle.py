@@ -73,6 +73,10 @@ def lib():
         L.orc_bandpass_biquad_params.argtypes = [f32, f32, f32, vp]
         L.orc_linkwitz_riley_params.restype = None
         L.orc_linkwitz_riley_params.argtypes = [f32, f32, f32, vp]
+        L.orc_sinc_bandpass_kernel.restype = None
+        L.orc_sinc_bandpass_kernel.argtypes = [f32, f32, f32, vp]
+        L.orc_filter_channel_sinc.restype = i32
+        L.orc_filter_channel_sinc.argtypes = [vp, u64, u64, f32, f32, vp]
         L.orc_air_coefficient.restype = None
         L.orc_air_coefficient.argtypes = [vp]
         L.orc_sphere_point.restype = None
@@ -173,8 +177,30 @@ def flatten(attenuated, samplerate):
     return out
 
 
+SINC_KERNEL_LENGTH = 29
+
+
+def sinc_bandpass_kernel(sr, lo, hi):
+    k = np.zeros(SINC_KERNEL_LENGTH, dtype=np.float32)
+    lib().orc_sinc_bandpass_kernel(C.c_float(sr), C.c_float(lo), C.c_float(hi), _p(k))
+    return k
+
+
+def filter_channel_sinc(data, sr, lo_cutoff, first_len=None):
+    """BandpassWindowedSinc on one channel [8, L] -> [8, 29 + first_len - 1] (the data grows)."""
+    d = np.ascontiguousarray(data, dtype=np.float32)
+    first_len = d.shape[1] if first_len is None else int(first_len)
+    out = np.zeros((NBANDS, SINC_KERNEL_LENGTH + first_len - 1), dtype=np.float32)
+    rc = lib().orc_filter_channel_sinc(_p(d), d.shape[1], first_len, C.c_float(sr), C.c_float(lo_cutoff), _p(out))
+    if rc:
+        raise ValueError("a channel longer than the first one overflows the reference's FFT buffer")
+    return out
+
+
 def filter_channel(ft, data, sr, lo_cutoff):
     """RayverbFiltering::filter on one channel [8, L], returns a filtered copy."""
+    if (FILTER_TYPES[ft] if isinstance(ft, str) else int(ft)) == 0:
+        return filter_channel_sinc(data, sr, lo_cutoff)
     d = np.array(data, dtype=np.float32, order="C", copy=True)
     rc = lib().orc_filter_channel(FILTER_TYPES[ft] if isinstance(ft, str) else int(ft), _p(d), d.shape[1],
                                   C.c_float(sr), C.c_float(lo_cutoff))
@@ -187,6 +213,29 @@ def process(ft, flattened, sr, do_normalize=True, lo_cutoff=45.0, do_trim_tail=T
     """process() (rayverb.cpp:125-149).  flattened: list of [8, L_c] arrays (copied).
     Returns a list of float32 channels, trimmed/resized like the reference."""
     data = [np.array(f, dtype=np.float32, order="C", copy=True) for f in flattened]
+    ftid = FILTER_TYPES[ft] if isinstance(ft, str) else int(ft)
+    if ftid == 0:   # windowed sinc: the channels grow to 29 + len(first) - 1; then mixdown / normalize / mul / trimTail
+        first = data[0].shape[1]
+        filt = [filter_channel_sinc(d, sr, lo_cutoff, first) for d in data]
+        outs = []
+        for f in filt:   # mixdown (rayverb.cpp:80-92): float adds in band order
+            acc = np.zeros(f.shape[1], dtype=np.float32)
+            for b in range(NBANDS):
+                acc = (acc + f[b]).astype(np.float32)
+            outs.append(acc)
+        if do_normalize:
+            m = np.float32(max(np.abs(o).max() for o in outs))
+            fmul = np.float32(1.0 / np.float64(m))
+            outs = [(o * fmul).astype(np.float32) for o in outs]
+        if volume_scale != 1:
+            outs = [(o * np.float32(volume_scale)).astype(np.float32) for o in outs]
+        if do_trim_tail:
+            n = 0
+            for o in outs:
+                loud = np.nonzero(np.abs(o) >= np.float32(0.00001))[0]
+                n = max(n, int(loud[-1]) if len(loud) else -1)
+            outs = [np.concatenate([o[:n], np.zeros(max(0, n - len(o)), np.float32)]) for o in outs]
+        return outs
     lens = np.array([d.shape[1] for d in data], dtype=np.uint64)
     outs = [np.zeros(int(l), dtype=np.float32) for l in lens]
     dptr = (C.c_void_p * len(data))(*[d.ctypes.data for d in data])
@@ -245,7 +294,10 @@ def render_ir(triangles, vertices, surfaces, mic, source, directions, nreflectio
     flat = [flatten(a, sr) for a in att]
     out = process(ft, flat, sr, do_normalize, lo_cutoff, do_trim_tail, volume_scale)
     if return_bands:
-        bands = [filter_channel(ft, f, sr, lo_cutoff) for f in flat]
+        if (FILTER_TYPES[ft] if isinstance(ft, str) else int(ft)) == 0:
+            bands = [filter_channel_sinc(f, sr, lo_cutoff, flat[0].shape[1]) for f in flat]
+        else:
+            bands = [filter_channel(ft, f, sr, lo_cutoff) for f in flat]
         return out, flat, bands
     return out
 

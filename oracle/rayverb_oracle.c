@@ -541,6 +541,95 @@ void orc_linkwitz_riley_params(float l, float h, float s, double *coef)
     }
 }
 
+/* ---- windowed-sinc crossover, filters.cpp:10-154,308-346 + filters.h:44-147 ------------------ *
+ * The reference convolves through FFTW (r2c, pointwise product, c2r) with FFT_LENGTH =
+ * 29 + inputLength - 1, so the circular convolution equals the linear one, and FFTW's c2r is
+ * un-normalised: the result is FFT_LENGTH * (kernel (*) data).  FFTW is a third-party dependency
+ * (FFTW 3.x, libfftw3f; not in the reference tree, not installed here); its published contract is
+ * the unnormalised DFT, which is what is restated here as a direct convolution in double
+ * precision.  Single-precision FFT rounding (~1e-7 of the signal norm) is the expected difference
+ * from the reference's own output.                                                              */
+#define SINC_KERNEL_LENGTH 29
+
+/* filters.cpp:10-31 sincKernel<float>: centre tap 1, else sin(pi t)/(pi t), t = 2*cutoff*(i - (len-1)/2) */
+static void sinc_kernel(double cutoff, int length, float *out)
+{
+    for (int i = 0; i != length; ++i) {
+        if (i == (length - 1) / 2) out[i] = 1;
+        else {
+            double t = 2 * cutoff * (i - (length - 1) / 2.0);
+            double pit = M_PI * t;
+            out[i] = (float)(sin(pit) / pit);
+        }
+    }
+}
+/* filters.cpp:34-52 blackman<float> */
+static void blackman(int length, float *out)
+{
+    const double a0 = 7938.0 / 18608.0, a1 = 9240.0 / 18608.0, a2 = 1430.0 / 18608.0;
+    for (int i = 0; i != length; ++i) {
+        const double offset = i / (length - 1.0);
+        out[i] = (float)(a0 - a1 * cos(2 * M_PI * offset) + a2 * cos(4 * M_PI * offset));
+    }
+}
+/* filters.cpp:56-70 lopassKernel: window * sinc (float product), normalised by the largest magnitude */
+static void lopass_kernel(float sr, float cutoff, int length, float *out)
+{
+    float window[SINC_KERNEL_LENGTH];
+    blackman(length, window);
+    sinc_kernel(cutoff / sr, length, out);
+    float m = 0;
+    for (int i = 0; i != length; ++i) { out[i] = window[i] * out[i]; float a = fabsf(out[i]); m = m > a ? m : a; }
+    const float f = (float)(1.0 / m);
+    for (int i = 0; i != length; ++i) out[i] *= f;
+}
+/* filters.cpp:74-80 hipassKernel */
+static void hipass_kernel(float sr, float cutoff, int length, float *out)
+{
+    lopass_kernel(sr, cutoff, length, out);
+    for (int i = 0; i != length; ++i) out[i] = -out[i];
+    out[(length - 1) / 2] += 1;
+}
+/* filters.cpp:114-124 bandpassKernel: FastConvolution(29).convolve(lop15, hip15) = 29 * (lop (*) hip) */
+void orc_sinc_bandpass_kernel(float sr, float lo, float hi, float *kernel29)
+{
+    enum { HALF = 1 + SINC_KERNEL_LENGTH / 2 };
+    float lop[HALF], hip[HALF];
+    lopass_kernel(sr, hi, HALF, lop);
+    hipass_kernel(sr, lo, HALF, hip);
+    for (int k = 0; k < SINC_KERNEL_LENGTH; ++k) {
+        double acc = 0;
+        for (int j = 0; j < HALF; ++j) {
+            int i = k - j;
+            if (i >= 0 && i < HALF) acc += (double)lop[j] * (double)hip[i];
+        }
+        kernel29[k] = (float)(acc * SINC_KERNEL_LENGTH);
+    }
+}
+/* filters.cpp:126-131 BandpassWindowedSinc::filter on one channel: in [8][len] -> out [8][fft_len],
+ * fft_len = 29 + first_len - 1 where first_len is the length of the FIRST channel's first band
+ * (filters.cpp:280-283: the convolver is sized once).  len must not exceed fft_len.             */
+int orc_filter_channel_sinc(const float *in, uint64_t len, uint64_t first_len, float sr, float lo_cutoff, float *out)
+{
+    const float EDGES[9] = {lo_cutoff, 175, 350, 700, 1400, 2800, 5600, 11200, 20000};
+    const uint64_t fft_len = SINC_KERNEL_LENGTH + first_len - 1;
+    if (len > fft_len) return -2;
+    for (int b = 0; b < NBANDS; ++b) {
+        float k[SINC_KERNEL_LENGTH];
+        orc_sinc_bandpass_kernel(sr, EDGES[b], EDGES[b + 1], k);
+        const float *x = in + (uint64_t)b * len;
+        float *y = out + (uint64_t)b * fft_len;
+        for (uint64_t n = 0; n < fft_len; ++n) {
+            double acc = 0;
+            for (int j = 0; j < SINC_KERNEL_LENGTH; ++j) {
+                if (n >= (uint64_t)j && n - j < len) acc += (double)k[j] * (double)x[n - j];
+            }
+            y[n] = (float)(acc * (double)fft_len);
+        }
+    }
+    return 0;
+}
+
 /* FilterType, filters.h:196-201 */
 enum { FILTER_TYPE_WINDOWED_SINC = 0, FILTER_TYPE_BIQUAD_ONEPASS = 1, FILTER_TYPE_BIQUAD_TWOPASS = 2, FILTER_TYPE_LINKWITZ_RILEY = 3 };
 

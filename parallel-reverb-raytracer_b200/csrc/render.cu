@@ -601,10 +601,99 @@ static void lr_coef(float l, float h, float s, BiquadCoef &lop, BiquadCoef &hip)
     }
 }
 
+// ---- windowed-sinc crossover (filters.cpp:10-154, filters.h:44-147) --------------------------------
+// The reference convolves through FFTW with FFT_LENGTH = 29 + inputLength - 1 (circular == linear
+// convolution) and an un-normalised c2r, i.e. it computes FFT_LENGTH * (kernel (*) data).  A 29-tap
+// kernel needs no FFT on a GPU: this is the same sum evaluated directly, in double.
+#define RVB_SINC_TAPS 29
+
+static void sinc_lopass(float sr, float cutoff, int length, float *out)   // filters.cpp:10-70
+{
+    const double a0 = 7938.0 / 18608.0, a1 = 9240.0 / 18608.0, a2 = 1430.0 / 18608.0;
+    const double fc = cutoff / sr;   // float division, promoted (lopassKernel passes cutoff / sr)
+    float m = 0;
+    for (int i = 0; i != length; ++i) {
+        const double offset = i / (length - 1.0);
+        const float window = (float)(a0 - a1 * std::cos(2 * M_PI * offset) + a2 * std::cos(4 * M_PI * offset));
+        float s = 1;
+        if (i != (length - 1) / 2) {
+            const double pit = M_PI * (2 * fc * (i - (length - 1) / 2.0));
+            s = (float)(std::sin(pit) / pit);
+        }
+        out[i] = window * s;
+        m = std::max(m, std::fabs(out[i]));
+    }
+    const float f = (float)(1.0 / m);   // normalize(): scaled by the largest magnitude
+    for (int i = 0; i != length; ++i) out[i] *= f;
+}
+static void sinc_bandpass(float sr, float lo, float hi, float *k29)       // filters.cpp:74-124
+{
+    enum { HALF = 1 + RVB_SINC_TAPS / 2 };
+    float lop[HALF], hip[HALF];
+    sinc_lopass(sr, hi, HALF, lop);
+    sinc_lopass(sr, lo, HALF, hip);
+    for (int i = 0; i != HALF; ++i) hip[i] = -hip[i];
+    hip[(HALF - 1) / 2] += 1;
+    for (int k = 0; k < RVB_SINC_TAPS; ++k) {   // FastConvolution(29): 29 * (lop (*) hip)
+        double acc = 0;
+        for (int j = 0; j < HALF; ++j) {
+            const int i = k - j;
+            if (i >= 0 && i < HALF) acc += (double)lop[j] * (double)hip[i];
+        }
+        k29[k] = (float)(acc * RVB_SINC_TAPS);
+    }
+}
+
+// out[row][n] = fft_len * sum_j k[band][j] * in[row][n - j]; rows of `in` have their own lengths
+__global__ void sinc_conv_kernel(const float *in, const uint32_t *in_off, const uint32_t *in_len, const float *kernels /*[8][29]*/,
+                                 uint32_t fft_len, float *out)
+{
+    const uint32_t row = blockIdx.y;
+    const float *x = in + in_off[row];
+    const uint32_t len = in_len[row];
+    const float *k = kernels + (row % RVB_NBANDS) * RVB_SINC_TAPS;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < fft_len; n += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < RVB_SINC_TAPS; ++j)
+            if (n >= (uint32_t)j && n - j < len) acc = __dadd_rn(acc, __dmul_rn((double)k[j], (double)x[n - j]));
+        out[(size_t)row * fft_len + n] = (float)__dmul_rn(acc, (double)fft_len);
+    }
+}
+
+// BandpassWindowedSinc over all channels: rows [nch][8][len_c] -> d_out [nch][8][fft_len],
+// fft_len = 29 + lengths[0] - 1 (the convolver is sized by the first channel, filters.cpp:280-283).
+static int sinc_device(const float *d_in, const size_t *lengths, size_t nch, float sr, float lo_cutoff, float *d_out, size_t fft_len)
+{
+    cudaStream_t st = lib_stream();
+    const float EDGES[9] = {lo_cutoff, 175, 350, 700, 1400, 2800, 5600, 11200, 20000};
+    std::vector<float> hk(RVB_NBANDS * RVB_SINC_TAPS);
+    for (int b = 0; b < RVB_NBANDS; ++b) sinc_bandpass(sr, EDGES[b], EDGES[b + 1], hk.data() + b * RVB_SINC_TAPS);
+    const size_t nrows = nch * RVB_NBANDS;
+    std::vector<uint32_t> off(nrows), len(nrows);
+    size_t o = 0;
+    for (size_t c = 0; c < nch; ++c) {
+        if (lengths[c] > fft_len)
+            return fail(RVB_ERR_INVALID, "windowed-sinc: a channel longer than the first overflows the reference's FFT buffer");
+        for (int b = 0; b < RVB_NBANDS; ++b) { off[c * RVB_NBANDS + b] = (uint32_t)o; len[c * RVB_NBANDS + b] = (uint32_t)lengths[c]; o += lengths[c]; }
+    }
+    float *d_k = nullptr; uint32_t *d_off = nullptr, *d_len = nullptr;
+    RVB_TRY(dev_alloc(&d_k, hk.size())); RVB_TRY(dev_alloc(&d_off, nrows)); RVB_TRY(dev_alloc(&d_len, nrows));
+    RVB_CUDA(cudaMemcpyAsync(d_k, hk.data(), hk.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    RVB_CUDA(cudaMemcpyAsync(d_off, off.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    RVB_CUDA(cudaMemcpyAsync(d_len, len.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    dim3 grid((unsigned)std::min<size_t>((fft_len + 255) / 256, 1024), (unsigned)nrows);
+    note_launch(), sinc_conv_kernel<<<grid, 256, 0, st>>>(d_in, d_off, d_len, d_k, (uint32_t)fft_len, d_out);
+    RVB_CUDA(cudaGetLastError());
+    RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_k); dev_free(d_off); dev_free(d_len);
+    return RVB_OK;
+}
+
 // RayverbFiltering::filter (filters.cpp:268-306) on device rows [nch][8][len_c]
 static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nch, float sr, float lo_cutoff)
 {
-    if (ft == RVB_FILTER_WINDOWED_SINC) return fail(RVB_ERR_UNSUPPORTED, "windowed-sinc filter is not implemented (SURVEY 8f rank 1)");
+    if (ft == RVB_FILTER_WINDOWED_SINC) return fail(RVB_ERR_INVALID, "the windowed-sinc filter changes the data length: use rvb_filter_sinc");
     if (ft < 0 || ft > RVB_FILTER_LINKWITZ_RILEY) return fail(RVB_ERR_INVALID, "unknown filter type");
     cudaStream_t st = lib_stream();
     const float EDGES[9] = {lo_cutoff, 175, 350, 700, 1400, 2800, 5600, 11200, 20000};
@@ -635,12 +724,35 @@ static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nc
 }
 
 // process (rayverb.cpp:125-149) on a device histogram; fills an Ir
+static int finish_filtered(const rvb_render_config *cfg, float *d_hist, const size_t *lengths, size_t nch, Ir *ir, bool keep_bands);
+
 static int finish_device(const rvb_render_config *cfg, float *d_hist /* modified */, const size_t *lengths, size_t nch, Ir *ir, bool keep_bands)
 {
     cudaStream_t st = lib_stream();
     Timer tf(st);
+    if (cfg->filter_type == RVB_FILTER_WINDOWED_SINC && nch > 0) {
+        // every channel grows to 29 + lengths[0] - 1 samples
+        const size_t fft_len = RVB_SINC_TAPS + lengths[0] - 1;
+        float *d_out = nullptr;
+        RVB_TRY(dev_alloc(&d_out, nch * RVB_NBANDS * fft_len));
+        int rc = sinc_device(d_hist, lengths, nch, cfg->sample_rate, cfg->lo_cutoff, d_out, fft_len);
+        g_stats.filter_ms += tf.stop();
+        if (rc == RVB_OK) {
+            std::vector<size_t> grown(nch, fft_len);
+            rc = finish_filtered(cfg, d_out, grown.data(), nch, ir, keep_bands);
+        }
+        dev_free(d_out);
+        return rc;
+    }
     RVB_TRY(filter_device(cfg->filter_type, d_hist, lengths, nch, cfg->sample_rate, cfg->lo_cutoff));
     g_stats.filter_ms += tf.stop();
+    return finish_filtered(cfg, d_hist, lengths, nch, ir, keep_bands);
+}
+
+// mixdown + normalize + scale + trimTail on already filtered rows (rayverb.cpp:136-148)
+static int finish_filtered(const rvb_render_config *cfg, float *d_hist, const size_t *lengths, size_t nch, Ir *ir, bool keep_bands)
+{
+    cudaStream_t st = lib_stream();
     Timer tm(st);
     size_t total = 0;
     for (size_t c = 0; c < nch; ++c) total += lengths[c];
@@ -917,6 +1029,27 @@ int rvb_filter(int filter_type, float *data, size_t nchannels, size_t length, fl
     return rc;
 }
 
+int rvb_filter_sinc(const float *in, size_t nchannels, size_t length, float sample_rate, float lo_cutoff, float *out)
+{
+    if ((!in || !out) && nchannels) return fail(RVB_ERR_INVALID, "null argument");
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    if (nchannels == 0) return RVB_OK;
+    const size_t fft_len = RVB_SINC_TAPS + length - 1;
+    float *d_in = nullptr, *d_out = nullptr;
+    RVB_TRY(dev_alloc(&d_in, std::max<size_t>(1, nchannels * RVB_NBANDS * length)));
+    RVB_TRY(dev_alloc(&d_out, nchannels * RVB_NBANDS * fft_len));
+    if (length) RVB_CUDA(cudaMemcpyAsync(d_in, in, nchannels * RVB_NBANDS * length * sizeof(float), cudaMemcpyHostToDevice, st));
+    std::vector<size_t> lens(nchannels, length);
+    int rc = sinc_device(d_in, lens.data(), nchannels, sample_rate, lo_cutoff, d_out, fft_len);
+    if (rc == RVB_OK) {
+        cudaMemcpyAsync(out, d_out, nchannels * RVB_NBANDS * fft_len * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    dev_free(d_in); dev_free(d_out);
+    return rc;
+}
+
 int rvb_process(int filter_type, float *const *data, const size_t *lengths, size_t nchannels, float sample_rate, int do_normalize,
                 float lo_cutoff, int do_trim_tail, float volume_scale, float *const *out, int64_t *out_length)
 {
@@ -938,11 +1071,14 @@ int rvb_process(int filter_type, float *const *data, const size_t *lengths, size
     Ir ir;
     int rc = finish_device(&cfg, d, lengths, nchannels, &ir, true);
     if (rc == RVB_OK) {
+        const bool sinc = filter_type == RVB_FILTER_WINDOWED_SINC;
         *out_length = do_trim_tail ? (int64_t)(nchannels ? ir.channels[0].size() : 0) : -1;
         for (size_t c = 0; c < nchannels; ++c) {
-            // like the reference, `data` ends up filtered in place (rayverb.cpp:135)
-            std::copy(ir.bands[c].begin(), ir.bands[c].end(), data[c]);
-            size_t m = std::min(ir.channels[c].size(), lengths[c]);
+            // like the reference, `data` ends up filtered in place (rayverb.cpp:135) -- except for the
+            // windowed sinc, whose rows grow to 29 + lengths[0] - 1 and do not fit back
+            if (!sinc) std::copy(ir.bands[c].begin(), ir.bands[c].end(), data[c]);
+            const size_t cap = sinc ? RVB_SINC_TAPS + lengths[0] - 1 : lengths[c];
+            size_t m = std::min(ir.channels[c].size(), cap);
             std::copy(ir.channels[c].begin(), ir.channels[c].begin() + m, out[c]);
         }
     }

@@ -15,7 +15,8 @@ namespace RayverbFiltering
 
     /// data[channel][band][sample] is band-pass filtered in place with the band edges
     /// {lo_cutoff, 175, 350, 700, 1400, 2800, 5600, 11200, 20000} (filters.cpp:268-306).
-    /// Throws std::runtime_error for FILTER_TYPE_WINDOWED_SINC (not implemented yet).
+    /// FILTER_TYPE_WINDOWED_SINC grows every band to 29 + (length of the first band) - 1 samples,
+    /// scaled by that length like the reference's un-normalised FFT round trip.
     void filter
     (   FilterType ft
     ,   std::vector <std::vector <std::vector <float>>> & data

@@ -96,6 +96,30 @@ namespace
 
 void RayverbFiltering::filter (FilterType ft, vector <vector <vector <float>>> & data, float sr, float lo_cutoff)
 {
+    if (ft == FILTER_TYPE_WINDOWED_SINC)
+    {
+        //  The convolver is sized once by the first channel's first band (filters.cpp:280-283):
+        //  every band of every channel comes back with 29 + that length - 1 samples.
+        if (data.empty()) return;
+        const size_t len = data.front().front().size();
+        vector <float> packed (data.size() * RVB_NBANDS * len, 0.0f);
+        for (size_t c = 0; c != data.size(); ++c)
+            for (int b = 0; b != RVB_NBANDS; ++b)
+            {
+                if (data [c] [b].size() > len + RVB_SINC_KERNEL_LENGTH - 1)
+                    throw runtime_error ("windowed-sinc: a channel longer than the first overflows the convolution buffer");
+                if (data [c] [b].size() > len)   // fits the FFT buffer of the reference, not this packed layout
+                    throw runtime_error ("windowed-sinc: channels longer than the first are not supported");
+                copy (data [c] [b].begin(), data [c] [b].end(), packed.begin() + (c * RVB_NBANDS + b) * len);
+            }
+        const size_t grown = len + RVB_SINC_KERNEL_LENGTH - 1;
+        vector <float> out (data.size() * RVB_NBANDS * grown);
+        check (rvb_filter_sinc (packed.data(), data.size(), len, sr, lo_cutoff, out.data()));
+        for (size_t c = 0; c != data.size(); ++c)
+            for (int b = 0; b != RVB_NBANDS; ++b)
+                data [c] [b].assign (out.begin() + (c * RVB_NBANDS + b) * grown, out.begin() + (c * RVB_NBANDS + b + 1) * grown);
+        return;
+    }
     for (auto && channel : data)
     {
         size_t len = 0;
@@ -116,6 +140,25 @@ vector <vector <float>> process
 )
 {
     const size_t nch = data.size();
+    if (filtertype == RayverbFiltering::FILTER_TYPE_WINDOWED_SINC && nch != 0)
+    {
+        //  The rows grow to 29 + (first length) - 1: the device computes the processed channels from
+        //  the unfiltered data, then `data` itself is filtered (and grown) as the reference leaves it.
+        vector <vector <float>> packed (nch);
+        vector <size_t> lengths (nch);
+        vector <float *> in (nch), out (nch);
+        for (size_t c = 0; c != nch; ++c) packed [c] = packChannel (data [c], lengths [c]);
+        const size_t grown = lengths [0] + RVB_SINC_KERNEL_LENGTH - 1;
+        vector <vector <float>> ret (nch, vector <float> (grown, 0.0f));
+        for (size_t c = 0; c != nch; ++c) { in [c] = packed [c].data(); out [c] = ret [c].data(); }
+        int64_t trimmed = -1;
+        check (rvb_process ((int) filtertype, in.data(), lengths.data(), nch, sr, do_normalize, lo_cutoff, do_trim_tail,
+                            volumme_scale, out.data(), &trimmed));
+        if (trimmed >= 0)
+            for (auto && ch : ret) ch.resize ((size_t) trimmed);
+        RayverbFiltering::filter (filtertype, data, sr, lo_cutoff);
+        return ret;
+    }
     vector <vector <float>> packed (nch);
     vector <size_t> lengths (nch);
     vector <float *> in (nch), out (nch);

@@ -168,10 +168,12 @@ static void postprocess_test()
     auto out = process (RayverbFiltering::FILTER_TYPE_LINKWITZ_RILEY, flat, 44100.0f, true, 45.0f, false, 1.0f);
     EXPECT_TRUE (out.size() == 2 && out [0].size() == 11);
     EXPECT_FLOAT_EQ (max_amp (out), 1.0f);
-    bool threw = false;
-    try { process (RayverbFiltering::FILTER_TYPE_WINDOWED_SINC, flat, 44100.0f, true, 45.0f, false, 1.0f); }
-    catch (const runtime_error &) { threw = true; }
-    EXPECT_TRUE (threw);
+    //  windowed sinc: the data grows by 28 samples (filters.cpp:126-131)
+    auto flat2 = flattenImpulses (channels, 1000.0f);
+    const size_t before = flat2 [0] [0].size();
+    auto sinc = process (RayverbFiltering::FILTER_TYPE_WINDOWED_SINC, flat2, 44100.0f, true, 45.0f, false, 1.0f);
+    EXPECT_TRUE (sinc.size() == 2 && sinc [0].size() == before + 28 && flat2 [0] [0].size() == before + 28);
+    EXPECT_FLOAT_EQ (max_amp (sinc), 1.0f);
 }
 
 int main (int argc, char ** argv)

@@ -55,7 +55,7 @@ EXPORTS = [
     "rvb_trace_image_count", "rvb_trace_copy_images", "rvb_trace_set_images", "rvb_images_merge",
     "rvb_trace_copy_debug", "rvb_trace_get_stats",
     "rvb_attenuate_speaker", "rvb_attenuate_hrtf",
-    "rvb_flatten", "rvb_filter", "rvb_process", "rvb_free",
+    "rvb_flatten", "rvb_filter", "rvb_filter_sinc", "rvb_process", "rvb_free",
     "rvb_render_ir", "rvb_render_times", "rvb_render_histogram", "rvb_render_finish",
     "rvb_ir_channels", "rvb_ir_length", "rvb_ir_copy", "rvb_ir_band_length", "rvb_ir_copy_bands", "rvb_ir_destroy",
     "rvb_render_get_stats", "rvb_render_keep_bands",
@@ -101,6 +101,7 @@ def lib():
         L.rvb_attenuate_hrtf.argtypes = [vp, sz, vp, vp, vp, vp, u64, vp]
         L.rvb_flatten.argtypes = [vp, sz, f32, vp, vp]
         L.rvb_filter.argtypes = [i32, vp, sz, sz, f32, f32]
+        L.rvb_filter_sinc.argtypes = [vp, sz, sz, f32, f32, vp]
         L.rvb_process.argtypes = [i32, vp, vp, sz, f32, i32, f32, i32, f32, vp, vp]
         L.rvb_render_ir.argtypes = [vp, vp, vp]
         L.rvb_render_times.argtypes = [vp, vp, vp, vp, vp]
@@ -426,6 +427,10 @@ def filter_bands(ft, data, sr, lo_cutoff):
     """RayverbFiltering::filter (filters.cpp:268-306) on [nch, 8, L]; returns a filtered copy."""
     d = np.array(data, dtype=np.float32, order="C", copy=True)
     assert d.ndim == 3 and d.shape[1] == NBANDS
+    if _filter_id(ft) == 0:   # windowed sinc: the data grows by 28 samples
+        out = np.zeros((d.shape[0], NBANDS, d.shape[2] + 28), dtype=np.float32)
+        _check(lib().rvb_filter_sinc(_p(d), d.shape[0], d.shape[2], C.c_float(sr), C.c_float(lo_cutoff), _p(out)))
+        return out
     _check(lib().rvb_filter(_filter_id(ft), _p(d), d.shape[0], d.shape[2], C.c_float(sr), C.c_float(lo_cutoff)))
     return d
 
@@ -434,7 +439,8 @@ def process(ft, flattened, sr, do_normalize=True, lo_cutoff=45.0, do_trim_tail=T
     """process() (rayverb.cpp:125-149) on a list of [8, L_c] arrays."""
     data = [np.array(f, dtype=np.float32, order="C", copy=True) for f in flattened]
     lens = np.array([d.shape[1] for d in data], dtype=np.uint64)
-    outs = [np.zeros(int(l), dtype=np.float32) for l in lens]
+    sinc = _filter_id(ft) == 0
+    outs = [np.zeros(int(lens[0]) + 28 if sinc else int(l), dtype=np.float32) for l in lens]
     dptr = (C.c_void_p * len(data))(*[d.ctypes.data for d in data])
     optr = (C.c_void_p * len(outs))(*[o.ctypes.data for o in outs])
     out_len = C.c_int64(-1)

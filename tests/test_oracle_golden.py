@@ -140,3 +140,24 @@ def test_image_sources_match_shoebox_lattice(orc):
         assert sel.sum() > 0
         assert all(np.min(np.abs(lat - x)) < 1e-3 for x in dist)
     assert (klen == 2).sum() == 6                            # all six first-order images found
+
+
+def test_windowed_sinc_restatement_equals_fft_round_trip(orc):
+    """The reference convolves through FFTW (r2c * r2c -> un-normalised c2r, filters.h:56-80); the
+    oracle restates that as FFT_LENGTH x direct convolution.  Emulate the reference's algorithm
+    with a double-precision FFT and compare."""
+    def fftconv(a, b, n):
+        return np.fft.irfft(np.fft.rfft(a, n) * np.fft.rfft(b, n), n) * n
+    sr = 44100.0
+    edges = [45.0, 175, 350, 700, 1400, 2800, 5600, 11200, 20000]
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((8, 3000)) * np.exp(-np.arange(3000) / 500.0)).astype(np.float32)
+    y = orc.filter_channel_sinc(x, sr, 45.0)
+    assert y.shape == (8, 3028)
+    for b in range(8):
+        k = orc.sinc_bandpass_kernel(sr, edges[b], edges[b + 1])
+        ref = fftconv(k.astype(np.float64), x[b].astype(np.float64), 3028)
+        assert np.linalg.norm(y[b] - ref) <= 1e-6 * np.linalg.norm(ref)
+    # the 29-tap kernel itself is an FFT convolution of two 15-tap kernels with length 29 (x29)
+    k = orc.sinc_bandpass_kernel(sr, 175.0, 350.0)
+    assert k.shape == (29,) and abs(k[14]) == np.abs(k).max()
