@@ -132,38 +132,63 @@ __global__ void refit_kernel(const Aabb *tri_boxes, const uint32_t *ids, int n, 
     }
 }
 
-__device__ __forceinline__ void child_ref(int c, const int2 *ranges, const Aabb *tri_boxes, const uint32_t *ids, const Aabb *node_boxes,
-                                          float pad, int &ref, float4 &lo, float4 &hi)
+struct Slot { int ref; Aabb box; };
+
+// reference + box of binary child c as seen from a 4-wide parent: a single triangle, a collapsed
+// subtree (<= RVB_LEAF_MAX triangles, contiguous in sorted order) or an inner node
+__device__ __forceinline__ Slot make_slot(int c, const int2 *ranges, const Aabb *tri_boxes, const uint32_t *ids, const Aabb *node_boxes)
 {
-    Aabb b;
+    Slot s;
     if (c < 0) {
-        b = tri_boxes[ids[~c]];
-        ref = ~(int)((uint32_t)(~c));                         // leaf: first = position, count 1
+        s.box = tri_boxes[ids[~c]];
+        s.ref = c;                                             // leaf: first = position, count 1
     } else {
-        b = node_boxes[c];
-        int2 r = ranges[c];
-        int cnt = r.y - r.x + 1;
-        if (cnt <= RVB_LEAF_MAX) ref = ~(int)((uint32_t)r.x | ((uint32_t)(cnt - 1) << 28));   // collapsed subtree
-        else ref = c;
+        s.box = node_boxes[c];
+        const int2 r = ranges[c];
+        const int cnt = r.y - r.x + 1;
+        s.ref = cnt <= RVB_LEAF_MAX ? ~(int)((uint32_t)r.x | ((uint32_t)(cnt - 1) << 28)) : c;
     }
-    lo = make_float4(b.lo.x - pad, b.lo.y - pad, b.lo.z - pad, 0.f);
-    hi = make_float4(b.hi.x + pad, b.hi.y + pad, b.hi.z + pad, 0.f);
+    return s;
 }
 
+// 4-wide node of binary inner node i: its two children, each replaced by ITS two children when it
+// is a (non-collapsed) inner node.  Only nodes reachable from the root this way are ever visited.
 __global__ void emit_nodes_kernel(int n, const int2 *children, const int2 *ranges, const Aabb *tri_boxes, const uint32_t *ids,
                                   const Aabb *node_boxes, float pad, BvhNode *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    int2 c = children[i];
-    int rl, rr;
-    float4 ll, lh, rlo, rhi;
-    child_ref(c.x, ranges, tri_boxes, ids, node_boxes, pad, rl, ll, lh);
-    child_ref(c.y, ranges, tri_boxes, ids, node_boxes, pad, rr, rlo, rhi);
+    Slot slots[4];
+    int ns = 0;
+    const int2 c = children[i];
+    const int kids[2] = {c.x, c.y};
+    for (int k = 0; k < 2; ++k) {
+        const Slot s = make_slot(kids[k], ranges, tri_boxes, ids, node_boxes);
+        if (s.ref >= 0) {   // inner: expand
+            const int2 g = children[s.ref];
+            slots[ns++] = make_slot(g.x, ranges, tri_boxes, ids, node_boxes);
+            slots[ns++] = make_slot(g.y, ranges, tri_boxes, ids, node_boxes);
+        } else slots[ns++] = s;
+    }
+    float lo[3][4], hi[3][4];
+    int ref[4];
+    for (int k = 0; k < 4; ++k) {
+        if (k < ns) {
+            const Aabb &b = slots[k].box;
+            lo[0][k] = b.lo.x - pad; lo[1][k] = b.lo.y - pad; lo[2][k] = b.lo.z - pad;
+            hi[0][k] = b.hi.x + pad; hi[1][k] = b.hi.y + pad; hi[2][k] = b.hi.z + pad;
+            ref[k] = slots[k].ref;
+        } else {
+            for (int a = 0; a < 3; ++a) { lo[a][k] = 3e38f; hi[a][k] = -3e38f; }
+            ref[k] = RVB_BVH_EMPTY;
+        }
+    }
     BvhNode nd;
-    nd.lo_l = make_float4(ll.x, ll.y, ll.z, __int_as_float(rl));
-    nd.hi_l = make_float4(lh.x, lh.y, lh.z, __int_as_float(rr));
-    nd.lo_r = rlo; nd.hi_r = rhi;
+    nd.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); nd.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+    nd.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); nd.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+    nd.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]); nd.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+    nd.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    nd.pad = make_float4(0.f, 0.f, 0.f, 0.f);
     out[i] = nd;
 }
 

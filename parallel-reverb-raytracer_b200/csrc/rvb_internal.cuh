@@ -61,15 +61,17 @@ inline void dev_free(T *&p)
 }
 
 // ---- BVH node (see bvh.cu) ------------------------------------------------------------------
-// 64-byte node holding BOTH children's boxes, so one visit decides both descents.
+// 4-wide node, one 128-byte line: the boxes of up to four children in SoA form (slot k of every
+// float4), so one visit decides four descents and the dependent-load chain is half as long as with
+// a binary tree.  Child ref: >= 0 -> inner node index; < 0 (and != RVB_BVH_EMPTY) -> leaf:
+// ~ref = first position in the sorted triangle order | (count - 1) << 28.  Unused slots carry
+// RVB_BVH_EMPTY and an inverted box.
+#define RVB_BVH_EMPTY ((int)0x80000001)
 struct __align__(16) BvhNode {
-    float4 lo_l;   // left  box min xyz, w = bits of left  child ref
-    float4 hi_l;   // left  box max xyz, w = bits of right child ref
-    float4 lo_r;   // right box min xyz, w = unused
-    float4 hi_r;   // right box max xyz, w = unused
+    float4 lox, loy, loz, hix, hiy, hiz;
+    int4 ref;
+    float4 pad;
 };
-// child ref: >= 0 -> inner node index; < 0 -> leaf: ~ref = first position in the sorted
-// triangle order, leaf covers `leaf_count` consecutive positions (stored in the high bits)
 
 // ---- scene ----------------------------------------------------------------------------------
 struct Scene {

@@ -18,6 +18,8 @@
 //
 // Output is a bounce-major SoA (slot = bounce * nrays + ray) so that the 32 lanes of a warp,
 // which sit at the same bounce, write 32 consecutive 32-byte sectors.
+#include <cstdlib>
+
 #include "rvb_internal.cuh"
 
 namespace rvb {
@@ -104,17 +106,49 @@ struct BvhAccel {
     const float4 *tri;       // sorted (v0,e0,e1)
     const uint32_t *order;   // sorted position -> original index
 
-    __device__ __forceinline__ static bool slab(float4 lo, float4 hi, f3 o, f3 inv, float tmax, float &tnear)
+    __device__ __forceinline__ static bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, f3 o, f3 inv,
+                                                float tmax, float &tnear)
     {
-        float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
-        float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
-        float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
+        float tx0 = (lox - o.x) * inv.x, tx1 = (hix - o.x) * inv.x;
+        float ty0 = (loy - o.y) * inv.y, ty1 = (hiy - o.y) * inv.y;
+        float tz0 = (loz - o.z) * inv.z, tz1 = (hiz - o.z) * inv.z;
         float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
         float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
         tnear = tn;
         // fminf/fmaxf drop NaNs (0 * inf on a face-parallel ray exactly on the slab plane), which
         // widens the interval: conservative.  1.00001f covers the rounding of the six products.
         return tn <= tf * 1.00001f + 1e-6f;
+    }
+
+    // One visit of a 4-wide node: test the four child boxes, continue with the nearest hit child
+    // and push the others so that the nearer ones are popped first.  Returns the next node.
+    __device__ __forceinline__ static int visit(const BvhNode *nodes, int node, f3 pos, f3 inv, float tbest, int *stack, int &sp)
+    {
+        const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+        const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
+        const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
+        const int4 ref = __ldg(reinterpret_cast<const int4 *>(np + 6));
+        // candidates farther than the best are useless; equal t must still be visited (tie-break)
+        const float lim = tbest * 1.00001f + 1e-6f;
+        const float INF = RVB_INF;
+        float t0, t1, t2, t3;
+        if (!slab(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, pos, inv, lim, t0)) t0 = INF;
+        if (!slab(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, pos, inv, lim, t1)) t1 = INF;
+        if (!slab(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, pos, inv, lim, t2)) t2 = INF;
+        if (!slab(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, pos, inv, lim, t3)) t3 = INF;
+        int r0 = ref.x, r1 = ref.y, r2 = ref.z, r3 = ref.w;
+        // slots 0 and 1 always exist; the min/max slab form would accept an unused slot's box
+        if (r2 == RVB_BVH_EMPTY) t2 = INF;
+        if (r3 == RVB_BVH_EMPTY) t3 = INF;
+        // sorting network on (t, ref), ascending; misses carry +inf
+#define RVB_CSWAP(ta, ra, tb, rb) { const bool sw = tb < ta; const float tt = sw ? tb : ta; const int rr = sw ? rb : ra; \
+                                    tb = sw ? ta : tb; rb = sw ? ra : rb; ta = tt; ra = rr; }
+        RVB_CSWAP(t0, r0, t1, r1) RVB_CSWAP(t2, r2, t3, r3) RVB_CSWAP(t0, r0, t2, r2) RVB_CSWAP(t1, r1, t3, r3) RVB_CSWAP(t1, r1, t2, r2)
+#undef RVB_CSWAP
+        if (t3 < INF) stack[sp++] = r3;
+        if (t2 < INF) stack[sp++] = r2;
+        if (t1 < INF) stack[sp++] = r1;
+        return t0 < INF ? r0 : stack[--sp];
     }
 
     template <bool ANY>
@@ -127,50 +161,41 @@ struct BvhAccel {
         if (dir.z == 0.0f) inv.z = RVB_INF;
         tbest = tlimit;
         ibest = RVB_NONE;
+        // while-while traversal: every lane first walks inner nodes until it holds a leaf (or is
+        // done), then the leaves are intersected together -- inner-node code and triangle code are
+        // never interleaved inside a warp.
+        const int SENTINEL = (int)0x80000000;   // leaf refs are >= -2^30, inner nodes >= 0
         int stack[64];
         int sp = 0;
+        stack[sp++] = SENTINEL;
         int node = 0;
         uint32_t nbox = 0, ntri = 0;
         bool found = false;
-        while (true) {
-            if (node >= 0) {
-                const BvhNode n = nodes[node];
-                float tl, tr;
-                // candidates farther than the best are useless; equal t must still be visited (tie-break)
-                float lim = tbest * 1.00001f + 1e-6f;
-                bool hl = slab(n.lo_l, n.hi_l, pos, inv, lim, tl);
-                bool hr = slab(n.lo_r, n.hi_r, pos, inv, lim, tr);
-                nbox += 2;
-                int cl = __float_as_int(n.lo_l.w), cr = __float_as_int(n.hi_l.w);
-                if (hl && hr) {
-                    if (tr < tl) { int t_ = cl; cl = cr; cr = t_; }
-                    stack[sp++] = cr;
-                    node = cl;
-                    continue;
-                } else if (hl) { node = cl; continue; }
-                else if (hr) { node = cr; continue; }
-            } else {
-                uint32_t ref = ~(uint32_t)node;
-                uint32_t first = ref & 0x0fffffffu, cnt = (ref >> 28) + 1;
+        while (node != SENTINEL) {
+            while (node >= 0) {
+                node = visit(nodes, node, pos, inv, tbest, stack, sp);
+                nbox += 4;
+            }
+            while (node < 0 && node != SENTINEL) {
+                const uint32_t ref = ~(uint32_t)node;
+                const uint32_t first = ref & 0x0fffffffu, cnt = (ref >> 28) + 1;
                 for (uint32_t k = 0; k < cnt; ++k) {
-                    uint32_t p = first + k;
-                    float4 A = __ldg(tri + 3 * p), B = __ldg(tri + 3 * p + 1), C = __ldg(tri + 3 * p + 2);
+                    const uint32_t p = first + k;
+                    const float4 A = __ldg(tri + 3 * p), B = __ldg(tri + 3 * p + 1), C = __ldg(tri + 3 * p + 2);
                     bool ok;
-                    float t = mt_intersect_pred(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), mk3(B.z, B.w, C.x), pos, dir, ok);
+                    const float t = mt_intersect_pred(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), mk3(B.z, B.w, C.x), pos, dir, ok);
                     ++ntri;
                     if (ok && t > RVB_EPSILON) {
                         if (ANY) {
-                            if (t <= tlimit) { found = true; }
+                            if (t <= tlimit) found = true;
                         } else {
-                            uint32_t oi = __ldg(order + p);
+                            const uint32_t oi = __ldg(order + p);
                             if (t < tbest || (t == tbest && oi < ibest)) { tbest = t; ibest = oi; }
                         }
                     }
                 }
-                if (ANY && found) break;
+                node = (ANY && found) ? SENTINEL : stack[--sp];
             }
-            if (sp == 0) break;
-            node = stack[--sp];
         }
         c.queries++; c.tri += ntri; c.box += nbox;
         return ANY ? found : (ibest != RVB_NONE);
@@ -539,6 +564,218 @@ static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
     return launch_phase(trace_bruteforce_kernel<IMAGES, 256>, P, 256, smem, st);
 }
 
+// =================================================================================================
+// Wavefront form of the steady phase for the BVH path.
+//
+// Thread-per-ray traversal leaves most lanes idle: traversal lengths differ from ray to ray and a
+// warp runs until its slowest lane is done (ncu: 10.8 of 32 threads active per instruction).  Here
+// every reflection is three launches over the ray-state records in HBM:
+//   wf_traverse<false>  persistent warps, dynamic ray fetch: a lane that finishes its query pulls
+//                       the next ray from a global counter, so lanes stay busy; nearest hit
+//   wf_traverse<true>   same, any-hit visibility query from the hit point to the microphone
+//   wf_emit             one thread per ray: shade, emit the impulse, reflect (kernel.cpp:459-501)
+// The arithmetic is the same device code as the per-ray kernels (same bits).
+// =================================================================================================
+struct WfParams {
+    TraceParams P;
+    float4 *hit;              // [nrays] x = t, y = triangle (bits), z = blocked (0/1)
+    unsigned int *fetch;      // one work counter per launch
+};
+
+#define RVB_WF_REFETCH 20     // go back for more rays when fewer lanes than this are still traversing
+
+template <bool ANY>
+__global__ void __launch_bounds__(128) wf_traverse_kernel(const WfParams W)
+{
+    const TraceParams &P = W.P;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+    const int SENTINEL = (int)0x80000000;
+    int stack[64];
+    int sp = 0, node = SENTINEL;
+    bool has = false, exhausted = false, found = false;
+    uint32_t ray = 0, ibest = RVB_NONE, nbox = 0, ntri = 0, nq = 0;
+    float tbest = 0.f, tlimit = 0.f;
+    f3 pos = mk3(0.f, 0.f, 0.f), dir = pos, inv = pos;
+
+    while (true) {
+        // ---- refill idle lanes ---------------------------------------------------------------
+        bool want = !has && !exhausted;
+        while (true) {
+            const unsigned m = __ballot_sync(FULL, want);
+            if (!m) break;
+            const int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(W.fetch, (unsigned)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (want) {
+                const uint32_t r = base + __popc(m & ((1u << lane) - 1u));
+                if (r >= P.nrays) { want = false; exhausted = true; }
+                else {
+                    const float4 s0 = P.state[4 * (size_t)r], s1 = P.state[4 * (size_t)r + 1];
+                    bool live = s1.w != 0.0f;
+                    f3 o = mk3(s0), d = mk3(s1);
+                    float lim = RVB_INF;
+                    if (ANY && live) {   // visibility from the hit point to the microphone (kernel.cpp:274-296)
+                        const float4 h = W.hit[r];
+                        live = __float_as_uint(h.y) != RVB_NONE;
+                        if (live) {
+                            const f3 X = madd(o, d, h.x);
+                            const f3 btp = mic - X;
+                            lim = length(btp);
+                            d = normalize(btp);
+                            o = X;
+                        }
+                    }
+                    if (live) {
+                        ray = r; pos = o; dir = d; tlimit = lim;
+                        inv = mk3(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
+                        if (d.x == 0.0f) inv.x = RVB_INF;
+                        if (d.y == 0.0f) inv.y = RVB_INF;
+                        if (d.z == 0.0f) inv.z = RVB_INF;
+                        tbest = lim; ibest = RVB_NONE; found = false;
+                        sp = 0; stack[sp++] = SENTINEL; node = 0;
+                        has = true; want = false;
+                    }
+                    // dead rays are skipped: keep asking
+                }
+            }
+        }
+        if (!__any_sync(FULL, has)) break;
+
+        // ---- traverse (same loops as BvhAccel::traverse) -------------------------------------------
+        while (node != SENTINEL) {
+            while (node >= 0) {
+                node = BvhAccel::visit(P.nodes, node, pos, inv, tbest, stack, sp);
+                nbox += 4;
+            }
+            while (node < 0 && node != SENTINEL) {
+                const uint32_t ref = ~(uint32_t)node;
+                const uint32_t first = ref & 0x0fffffffu, cnt = (ref >> 28) + 1;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const uint32_t p = first + k;
+                    const float4 A = __ldg(P.tri_sorted + 3 * p), B = __ldg(P.tri_sorted + 3 * p + 1), C = __ldg(P.tri_sorted + 3 * p + 2);
+                    bool ok;
+                    const float t = mt_intersect_pred(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), mk3(B.z, B.w, C.x), pos, dir, ok);
+                    ++ntri;
+                    if (ok && t > RVB_EPSILON) {
+                        if (ANY) {
+                            if (t <= tlimit) found = true;
+                        } else {
+                            const uint32_t oi = __ldg(P.order + p);
+                            if (t < tbest || (t == tbest && oi < ibest)) { tbest = t; ibest = oi; }
+                        }
+                    }
+                }
+                node = (ANY && found) ? SENTINEL : stack[--sp];
+            }
+            if (__popc(__activemask()) < RVB_WF_REFETCH) break;   // heuristic only: results do not depend on it
+        }
+        if (has && node == SENTINEL) {
+            float4 h = ANY ? W.hit[ray] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ANY) h.z = found ? 1.0f : 0.0f;
+            else { h.x = tbest; h.y = __uint_as_float(ibest); }
+            W.hit[ray] = h;
+            has = false;
+            ++nq;
+        }
+    }
+    Counters c;
+    c.queries = nq; c.tri = ntri; c.box = nbox;
+    flush_counters(P, c);
+}
+
+// the visibility answer was computed by wf_traverse<true>
+struct KnownVisibility {
+    bool blocked;
+    __device__ __forceinline__ bool occluded(f3, f3, float, Counters &) const { return blocked; }
+};
+
+__global__ void __launch_bounds__(256) wf_emit_kernel(const WfParams W)
+{
+    const TraceParams &P = W.P;
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters c;
+    if (ray < P.nrays) {
+        const uint32_t index = P.first;
+        float4 *s = P.state + 4 * (size_t)ray;
+        const float4 a = s[0], d = s[1];
+        bool alive = d.w != 0.0f;
+        uint32_t prim = RVB_NONE;
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (alive) {
+            h = W.hit[ray];
+            prim = __float_as_uint(h.y);
+            if (prim == RVB_NONE) { alive = false; s[1] = make_float4(d.x, d.y, d.z, 0.0f); }   // left the mesh (kernel.cpp:372-375)
+        }
+        if (!alive) {
+            // zero impulse in this slot (rayverb.cpp:601-603)
+            const size_t slot = (size_t)index * P.nrays + ray;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            P.vol[2 * slot] = z; P.vol[2 * slot + 1] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
+            if (P.hit) P.hit[slot] = RVB_NONE;
+        } else {
+            const float4 va = s[2], vb = s[3];
+            RayState R;
+            R.pos = mk3(a); R.distance = a.w; R.dir = mk3(d);
+            R.volume[0] = va.x; R.volume[1] = va.y; R.volume[2] = va.z; R.volume[3] = va.w;
+            R.volume[4] = vb.x; R.volume[5] = vb.y; R.volume[6] = vb.z; R.volume[7] = vb.w;
+            const KnownVisibility vis{h.z != 0.0f};
+            const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+            shade_and_reflect(vis, P, mic, ray, index, h.x, prim, R, c);
+            store_state(P, ray, R, true);
+            c.bounces = 1;
+            if (P.count) P.count[ray] += 1;
+        }
+    }
+    c.queries = 0;
+    flush_counters(P, c);
+}
+
+// reflections [first, last) of the BVH path, three launches each
+static int launch_wavefront(TraceParams P, uint32_t first, uint32_t last, bool fresh, cudaStream_t st)
+{
+    WfParams W{};
+    W.P = P;
+    const uint32_t nb = last - first;
+    RVB_TRY(dev_alloc(&W.hit, (size_t)P.nrays));
+    RVB_TRY(dev_alloc(&W.fetch, 2 * (size_t)nb));
+    RVB_CUDA(cudaMemsetAsync(W.fetch, 0, 2 * (size_t)nb * sizeof(unsigned), st));
+    unsigned *fetch0 = W.fetch;
+    int per_sm = 0;
+    RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_traverse_kernel<false>, 128, 0));
+    const unsigned tgrid = (unsigned)std::min<size_t>(((size_t)P.nrays + 127) / 128, (size_t)std::max(per_sm, 1) * sm_count());
+    const unsigned egrid = (unsigned)(((size_t)P.nrays + 255) / 256);
+    (void)fresh;
+    for (uint32_t b = first; b < last; ++b) {
+        W.P.first = b; W.P.last = b + 1;
+        W.fetch = fetch0 + 2 * (b - first);
+        note_launch(), wf_traverse_kernel<false><<<tgrid, 128, 0, st>>>(W);
+        W.fetch = fetch0 + 2 * (b - first) + 1;
+        note_launch(), wf_traverse_kernel<true><<<tgrid, 128, 0, st>>>(W);
+        note_launch(), wf_emit_kernel<<<egrid, 256, 0, st>>>(W);
+    }
+    RVB_CUDA(cudaGetLastError());
+    W.fetch = fetch0;
+    dev_free(W.hit); dev_free(W.fetch);
+    return RVB_OK;
+}
+
+// ray state for a trace that starts in the steady phase (RVB_TRACE_NO_IMAGES)
+__global__ void wf_init_state_kernel(const TraceParams P)
+{
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= P.nrays) return;
+    const float4 d = __ldg(P.dirs + ray);
+    float4 *s = P.state + 4 * (size_t)ray;
+    s[0] = make_float4(P.src[0], P.src[1], P.src[2], 0.0f);
+    s[1] = make_float4(d.x, d.y, d.z, 1.0f);
+    s[2] = make_float4(1.f, 1.f, 1.f, 1.f);
+    s[3] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (P.count) P.count[ray] = 0;
+}
+
 int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB, float4 *d_cand_pt,
                  uint32_t *d_cand_idx)
 {
@@ -565,9 +802,13 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     const bool images = !(tr->flags & RVB_TRACE_NO_IMAGES);
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
     float4 *d_state = nullptr;
-    if (split > 0 && split < tr->nrefl) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
-    P.state = d_state;
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
+    // The wavefront form (see launch_wavefront) measured SLOWER than one thread per ray on B200
+    // (C3, 1 Mi rays: 126 ms vs 106 ms): the traversal is bound by dependent L1/L2 round trips, not
+    // by idle lanes.  It stays available for experiments behind RVB_WAVEFRONT=1.
+    static const bool wavefront = getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '1';
+    if (split < tr->nrefl && (split > 0 || (!brute && wavefront))) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
+    P.state = d_state;
     const size_t smem = brute ? (size_t)3 * sc->T * sizeof(float4) : 0;
 
     cudaEvent_t e0, e1, em;
@@ -588,7 +829,13 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
             if (brute) RVB_TRY(launch_bruteforce<false>(P, smem, st));
-            else RVB_TRY(launch_phase(trace_bvh_kernel<false>, P, 128, 0, st));
+            else if (!wavefront) RVB_TRY(launch_phase(trace_bvh_kernel<false>, P, 128, 0, st));
+            else {
+                if (split == 0) {
+                    note_launch(), wf_init_state_kernel<<<(unsigned)((tr->nrays + 255) / 256), 256, 0, st>>>(P);
+                }
+                RVB_TRY(launch_wavefront(P, split, (uint32_t)tr->nrefl, split == 0, st));
+            }
         }
     } else if (tr->nrays > 0 && images && tr->ray_offset == 0) {
         // zero reflections: the reference still computes the direct path for ray 0
