@@ -240,16 +240,17 @@ static void launch_reduce(int nsub, unsigned grid, cudaStream_t st, const Source
 struct BiquadCoef { double b0, b1, b2, a1, a2; };
 struct RowFilter { int npass; BiquadCoef q[2]; };   // LR: q[0] lopass.twopass, q[1] hipass.twopass
 
-#define RVB_IIR_THREADS 256
-#define RVB_IIR_CHUNK 64
+#define RVB_IIR_THREADS 1024
+#define RVB_IIR_CHUNK 16
 #define RVB_IIR_TILE (RVB_IIR_THREADS * RVB_IIR_CHUNK)
+#define RVB_IIR_WARPS (RVB_IIR_THREADS / 32)
 
 // Biquad::onepass (filters.cpp:156-168) over one chunk held in shared memory.
 // STORE = false: only the end state is wanted.
 template <bool STORE>
 __device__ __forceinline__ void biquad_chunk(const BiquadCoef &q, float *x, double &z1, double &z2)
 {
-#pragma unroll 8
+#pragma unroll
     for (int k = 0; k < RVB_IIR_CHUNK; ++k) {
         const double in = (double)x[k];
         const double out = __dadd_rn(__dmul_rn(in, q.b0), z1);
@@ -259,13 +260,21 @@ __device__ __forceinline__ void biquad_chunk(const BiquadCoef &q, float *x, doub
     }
 }
 
-// One CTA per (channel, band) row.  The recurrence is linear in its (z1, z2) state, so a sweep
-// is split into 256 chunks of 64 samples per shared-memory tile:
+struct M2 { double a, b, c, d; };   // [[a, b], [c, d]]
+__device__ __forceinline__ M2 m2_mul(const M2 &x, const M2 &y)
+{
+    return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+}
+
+// One CTA (1024 threads) per (channel, band) row.  The recurrence is linear in its (z1, z2) state,
+// so a sweep is split into 1024 chunks of 16 samples per shared-memory tile:
 //   pass 1  every thread runs the reference recurrence over its chunk from a ZERO state and keeps
 //           the end state e_j;
-//   scan    the true start state of chunk j is S_j = A^64 S_{j-1} + e_{j-1}  (A = homogeneous
-//           transition [[-a1, 1], [-a2, 0]], A^64 obtained by running the same recurrence on
-//           the two unit states), carried across tiles;
+//   scan    the true start state of chunk j is S_j = M S_{j-1} + e_{j-1}, M = A^16 (A = homogeneous
+//           transition [[-a1, 1], [-a2, 0]], obtained by running the same recurrence on the unit
+//           states).  Three levels: lane 0 of every warp composes its 32 chunks from a zero state,
+//           thread 0 composes the 32 warp totals with M^32, then every thread adds M^lane times its
+//           warp's start state.  The carry crosses tiles.
 //   pass 2  every thread re-runs the reference recurrence from S_j and stores (float)out.
 // Pass 2 is the reference's own arithmetic; only S_j is associated differently (double, ~1e-16
 // relative), so the float outputs equal the serial filter's except for vanishingly rare
@@ -274,23 +283,34 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                                                               const RowFilter *filters, int mode /* 1 onepass, 2 twopass */)
 {
     extern __shared__ float tile[];                       // RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1), padded rows
-    __shared__ double e1[RVB_IIR_THREADS], e2[RVB_IIR_THREADS], s1[RVB_IIR_THREADS], s2[RVB_IIR_THREADS];
-    __shared__ double AM[4], carry[2];
-    const uint32_t row = blockIdx.x, tid = threadIdx.x;
+    __shared__ double e1[RVB_IIR_THREADS], e2[RVB_IIR_THREADS];   // pass-1 end states, then local prefixes
+    __shared__ double w1[RVB_IIR_WARPS], w2[RVB_IIR_WARPS];       // warp totals, then warp start states
+    __shared__ M2 pw[32];                                          // M^lane
+    __shared__ M2 MW;                                              // M^32
+    __shared__ double carry[2];
+    const uint32_t row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *x = data + row_off[row];
     const uint32_t n = row_len[row];
     const RowFilter F = filters[row];
     float *mine = tile + tid * (RVB_IIR_CHUNK + 1);
     for (int p = 0; p < F.npass; ++p) {
         const BiquadCoef q = F.q[p];
-        if (tid < 2) {   // column tid of A^CHUNK: homogeneous response to the unit state
-            double z1 = tid == 0 ? 1.0 : 0.0, z2 = tid == 0 ? 0.0 : 1.0;
-            for (int k = 0; k < RVB_IIR_CHUNK; ++k) {
-                const double out = z1;
-                z1 = __dsub_rn(z2, __dmul_rn(q.a1, out));
-                z2 = -__dmul_rn(q.a2, out);
+        __syncthreads();
+        if (tid < 32) {
+            // M = A^CHUNK from the homogeneous response to the unit states, then M^lane
+            M2 Mc;
+            {
+                double c0z1 = 1.0, c0z2 = 0.0, c1z1 = 0.0, c1z2 = 1.0;
+                for (int k = 0; k < RVB_IIR_CHUNK; ++k) {
+                    double o = c0z1; c0z1 = c0z2 - q.a1 * o; c0z2 = -(q.a2 * o);
+                    o = c1z1; c1z1 = c1z2 - q.a1 * o; c1z2 = -(q.a2 * o);
+                }
+                Mc = M2{c0z1, c1z1, c0z2, c1z2};
             }
-            AM[tid] = z1; AM[2 + tid] = z2;       // AM = [[m00, m01], [m10, m11]]
+            M2 P = M2{1.0, 0.0, 0.0, 1.0};
+            for (uint32_t k = 0; k < lane; ++k) P = m2_mul(Mc, P);
+            pw[lane] = P;
+            if (lane == 31) MW = m2_mul(Mc, P);
         }
         for (int dirn = 0; dirn < mode; ++dirn) {
             if (tid == 0) { carry[0] = 0.0; carry[1] = 0.0; }
@@ -306,20 +326,37 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                 double z1 = 0.0, z2 = 0.0;
                 biquad_chunk<false>(q, mine, z1, z2);
                 e1[tid] = z1; e2[tid] = z2;
+                __syncwarp();
+                if (lane == 0) {   // level 1: local prefixes of this warp's chunks, from a zero state
+                    const M2 M = pw[1];
+                    double a = 0.0, b = 0.0;
+                    for (int j = 0; j < 32; ++j) {
+                        const double ea = e1[tid + j], eb = e2[tid + j];
+                        e1[tid + j] = a; e2[tid + j] = b;
+                        const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
+                        a = na; b = nb;
+                    }
+                    w1[warp] = a; w2[warp] = b;
+                }
                 __syncthreads();
-                if (tid == 0) {
+                if (tid == 0) {    // level 2: start state of every warp
+                    const M2 M = MW;
                     double a = carry[0], b = carry[1];
-                    const double m00 = AM[0], m01 = AM[1], m10 = AM[2], m11 = AM[3];
-                    for (int j = 0; j < RVB_IIR_THREADS; ++j) {
-                        s1[j] = a; s2[j] = b;
-                        const double na = m00 * a + m01 * b + e1[j];
-                        const double nb = m10 * a + m11 * b + e2[j];
+                    for (int w = 0; w < RVB_IIR_WARPS; ++w) {
+                        const double ea = w1[w], eb = w2[w];
+                        w1[w] = a; w2[w] = b;
+                        const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
                         a = na; b = nb;
                     }
                     carry[0] = a; carry[1] = b;
                 }
                 __syncthreads();
-                z1 = s1[tid]; z2 = s2[tid];
+                {                  // level 3: S_j = M^lane * (warp start) + local prefix
+                    const M2 P = pw[lane];
+                    const double a = w1[warp], b = w2[warp];
+                    z1 = P.a * a + P.b * b + e1[tid];
+                    z2 = P.c * a + P.d * b + e2[tid];
+                }
                 biquad_chunk<true>(q, mine, z1, z2);
                 __syncthreads();
                 for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {

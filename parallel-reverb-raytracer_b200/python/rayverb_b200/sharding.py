@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import api
-from .types import IMPULSE, NBANDS
+from .types import IMPULSE, NBANDS, NUM_IMAGE_SOURCE
 
 
 def flatten_length(maxtime, predelay, fix, sr):
@@ -53,15 +53,38 @@ def global_times(mn, mx, device):
     return predelay, gmx
 
 
-def merge_images(img, keys, klen, rank, world):
-    """Gather the per-shard unique image-source lists; rank 0 returns the global list (first
-    occurrence in rank order wins), the others an empty one."""
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (np.asarray(img), np.asarray(keys), np.asarray(klen)))
+_REC = 64 + 4 * NUM_IMAGE_SOURCE + 4   # Impulse + key[10] + key length, bytes per image source
+
+
+def merge_images(img, keys, klen, rank, world, device):
+    """Gather the per-shard unique image-source lists (two tensor collectives: counts, then the
+    padded records); rank 0 returns the global list (first occurrence in rank order wins), the
+    others an empty one."""
+    n = len(img)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    mine = torch.tensor([n], dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, mine)
+    counts = counts.tolist()
+    nmax = max(counts)
+    if nmax == 0:
+        return np.zeros(0, dtype=IMPULSE)
+    rec = np.zeros((nmax, _REC), dtype=np.uint8)
+    if n:
+        rec[:n, :64] = np.ascontiguousarray(img, dtype=IMPULSE).view(np.uint8).reshape(n, 64)
+        rec[:n, 64:64 + 4 * NUM_IMAGE_SOURCE] = np.ascontiguousarray(keys, dtype=np.uint32).reshape(n, -1).view(np.uint8)
+        rec[:n, 64 + 4 * NUM_IMAGE_SOURCE:] = np.ascontiguousarray(klen, dtype=np.int32).reshape(n, 1).view(np.uint8)
+    local = torch.from_numpy(rec).to(device)
+    gathered = torch.empty((world, nmax, _REC), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, local.unsqueeze(0))
     if rank != 0:
         return np.zeros(0, dtype=IMPULSE)
-    merged, _, _ = api.images_merge(np.concatenate([g[0] for g in gathered]), np.concatenate([g[1] for g in gathered]),
-                                    np.concatenate([g[2] for g in gathered]))
+    g = gathered.cpu().numpy()
+    parts = [g[r, :counts[r]] for r in range(world)]
+    allrec = np.ascontiguousarray(np.concatenate(parts))
+    gi = np.ascontiguousarray(allrec[:, :64]).view(IMPULSE).reshape(-1)
+    gk = np.ascontiguousarray(allrec[:, 64:64 + 4 * NUM_IMAGE_SOURCE]).view(np.uint32).reshape(-1, NUM_IMAGE_SOURCE)
+    gl = np.ascontiguousarray(allrec[:, 64 + 4 * NUM_IMAGE_SOURCE:]).view(np.int32).reshape(-1)
+    merged, _, _ = api.images_merge(gi, gk, gl)
     return merged
 
 
@@ -72,7 +95,7 @@ def sharded_histogram(shard, cfg, rank, world, device, sr, trim_predelay):
     predelay, gmx = global_times(mn, mx, device)
     lengths = [flatten_length(m, predelay, trim_predelay, sr) for m in gmx]
     img, keys, klen = shard.raw_images(with_keys=True)
-    shard.set_images(merge_images(img, keys, klen, rank, world))
+    shard.set_images(merge_images(img, keys, klen, rank, world, device))
     hist = torch.zeros(sum(NBANDS * l for l in lengths), device=device, dtype=torch.float32)
     shard.render_histogram(cfg, predelay, lengths, hist.data_ptr())
     dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
