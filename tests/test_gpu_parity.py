@@ -317,3 +317,52 @@ def test_windowed_sinc_filter_vs_oracle(orc):
     tri, vtx, srf = scenes.shoebox()
     _render_case(orc, tri, vtx, srf, (7, 2, 4), (2, 1.5, 2), scenes.sphere_directions(1500, seed=6), 16, api.ACCEL_BRUTE_FORCE,
                  speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], ft="sinc", lo_cutoff=60.0)
+
+
+def test_empty_and_degenerate_inputs(orc):
+    """Empty and degenerate inputs the reference's host code accepts: zero rays, zero reflections
+    (only the direct path remains), a scene every ray leaves at once."""
+    tri, vtx, srf = scenes.shoebox()
+    mic, src = (7, 2, 4), (2, 1.5, 2)
+    dirs = scenes.sphere_directions(257, seed=3)
+    # zero rays
+    rt = api.Raytracer(8, tri, vtx, srf, accel=api.ACCEL_BRUTE_FORCE)
+    tr = rt.raytrace(mic, src, dirs[:0])
+    assert len(tr.raw_diffuse()) == 0 and len(tr.raw_images()) == 0
+    ir = tr.render_ir(speakers=[((0, 0, 1), 0.0)], do_normalize=False, do_trim_tail=False)
+    assert len(ir.channels) == 1 and len(ir.channels[0]) == 1 and ir.channels[0][0] == 0     # round(0)+1 samples
+    rt.close()
+    # zero reflections: getRawDiffuse is empty, getRawImages holds the direct path only
+    for accel in (api.ACCEL_BRUTE_FORCE, api.ACCEL_BVH):
+        rt = api.Raytracer(0, tri, vtx, srf, accel=accel)
+        tr = rt.raytrace(mic, src, dirs)
+        ref = orc.raytrace(tri, vtx, srf, mic, src, dirs, 0)
+        rimg, rkeys, rklen = orc.image_dedupe(ref["image"], ref["image_idx"])
+        img, keys, klen = tr.raw_images(with_keys=True)
+        assert len(tr.raw_diffuse()) == 0 and len(img) == len(rimg) == 1 and klen[0] == 1
+        assert np.array_equal(bits(img["time"]), bits(rimg["time"]))
+        np.testing.assert_allclose(img["volume"], rimg["volume"], rtol=VOL_RTOL)
+        assert len(tr.raw_images(remove_direct=True)) == 0
+        rt.close()
+    # a single triangle far away: every ray escapes without a hit; the direct path is unobstructed
+    far = tri[:1].copy()
+    for accel in (api.ACCEL_BRUTE_FORCE,):
+        check_trace_against_oracle(orc, far, vtx, srf, mic, src, dirs, 4, accel)
+    # mic exactly at the source: zero-length direct path (normalize(0) = 0 everywhere)
+    check_trace_against_oracle(orc, tri, vtx, srf, src, src, dirs[:64], 3, api.ACCEL_BRUTE_FORCE)
+
+
+def test_errors_are_reported_not_swallowed():
+    tri, vtx, srf = scenes.shoebox()
+    rt = api.Raytracer(4, tri, vtx, srf)
+    tr = rt.raytrace((7, 2, 4), (2, 1.5, 2), scenes.sphere_directions(64))
+    with pytest.raises(api.RayverbError, match="RVB_TRACE_DEBUG"):
+        tr.debug()
+    with pytest.raises(api.RayverbError):
+        tr.render_ir(speakers=[], ft="onepass")                      # speaker model needs a speaker
+    with pytest.raises(api.RayverbError, match="exactly one"):
+        tr.render_ir()
+    big = scenes.displaced_box(20.0, 8.0, 14.0, 6000)[0]
+    with pytest.raises(api.RayverbError, match="shared memory"):
+        api.Raytracer(4, big, scenes.displaced_box(20.0, 8.0, 14.0, 6000)[1], scenes.hall_surfaces(), accel=api.ACCEL_BRUTE_FORCE)
+    rt.close()
