@@ -392,6 +392,22 @@ def main():
         if not args.no_cpu_baseline:
             v, dt, cores, sample = cpu_leg(wl, tri, vtx, srf, 1, 0)
             line["cpu_baseline"] = {"value": v, "unit": "rays*bounces/s", "cores": cores, "kind": "port", "sample": sample}
+            # Extra, same-hardware context: the reference's verbatim OpenCL `raytrace` kernel on this
+            # B200 through NVIDIA's OpenCL ICD (kernel only: no host pipeline, no flatten/filter).
+            try:
+                from oracle import cl_reference as clr
+                if clr.available() and len(tri) <= 5000:
+                    n = int(min(nrays, (1 << 30) // (64 * nrefl), 1 << 17))
+                    mic0, src0 = wl["jobs"][0]
+                    clr.raytrace(tri, vtx, srf, mic0, src0, all_dirs[:4096], nrefl, read_back=False)        # JIT + warm-up
+                    secs = min(clr.raytrace(tri, vtx, srf, mic0, src0, all_dirs[:n], nrefl, read_back=False)["kernel_seconds"] for _ in range(3))
+                    line["reference_opencl_kernel_on_b200"] = {
+                        "value": n * nrefl / secs, "unit": "rays*bounces/s (raytrace kernel only)",
+                        "sample": f"{n} rays x {nrefl} reflections, best of 3, {secs * 1e3:.1f} ms",
+                        "ours_same_stage": nrays * nrefl / (both_ms * 1e-3),
+                        "note": "verbatim KERNEL_STRING of rayverb/kernel.cpp compiled by the driver's OpenCL 3.0 ICD"}
+            except Exception as e:   # never let the optional extra break the bench line
+                line["reference_opencl_kernel_on_b200"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line))
     for w in workers:
         w["rt"].close()
