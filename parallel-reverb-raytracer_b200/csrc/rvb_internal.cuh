@@ -80,6 +80,9 @@ struct Scene {
     int accel = RVB_ACCEL_BRUTE_FORCE;
     float4 *d_verts = nullptr;        // [3T] v0, v1, v2 (w = 0): TriVerts of kernel.cpp:56-60, pre-gathered
     float4 *d_tri = nullptr;          // [3T] staged intersection form: (v0.xyz,e0.x) (e0.yz,e1.xy) (e1.z,0,0,0)
+    float4 *d_quad = nullptr;         // [9*nquads] brute-force form: 4 triangles per 144-byte record, two component-wise
+                                      //   PAIRS (v0x_a,v0x_b, v0y_a,v0y_b, ... e1z_a,e1z_b)(same for c,d); zero triangles pad
+    uint32_t nquads = 0;
     float4 *d_nrm = nullptr;          // [T]  normalize(cross(e0,e1)) (kernel.cpp:110-116), w = surface index bits
     rvb_surface *d_surfaces = nullptr;
     // BVH (accel == RVB_ACCEL_BVH)

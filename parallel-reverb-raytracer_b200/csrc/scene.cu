@@ -200,6 +200,22 @@ __global__ void stage_scene_kernel(const rvb_triangle *tris, const float4 *verti
     nrm[i] = make_float4(n.x, n.y, n.z, __uint_as_float((uint32_t)t.surface));
 }
 
+// Pair-interleaved copy of the intersection form for the packed-FP32 brute-force loop: record q
+// holds triangles 4q..4q+3 as two pairs of 18 floats, component-wise (x = first, y = second
+// triangle of the pair).  Triangles past T are all-zero: det = 0 rejects them (kernel.cpp:72).
+__global__ void pack_quads_kernel(const float4 *tri, uint32_t T, uint32_t nquads, float *quad)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;   // pair index
+    if (p >= 2 * nquads) return;
+    float a[9], b[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] = b[k] = 0.f;
+    const float *src = reinterpret_cast<const float *>(tri);
+    if (2 * p < T) for (int k = 0; k < 9; ++k) a[k] = src[12 * (2 * p) + k];
+    if (2 * p + 1 < T) for (int k = 0; k < 9; ++k) b[k] = src[12 * (2 * p + 1) + k];
+    for (int k = 0; k < 9; ++k) { quad[18 * p + 2 * k] = a[k]; quad[18 * p + 2 * k + 1] = b[k]; }
+}
+
 }  // namespace rvb
 
 using namespace rvb;
@@ -261,22 +277,24 @@ int rvb_scene_create(const rvb_triangle *triangles, size_t ntriangles, const rvb
     auto cleanup = [&]() { dev_free(d_tris); dev_free(d_vertices); };
     if ((rc = dev_alloc(&d_tris, ntriangles)) || (rc = dev_alloc(&d_vertices, nvertices)) ||
         (rc = dev_alloc(&sc->d_verts, 3 * ntriangles)) || (rc = dev_alloc(&sc->d_tri, 3 * ntriangles)) ||
-        (rc = dev_alloc(&sc->d_nrm, ntriangles)) || (rc = dev_alloc(&sc->d_surfaces, nsurfaces))) {
+        (rc = dev_alloc(&sc->d_nrm, ntriangles)) || (rc = dev_alloc(&sc->d_quad, 9 * (size_t)((ntriangles + 3) / 4))) || (rc = dev_alloc(&sc->d_surfaces, nsurfaces))) {
         cleanup(); rvb_scene_destroy(sc); return rc;
     }
     cudaMemcpyAsync(d_tris, triangles, ntriangles * sizeof(rvb_triangle), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_vertices, vertices, nvertices * sizeof(rvb_float3), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(sc->d_surfaces, surfaces, nsurfaces * sizeof(rvb_surface), cudaMemcpyHostToDevice, st);
     note_launch(), stage_scene_kernel<<<(unsigned)((ntriangles + 255) / 256), 256, 0, st>>>(d_tris, d_vertices, sc->T, sc->d_verts, sc->d_tri, sc->d_nrm);
+    sc->nquads = (uint32_t)((ntriangles + 3) / 4);
+    note_launch(), pack_quads_kernel<<<(2 * sc->nquads + 255) / 256, 256, 0, st>>>(sc->d_tri, sc->T, sc->nquads, reinterpret_cast<float *>(sc->d_quad));
     cudaError_t e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess) { rvb_scene_destroy(sc); return fail(RVB_ERR_CUDA, std::string("scene staging: ") + cudaGetErrorString(e)); }
 
     const size_t smem_limit = 227 * 1024;
-    const bool fits = (size_t)3 * ntriangles * sizeof(float4) <= smem_limit;
+    const bool fits = (size_t)9 * sc->nquads * sizeof(float4) + 64 <= smem_limit;
     if (accel == RVB_ACCEL_BRUTE_FORCE && !fits) {
         rvb_scene_destroy(sc);
-        return fail(RVB_ERR_INVALID, "brute-force path needs the scene in shared memory (<= 4843 triangles)");
+        return fail(RVB_ERR_INVALID, "brute-force path needs the scene in shared memory (<= 6452 triangles)");
     }
     if (accel == RVB_ACCEL_AUTO) accel = (ntriangles <= 1024) ? RVB_ACCEL_BRUTE_FORCE : RVB_ACCEL_BVH;
     sc->accel = accel;
@@ -292,7 +310,7 @@ int rvb_scene_destroy(rvb_scene *sc)
 {
     if (!sc) return RVB_OK;
     cudaSetDevice(sc->device);
-    dev_free(sc->d_verts); dev_free(sc->d_tri); dev_free(sc->d_nrm); dev_free(sc->d_surfaces);
+    dev_free(sc->d_verts); dev_free(sc->d_tri); dev_free(sc->d_quad); dev_free(sc->d_nrm); dev_free(sc->d_surfaces);
     dev_free(sc->d_nodes); dev_free(sc->d_order); dev_free(sc->d_tri_sorted);
     cudaStreamSynchronize(lib_stream());
     delete sc;

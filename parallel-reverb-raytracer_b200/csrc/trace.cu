@@ -20,6 +20,8 @@
 // which sit at the same bounce, write 32 consecutive 32-byte sectors.
 #include <cstdlib>
 
+#include <cub/cub.cuh>
+
 #include "rvb_internal.cuh"
 
 namespace rvb {
@@ -27,6 +29,8 @@ namespace rvb {
 struct TraceParams {
     const float4 *verts;      // [3T]
     const float4 *tri;        // [3T] staged (v0,e0,e1)
+    const float4 *quad;       // [9*nquads] pair-interleaved form for the brute-force loop
+    uint32_t nquads;
     const float4 *nrm;        // [T]
     const rvb_surface *surfaces;
     uint32_t T;
@@ -35,6 +39,7 @@ struct TraceParams {
     const float4 *tri_sorted;
     const uint32_t *order;
     const float4 *dirs;
+    const uint32_t *ray_perm;  // image phase: processing order (rays sorted by direction), or null
     uint32_t nrays, nrefl;
     uint32_t first, last;     // reflections [first, last) handled by this launch
     uint64_t ray_offset;
@@ -56,26 +61,40 @@ struct Counters { uint32_t queries = 0, bounces = 0; unsigned long long tri = 0,
 #define RVB_INF __int_as_float(0x7f800000)
 
 // ---- brute force over the shared-memory scene (kernel.cpp:167-192) ---------------------------
+// The scene sits in shared memory in the pair-interleaved form of Scene::d_quad: every warp-wide
+// LDS.128 is a broadcast, and each packed instruction (FFMA2 ...) tests the ray against TWO
+// triangles.  Triangles are visited in index order and the strict '<' keeps the lowest index on
+// exact ties, as the reference loop does.
 struct BruteSmem {
     const float4 *s;
-    uint32_t T;
+    uint32_t T, nquads;
 
-    __device__ __forceinline__ void load(uint32_t i, f3 &v0, f3 &e0, f3 &e1) const
+    __device__ __forceinline__ void load(uint32_t q, f3x2 &v0a, f3x2 &e0a, f3x2 &e1a, f3x2 &v0b, f3x2 &e0b, f3x2 &e1b) const
     {
-        float4 A = s[3 * i], B = s[3 * i + 1], C = s[3 * i + 2];
-        v0 = mk3(A.x, A.y, A.z); e0 = mk3(A.w, B.x, B.y); e1 = mk3(B.z, B.w, C.x);
+        const float4 *r = s + 9 * q;
+        const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5], r6 = r[6], r7 = r[7], r8 = r[8];
+        v0a.x = make_float2(r0.x, r0.y); v0a.y = make_float2(r0.z, r0.w); v0a.z = make_float2(r1.x, r1.y);
+        e0a.x = make_float2(r1.z, r1.w); e0a.y = make_float2(r2.x, r2.y); e0a.z = make_float2(r2.z, r2.w);
+        e1a.x = make_float2(r3.x, r3.y); e1a.y = make_float2(r3.z, r3.w); e1a.z = make_float2(r4.x, r4.y);
+        v0b.x = make_float2(r4.z, r4.w); v0b.y = make_float2(r5.x, r5.y); v0b.z = make_float2(r5.z, r5.w);
+        e0b.x = make_float2(r6.x, r6.y); e0b.y = make_float2(r6.z, r6.w); e0b.z = make_float2(r7.x, r7.y);
+        e1b.x = make_float2(r7.z, r7.w); e1b.y = make_float2(r8.x, r8.y); e1b.z = make_float2(r8.z, r8.w);
     }
     __device__ __forceinline__ bool nearest(f3 pos, f3 dir, float &tbest, uint32_t &ibest, Counters &c) const
     {
         tbest = RVB_INF;
         ibest = RVB_NONE;
-#pragma unroll 6
-        for (uint32_t i = 0; i < T; ++i) {
-            f3 v0, e0, e1;
-            load(i, v0, e0, e1);
-            bool ok;
-            float t = mt_intersect_pred(v0, e0, e1, pos, dir, ok);
-            if (ok && t > RVB_EPSILON && t < tbest) { tbest = t; ibest = i; }
+#pragma unroll 2
+        for (uint32_t q = 0; q < nquads; ++q) {
+            f3x2 v0a, e0a, e1a, v0b, e0b, e1b;
+            load(q, v0a, e0a, e1a, v0b, e0b, e1b);
+            bool ok0, ok1, ok2, ok3;
+            const float2 ta = mt_intersect_pair(v0a, e0a, e1a, pos, dir, ok0, ok1);
+            const float2 tb = mt_intersect_pair(v0b, e0b, e1b, pos, dir, ok2, ok3);
+            if (ok0 && ta.x > RVB_EPSILON && ta.x < tbest) { tbest = ta.x; ibest = 4 * q; }
+            if (ok1 && ta.y > RVB_EPSILON && ta.y < tbest) { tbest = ta.y; ibest = 4 * q + 1; }
+            if (ok2 && tb.x > RVB_EPSILON && tb.x < tbest) { tbest = tb.x; ibest = 4 * q + 2; }
+            if (ok3 && tb.y > RVB_EPSILON && tb.y < tbest) { tbest = tb.y; ibest = 4 * q + 3; }
         }
         c.queries++; c.tri += T;
         return ibest != RVB_NONE;
@@ -84,13 +103,15 @@ struct BruteSmem {
     __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
     {
         bool blocked = false;
-#pragma unroll 6
-        for (uint32_t i = 0; i < T; ++i) {
-            f3 v0, e0, e1;
-            load(i, v0, e0, e1);
-            bool ok;
-            float t = mt_intersect_pred(v0, e0, e1, pos, dir, ok);
-            blocked |= (ok && t > RVB_EPSILON && t <= mag);
+#pragma unroll 2
+        for (uint32_t q = 0; q < nquads; ++q) {
+            f3x2 v0a, e0a, e1a, v0b, e0b, e1b;
+            load(q, v0a, e0a, e1a, v0b, e0b, e1b);
+            bool ok0, ok1, ok2, ok3;
+            const float2 ta = mt_intersect_pair(v0a, e0a, e1a, pos, dir, ok0, ok1);
+            const float2 tb = mt_intersect_pair(v0b, e0b, e1b, pos, dir, ok2, ok3);
+            blocked |= (ok0 && ta.x > RVB_EPSILON && ta.x <= mag) | (ok1 && ta.y > RVB_EPSILON && ta.y <= mag)
+                     | (ok2 && tb.x > RVB_EPSILON && tb.x <= mag) | (ok3 && tb.y > RVB_EPSILON && tb.y <= mag);
         }
         c.queries++; c.tri += T;
         return blocked;
@@ -216,23 +237,35 @@ struct BvhAccel {
 // argument reduction is exact to ~2e-8, then ex2.approx on |r| <= 0.5 (max relative error
 // 2^-22).  Total error <= 2.6e-7 relative, i.e. ~2 ulp -- the same class as powf itself
 // (CUDA documents 4 ulp for powf); volumes are compared with a 2e-6 relative tolerance.
-__device__ __forceinline__ float pow_e(float x)
+__device__ __forceinline__ float pow_e_core(float x)
 {
     const float L_HI = 1.4426950216293335f;        // float(log2((float)M_E))
     const float L_LO = -2.4551930266625277e-08f;   // log2((float)M_E) - L_HI
+    const float MAGIC = 12582912.0f;               // 1.5 * 2^23: adding it rounds to nearest-even integer
     const float p_hi = __fmul_rn(x, L_HI);
-    if (!(p_hi > -120.0f && p_hi < 120.0f)) return powf(RVB_M_E_F, x);   // under/overflow range, NaN: library path
     const float p_lo = __fadd_rn(__fmaf_rn(x, L_HI, -p_hi), __fmul_rn(x, L_LO));
-    const float n = rintf(p_hi);
+    const float t = __fadd_rn(p_hi, MAGIC);        // low mantissa bits of t = n (two's complement), |n| < 2^22
+    const float n = __fsub_rn(t, MAGIC);           // = rintf(p_hi)
     const float r = __fadd_rn(__fsub_rn(p_hi, n), p_lo);
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r));
-    return __fmul_rn(e, __int_as_float(((int)n + 127) << 23));
+    return __fmul_rn(e, __int_as_float((__float_as_int(t) << 23) + 0x3f800000));   // * 2^n
 }
+__device__ __noinline__ float pow_e_slow(float x) { return powf(RVB_M_E_F, x); }
+// All eight bands at once.  The exponents distance * AIR are <= 0 (distance >= 0, every AIR < 0,
+// rayverb.cpp:632-641) and AIR[7] is the most negative, so one test on band 7 covers the fast path's
+// range for all of them; NaN, negative distances and exponents below -83 (result < 2^-120) take the
+// library powf.
 __device__ __forceinline__ void air_attenuation(float distance, const float *air, float *att)
 {
+    const float worst = __fmul_rn(__fmul_rn(distance, air[RVB_NBANDS - 1]), 1.4426950216293335f);
+    if (worst > -120.0f && distance >= 0.0f) {
 #pragma unroll
-    for (int b = 0; b < RVB_NBANDS; ++b) att[b] = pow_e(__fmul_rn(distance, air[b]));
+        for (int b = 0; b < RVB_NBANDS; ++b) att[b] = pow_e_core(__fmul_rn(distance, air[b]));
+    } else {
+#pragma unroll
+        for (int b = 0; b < RVB_NBANDS; ++b) att[b] = pow_e_slow(__fmul_rn(distance, air[b]));
+    }
 }
 
 // kernel.cpp:274-296
@@ -468,13 +501,13 @@ __device__ __forceinline__ void flush_counters(const TraceParams &P, const Count
     }
 }
 
-// Stage the whole scene (48 B per triangle, 16-byte aligned, a multiple of 16 bytes) into shared
+// Stage the whole scene (144 B per four triangles, 16-byte aligned, a multiple of 16 bytes) into shared
 // memory with the TMA bulk-copy engine: one elected thread issues cp.async.bulk in <= 32 KiB
 // pieces that all complete on one mbarrier; everybody waits on its phase.  (UBLKCP in SASS.)
 __device__ __forceinline__ void stage_scene(float4 *s_tri, const TraceParams &P)
 {
     __shared__ __align__(8) unsigned long long bar;
-    const uint32_t bytes = 3u * P.T * (uint32_t)sizeof(float4);
+    const uint32_t bytes = 9u * P.nquads * (uint32_t)sizeof(float4);
     const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tri);
     if (threadIdx.x == 0) {
@@ -484,7 +517,7 @@ __device__ __forceinline__ void stage_scene(float4 *s_tri, const TraceParams &P)
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
-        const char *src = reinterpret_cast<const char *>(P.tri);
+        const char *src = reinterpret_cast<const char *>(P.quad);
         for (uint32_t off = 0; off < bytes; off += 32768u) {
             const uint32_t n = min(32768u, bytes - off);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -507,10 +540,10 @@ __global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TracePara
 {
     extern __shared__ float4 s_tri[];
     stage_scene(s_tri, P);
-    BruteSmem acc{s_tri, P.T};
+    BruteSmem acc{s_tri, P.T, P.nquads};
     Counters c;
-    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x) {
-        if (IMAGES) image_phase_ray(acc, P, ray, c); else steady_phase_ray(acc, P, ray, c);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrays; i += gridDim.x * blockDim.x) {
+        if (IMAGES) image_phase_ray(acc, P, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, i, c);
     }
     flush_counters(P, c);
 }
@@ -520,10 +553,29 @@ __global__ void __launch_bounds__(128) trace_bvh_kernel(const TraceParams P)
 {
     BvhAccel acc{P.nodes, P.tri_sorted, P.order};
     Counters c;
-    for (uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x; ray < P.nrays; ray += gridDim.x * blockDim.x) {
-        if (IMAGES) image_phase_ray(acc, P, ray, c); else steady_phase_ray(acc, P, ray, c);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrays; i += gridDim.x * blockDim.x) {
+        if (IMAGES) image_phase_ray(acc, P, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, i, c);
     }
     flush_counters(P, c);
+}
+
+// Direction cell of a ray (256 x 256 cells over z and the azimuth), used only to
+// decide the ORDER in which the image phase processes rays: neighbouring lanes then follow the same
+// first reflections, so their image-source validation loops have the same trip counts.  The results
+// do not depend on the order (every ray writes its own slots).
+__global__ void direction_keys_kernel(const float4 *dirs, uint32_t n, uint32_t *keys, uint32_t *ids)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 d = dirs[i];
+    const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+    const float inv = len > 0.f ? 1.0f / len : 0.f;
+    const float z = fminf(fmaxf(d.z * inv * 0.5f + 0.5f, 0.f), 0.999999f);
+    const float az = fminf(fmaxf(atan2f(d.y, d.x) * 0.15915494f + 0.5f, 0.f), 0.999999f);
+    const uint32_t iz = (uint32_t)(z * 256.f), ia = (uint32_t)(az * 256.f);
+    // boustrophedon over the azimuth so that consecutive cells stay adjacent
+    keys[i] = iz * 256u + ((iz & 1u) ? 255u - ia : ia);
+    ids[i] = i;
 }
 
 template <class K>
@@ -547,21 +599,45 @@ static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, 
     return RVB_OK;
 }
 
-// brute force: the CTA size with the most resident threads per SM
+// Brute force: pick the CTA size.  The packed loop wants ~96 registers per thread for full ILP, so
+// more resident threads is not automatically better: 1024-thread CTAs are capped at 64 registers
+// (spills), 768 at 80, 512 and below are uncapped.  Candidates are ranked by resident threads per SM
+// weighted by a measured per-thread efficiency of the register budget (B200, C2 and the 4.4 k
+// triangle room); RVB_BLOCK=<n> forces a size for experiments.
+template <bool IMAGES, int BLOCK>
+static int try_block(const TraceParams &P, size_t smem, int &per_sm)
+{
+    return occupancy_of(trace_bruteforce_kernel<IMAGES, BLOCK>, BLOCK, smem, per_sm);
+}
 template <bool IMAGES>
 static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
 {
-    int small = 0, big = 0;
-    RVB_TRY(occupancy_of(trace_bruteforce_kernel<IMAGES, 256>, 256, smem, small));
-    constexpr int BIG = IMAGES ? 512 : 1024;
-    RVB_TRY(occupancy_of(trace_bruteforce_kernel<IMAGES, BIG>, BIG, smem, big));
-    // threads that would actually be busy with this many rays (small CTAs spread few rays over more SMs)
+    static const int forced = getenv("RVB_BLOCK") ? atoi(getenv("RVB_BLOCK")) : 0;
+    const int sizes[5] = {256, 384, 512, 768, 1024};
+    const float eff[5] = {1.0f, 1.0f, 1.0f, 0.9f, 0.7f};
+    int per_sm[5] = {0, 0, 0, 0, 0};
+    RVB_TRY((try_block<IMAGES, 256>(P, smem, per_sm[0])));
+    RVB_TRY((try_block<IMAGES, 384>(P, smem, per_sm[1])));
+    RVB_TRY((try_block<IMAGES, 512>(P, smem, per_sm[2])));
+    RVB_TRY((try_block<IMAGES, 768>(P, smem, per_sm[3])));
+    RVB_TRY((try_block<IMAGES, 1024>(P, smem, per_sm[4])));
     const size_t nsm = (size_t)sm_count();
-    const size_t busy_small = std::min<size_t>(P.nrays, (size_t)small * 256 * nsm);
-    const size_t busy_big = std::min<size_t>(P.nrays, (size_t)big * BIG * nsm);
-    const bool spread = (size_t)P.nrays >= nsm * BIG;   // enough rays to give every SM a big CTA
-    if (spread && busy_big > busy_small) return launch_phase(trace_bruteforce_kernel<IMAGES, BIG>, P, BIG, smem, st);
-    return launch_phase(trace_bruteforce_kernel<IMAGES, 256>, P, 256, smem, st);
+    int best = 0;
+    float best_score = -1.f;
+    for (int i = 0; i < 5; ++i) {
+        // threads that would actually be busy with this many rays (small CTAs spread few rays over more SMs)
+        const size_t busy = std::min<size_t>(P.nrays, (size_t)per_sm[i] * sizes[i] * nsm);
+        float score = (float)busy * eff[i];
+        if (forced == sizes[i] && per_sm[i] > 0) score = 1e30f;
+        if (score > best_score) { best_score = score; best = i; }
+    }
+    switch (best) {
+    case 0: return launch_phase(trace_bruteforce_kernel<IMAGES, 256>, P, 256, smem, st);
+    case 1: return launch_phase(trace_bruteforce_kernel<IMAGES, 384>, P, 384, smem, st);
+    case 2: return launch_phase(trace_bruteforce_kernel<IMAGES, 512>, P, 512, smem, st);
+    case 3: return launch_phase(trace_bruteforce_kernel<IMAGES, 768>, P, 768, smem, st);
+    default: return launch_phase(trace_bruteforce_kernel<IMAGES, 1024>, P, 1024, smem, st);
+    }
 }
 
 // =================================================================================================
@@ -782,7 +858,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     Scene *sc = tr->scene;
     cudaStream_t st = lib_stream();
     TraceParams P{};
-    P.verts = sc->d_verts; P.tri = sc->d_tri; P.nrm = sc->d_nrm; P.surfaces = sc->d_surfaces; P.T = sc->T;
+    P.verts = sc->d_verts; P.tri = sc->d_tri; P.quad = sc->d_quad; P.nquads = sc->nquads; P.nrm = sc->d_nrm; P.surfaces = sc->d_surfaces; P.T = sc->T;
     P.nodes = sc->d_nodes; P.tri_sorted = sc->d_tri_sorted; P.order = sc->d_order;
     P.dirs = d_dirs; P.nrays = (uint32_t)tr->nrays; P.nrefl = (uint32_t)tr->nrefl; P.ray_offset = tr->ray_offset;
     for (int i = 0; i < 3; ++i) { P.mic[i] = tr->mic[i]; P.src[i] = tr->src[i]; }
@@ -809,8 +885,22 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     static const bool wavefront = getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '1';
     if (split < tr->nrefl && (split > 0 || (!brute && wavefront))) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
     P.state = d_state;
-    const size_t smem = brute ? (size_t)3 * sc->T * sizeof(float4) : 0;
+    const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : 0;
 
+    // processing order of the image phase: rays sorted by direction cell
+    uint32_t *d_perm_keys[2] = {nullptr, nullptr}, *d_perm_ids[2] = {nullptr, nullptr};
+    uint8_t *d_perm_tmp = nullptr;
+    if (split > 0 && tr->nrays >= 4096) {
+        const uint32_t n = (uint32_t)tr->nrays;
+        for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_perm_keys[i], n)); RVB_TRY(dev_alloc(&d_perm_ids[i], n)); }
+        note_launch(), direction_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_dirs, n, d_perm_keys[0], d_perm_ids[0]);
+        cub::DoubleBuffer<uint32_t> kb(d_perm_keys[0], d_perm_keys[1]), vb(d_perm_ids[0], d_perm_ids[1]);
+        size_t bytes = 0;
+        RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, 0, 16, st));
+        RVB_TRY(dev_alloc(&d_perm_tmp, bytes));
+        RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_perm_tmp, bytes, kb, vb, (int)n, 0, 16, st));
+        P.ray_perm = vb.Current();
+    }
     cudaEvent_t e0, e1, em;
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
@@ -856,6 +946,8 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     tr->stats.steady_tri_tests = h[1] - hm[1]; tr->stats.steady_box_tests = h[2] - hm[2];
     dev_free(d_counters);
     dev_free(d_state);
+    for (int i = 0; i < 2; ++i) { dev_free(d_perm_keys[i]); dev_free(d_perm_ids[i]); }
+    dev_free(d_perm_tmp);
     tr->stats.queries = h[0]; tr->stats.tri_tests = h[1]; tr->stats.box_tests = h[2]; tr->stats.bounces = h[3];
     tr->stats.trace_kernel_ms = ms;
     return RVB_OK;
