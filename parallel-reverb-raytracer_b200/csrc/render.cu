@@ -31,6 +31,10 @@ struct Source {
     uint32_t n_diffuse;
     const float4 *ivolA, *ivolB, *ipt;
     uint32_t n_images;
+    // host side: extrema of the diffuse times already reduced by the bounce kernels (time passes
+    // through the speaker attenuator unchanged, kernel.cpp:532)
+    bool have_ext;
+    float ext_min_nz, ext_max;
     __device__ __forceinline__ uint32_t size() const { return n_diffuse + n_images; }
     // returns false for impulses the attenuation kernels skip (kernel.cpp:524,607)
     __device__ __forceinline__ bool time_of(uint32_t i, float &t) const
@@ -449,6 +453,7 @@ static int make_source(const rvb_trace *tr, const rvb_render_config *cfg, Source
     if (diffuse) {
         size_t n = tr->nrays * tr->nrefl;
         S.vol = tr->d_vol; S.pt = tr->d_pt; S.tkey = tr->d_tkey; S.n_diffuse = (uint32_t)n;
+        S.have_ext = tr->has_time_ext; S.ext_min_nz = tr->diffuse_tmin_nz; S.ext_max = tr->diffuse_tmax;
     }
     if (images) {
         size_t skip = (cfg->remove_direct && tr->first_is_direct) ? 1 : 0;
@@ -521,9 +526,14 @@ static int make_channels(const float mic[3], const rvb_render_config *cfg, Chann
     return RVB_OK;
 }
 
-static int times_for_spec(const Source &S, const ChanSpec &C, float &mn, float &mx)
+static int times_for_spec(const Source &S_all, const ChanSpec &C, float &mn, float &mx)
 {
     cudaStream_t st = lib_stream();
+    // speaker / pass-through model: the diffuse extrema came with the trace; only the (few) image
+    // sources are scanned here
+    const bool use_ext = C.model != 1 && S_all.have_ext && S_all.n_diffuse > 0;
+    Source S = S_all;
+    if (use_ext) { S.n_diffuse = 0; S.vol = nullptr; S.pt = nullptr; S.tkey = nullptr; }
     int *d = nullptr, h[2];
     RVB_TRY(dev_alloc(&d, 2));
     const int init[2] = {0x7f800000, 0};   // ordered(+inf), ordered(0)
@@ -533,6 +543,7 @@ static int times_for_spec(const Source &S, const ChanSpec &C, float &mn, float &
     RVB_CUDA(cudaStreamSynchronize(st));
     dev_free(d);
     mn = unordered(h[0]); mx = unordered(h[1]);
+    if (use_ext) { mn = std::min(mn, S_all.ext_min_nz); mx = std::max(mx, S_all.ext_max); }
     if (std::isinf(mn)) mn = 0.0f;   // findPredelay: no non-zero time
     return RVB_OK;
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <cstring>
 #include <vector>
 
 #include "../../include/rayverb_b200.h"
@@ -60,6 +61,10 @@ inline void dev_free(T *&p)
     p = nullptr;
 }
 
+// order-preserving float <-> int keys for atomicMin / atomicMax on floats
+__host__ __device__ inline int ordered_key(float f) { int i; memcpy(&i, &f, 4); return i ^ ((i >> 31) & 0x7fffffff); }
+__host__ __device__ inline float unordered_key(int i) { i = i ^ ((i >> 31) & 0x7fffffff); float f; memcpy(&f, &i, 4); return f; }
+
 // ---- BVH node (see bvh.cu) ------------------------------------------------------------------
 // 4-wide node, one 128-byte line: the boxes of up to four children in SoA form (slot k of every
 // float4), so one visit decides four descents and the dependent-load chain is half as long as with
@@ -112,6 +117,9 @@ struct Trace {
     std::vector<uint32_t> img_keys;                // n_images * 10
     std::vector<int32_t> img_len;                  // n_images
     bool first_is_direct = false;                  // entry 0 has key {0}
+    // extrema of the emitted diffuse impulse times, reduced inside the bounce kernels
+    bool has_time_ext = false;
+    float diffuse_tmin_nz = 0.f, diffuse_tmax = 0.f;
     rvb_trace_stats stats{};
 };
 

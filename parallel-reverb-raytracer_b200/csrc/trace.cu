@@ -18,7 +18,9 @@
 //
 // Output is a bounce-major SoA (slot = bounce * nrays + ray) so that the 32 lanes of a warp,
 // which sit at the same bounce, write 32 consecutive 32-byte sectors.
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include <cub/cub.cuh>
 
@@ -52,10 +54,17 @@ struct TraceParams {
     float4 *cand_volA, *cand_volB, *cand_pt;   // [nrays*10] image-source candidates
     uint32_t *cand_idx;                        // [nrays*10] triangle+1, 0 = none (pre-zeroed)
     unsigned long long *counters;              // [0] queries [1] tri tests [2] box tests [3] bounces
+    int *time_ext;                             // [0] ordered min non-zero, [1] ordered max time of the emitted diffuse impulses
     uint32_t flags;
 };
 
-struct Counters { uint32_t queries = 0, bounces = 0; unsigned long long tri = 0, box = 0; };
+struct Counters {
+    uint32_t queries = 0, bounces = 0;
+    unsigned long long tri = 0, box = 0;
+    // extrema of the emitted (non-skipped) impulse times: what findPredelay / flattenImpulses need
+    // (rayverb.h:47-76, rayverb.cpp:54-57), gathered here so the renderer does not re-read 4 B per impulse
+    float tmin_nz = INFINITY, tmax = 0.0f;
+};
 
 #define RVB_NONE 0xffffffffu
 #define RVB_INF __int_as_float(0x7f800000)
@@ -354,6 +363,10 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
     P.vol[2 * slot + 1] = make_float4(out[4], out[5], out[6], out[7]);
     P.pt[slot] = make_float4(X.x, X.y, X.z, time);
     P.tkey[slot] = any ? time : -1.0f;
+    if (any) {
+        if (time != 0.0f) c.tmin_nz = fminf(c.tmin_nz, time);
+        c.tmax = fmaxf(c.tmax, time);
+    }
     if (P.hit) P.hit[slot] = prim;
 
     R.dir = reflect(normal, R.dir);                                          // :492-499
@@ -491,13 +504,17 @@ __device__ __forceinline__ void flush_counters(const TraceParams &P, const Count
 {
     // warp-aggregate, then one atomic per warp (integer adds: order-independent)
     unsigned long long q = c.queries, t = c.tri, b = c.box, n = c.bounces;
+    float mn = c.tmin_nz, mx = c.tmax;
     for (int o = 16; o; o >>= 1) {
         q += __shfl_down_sync(0xffffffffu, q, o); t += __shfl_down_sync(0xffffffffu, t, o);
         b += __shfl_down_sync(0xffffffffu, b, o); n += __shfl_down_sync(0xffffffffu, n, o);
+        mn = fminf(mn, __shfl_down_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(P.counters + 0, q); atomicAdd(P.counters + 1, t);
         atomicAdd(P.counters + 2, b); atomicAdd(P.counters + 3, n);
+        // order-preserving integer keys: min / max are order-independent, so this is deterministic
+        atomicMin(P.time_ext, ordered_key(mn)); atomicMax(P.time_ext + 1, ordered_key(mx));
     }
 }
 
@@ -871,9 +888,13 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     P.cand_volA = d_cand_volA; P.cand_volB = d_cand_volB; P.cand_pt = d_cand_pt; P.cand_idx = d_cand_idx;
     P.flags = tr->flags;
     unsigned long long *d_counters = nullptr;
-    RVB_TRY(dev_alloc(&d_counters, 4));
-    RVB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), st));
+    RVB_TRY(dev_alloc(&d_counters, 5));
+    {   // [4] holds the two ordered time keys: ordered(+inf), ordered(0)
+        const unsigned long long init[5] = {0, 0, 0, 0, 0x000000007f800000ull};
+        RVB_CUDA(cudaMemcpyAsync(d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
     P.counters = d_counters;
+    P.time_ext = reinterpret_cast<int *>(d_counters + 4);
 
     const bool images = !(tr->flags & RVB_TRACE_NO_IMAGES);
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
@@ -934,7 +955,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         else RVB_TRY(launch_phase(trace_bvh_kernel<true>, P, 128, 0, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
-    unsigned long long h[4];
+    unsigned long long h[5];
     RVB_CUDA(cudaMemcpyAsync(h, d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f, ms_image = 0.f, ms_steady = 0.f;
@@ -948,6 +969,13 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     dev_free(d_state);
     for (int i = 0; i < 2; ++i) { dev_free(d_perm_keys[i]); dev_free(d_perm_ids[i]); }
     dev_free(d_perm_tmp);
+    {
+        int ext[2];
+        memcpy(ext, &h[4], sizeof ext);
+        tr->diffuse_tmin_nz = unordered_key(ext[0]);   // +inf: no non-zero time
+        tr->diffuse_tmax = unordered_key(ext[1]);
+        tr->has_time_ext = true;
+    }
     tr->stats.queries = h[0]; tr->stats.tri_tests = h[1]; tr->stats.box_tests = h[2]; tr->stats.bounces = h[3];
     tr->stats.trace_kernel_ms = ms;
     return RVB_OK;

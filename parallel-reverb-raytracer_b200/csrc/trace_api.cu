@@ -6,6 +6,8 @@
 // launch and the results stay on the device behind the rvb_trace handle; the host copies below
 // exist for the drop-in getRaw* accessors and the parity tests.
 #include <algorithm>
+#include <cstring>
+#include <unordered_map>
 #include <map>
 
 #include "rvb_internal.cuh"
@@ -244,19 +246,41 @@ int rvb_images_merge(const rvb_impulse *images, const uint32_t *keys, const int3
                      uint32_t *out_keys, int32_t *out_key_lengths, size_t *nout)
 {
     if (!nout || (n && (!images || !keys || !key_lengths || !out))) return fail(RVB_ERR_INVALID, "null argument");
-    std::map<std::vector<uint32_t>, size_t> tally;
-    for (size_t i = 0; i < n; ++i) {
-        std::vector<uint32_t> k(keys + i * RVB_NUM_IMAGE_SOURCE, keys + i * RVB_NUM_IMAGE_SOURCE + key_lengths[i]);
-        tally.emplace(std::move(k), i);   // emplace keeps the first
-    }
-    size_t m = 0;
-    for (const auto &kv : tally) {
-        out[m] = images[kv.second];
-        if (out_keys) {
-            for (int j = 0; j < RVB_NUM_IMAGE_SOURCE; ++j)
-                out_keys[m * RVB_NUM_IMAGE_SOURCE + j] = j < (int)kv.first.size() ? kv.first[j] : 0u;
+    // std::map<vector<u64>> order = lexicographic with a proper prefix first.  Keys hold unsigned
+    // values, so comparing the zero-padded 10-tuples and then the lengths gives the same order.
+    struct PKey {
+        uint32_t k[RVB_NUM_IMAGE_SOURCE + 1];   // zero-padded key, then its length
+        bool operator==(const PKey &o) const { return memcmp(k, o.k, sizeof k) == 0; }
+        bool operator<(const PKey &o) const
+        {
+            for (int j = 0; j <= RVB_NUM_IMAGE_SOURCE; ++j) if (k[j] != o.k[j]) return k[j] < o.k[j];
+            return false;
         }
-        if (out_key_lengths) out_key_lengths[m] = (int32_t)kv.first.size();
+    };
+    struct PHash {
+        size_t operator()(const PKey &p) const
+        {
+            uint64_t h = 1469598103934665603ull;
+            for (int j = 0; j <= RVB_NUM_IMAGE_SOURCE; ++j) { h ^= p.k[j]; h *= 1099511628211ull; }
+            return (size_t)h;
+        }
+    };
+    // first occurrence of every key (O(n) with a hash set), then only the unique ones are sorted
+    std::unordered_map<PKey, uint32_t, PHash> first;
+    first.reserve(2 * n + 1);
+    std::vector<std::pair<PKey, uint32_t>> uniq;
+    for (size_t i = 0; i < n; ++i) {
+        PKey p;
+        for (int j = 0; j < RVB_NUM_IMAGE_SOURCE; ++j) p.k[j] = j < key_lengths[i] ? keys[i * RVB_NUM_IMAGE_SOURCE + j] : 0u;
+        p.k[RVB_NUM_IMAGE_SOURCE] = (uint32_t)key_lengths[i];
+        if (first.emplace(p, (uint32_t)i).second) uniq.emplace_back(p, (uint32_t)i);
+    }
+    std::sort(uniq.begin(), uniq.end(), [](const std::pair<PKey, uint32_t> &a, const std::pair<PKey, uint32_t> &b) { return a.first < b.first; });
+    size_t m = 0;
+    for (const auto &u : uniq) {
+        out[m] = images[u.second];
+        if (out_keys) memcpy(out_keys + m * RVB_NUM_IMAGE_SOURCE, u.first.k, RVB_NUM_IMAGE_SOURCE * sizeof(uint32_t));
+        if (out_key_lengths) out_key_lengths[m] = (int32_t)u.first.k[RVB_NUM_IMAGE_SOURCE];
         ++m;
     }
     *nout = m;

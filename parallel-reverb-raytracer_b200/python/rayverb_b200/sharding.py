@@ -3,9 +3,10 @@
 Rays are independent (kernel.cpp:319: one work-item per ray), so each rank traces a contiguous
 slice of the direction set against its own replica of the scene.  What couples the shards:
 
-  * the flatten length and the predelay are global: one all-reduce of (min non-zero, max) time;
+  * the flatten length and the predelay are global: one small all-gather of the per-shard
+    (min non-zero, max) times, which also carries the image-source counts;
   * image sources are de-duplicated across ALL rays with the lowest ray winning
-    (rayverb.cpp:654-676): the per-shard unique lists are gathered and merged in rank order
+    (rayverb.cpp:654-676): the per-shard unique lists are gathered to rank 0 and merged in rank order
     (contiguous slices => lowest rank == lowest ray), rank 0 keeps the merged list;
   * flattenImpulses is a sum, so the per-shard [channel][band][sample] histograms are combined with
     ONE reduce (NCCL over NVLink on GPUs); the band filters are linear, so rank 0 filters the sum.
@@ -37,34 +38,41 @@ def shard_slice(nrays_total, rank, world):
     return (nrays_total * rank) // world, (nrays_total * (rank + 1)) // world
 
 
-def global_times(mn, mx, device):
-    """All-reduce the per-channel (min non-zero, max) attenuated times; returns (predelay, max[])."""
-    t = torch.tensor([[(float(x) if x != 0 else math.inf) for x in mn], [-float(x) for x in mx]],
-                     device=device, dtype=torch.float32)
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    gmn = [0.0 if math.isinf(v) else v for v in t[0].tolist()]
-    gmx = (-t[1]).tolist()
+def _fold_predelay(gmn):
+    """findPredelay's fold over channels (rayverb.h:47-66): zeros are ignored."""
     predelay = 0.0
-    for v in gmn:   # findPredelay's fold over channels (rayverb.h:47-66): zeros are ignored
+    for v in gmn:
         if predelay == 0:
             predelay = v
         elif v != 0:
             predelay = min(predelay, v)
-    return predelay, gmx
+    return predelay
+
+
+def exchange_extrema(mn, mx, n_images, world, device):
+    """ONE small all-gather carries everything the shards need from each other before the
+    histogram: per-channel (min non-zero, max) attenuated times and the image-source count of
+    every rank.  Returns (predelay, max time per channel, image counts per rank)."""
+    nch = len(mn)
+    mine = torch.tensor([(float(x) if x != 0 else math.inf) for x in mn] + [float(x) for x in mx] + [float(n_images)],
+                        device=device, dtype=torch.float64)
+    allv = torch.empty((world, 2 * nch + 1), device=device, dtype=torch.float64)
+    dist.all_gather_into_tensor(allv, mine.unsqueeze(0))
+    allv = allv.cpu().numpy()   # float32 values and small integers are exact in float64
+    gmn = [0.0 if math.isinf(v) else float(v) for v in allv[:, :nch].min(axis=0)]
+    gmx = [float(v) for v in allv[:, nch:2 * nch].max(axis=0)]
+    counts = [int(v) for v in allv[:, 2 * nch]]
+    return _fold_predelay(gmn), gmx, counts
 
 
 _REC = 64 + 4 * NUM_IMAGE_SOURCE + 4   # Impulse + key[10] + key length, bytes per image source
 
 
-def merge_images(img, keys, klen, rank, world, device):
-    """Gather the per-shard unique image-source lists (two tensor collectives: counts, then the
-    padded records); rank 0 returns the global list (first occurrence in rank order wins), the
-    others an empty one."""
+def merge_images(img, keys, klen, counts, rank, world, device):
+    """Gather the per-shard unique image-source lists (one tensor collective over the padded
+    records; `counts` came with exchange_extrema); rank 0 returns the global list (first occurrence
+    in rank order wins), the others an empty one."""
     n = len(img)
-    counts = torch.zeros(world, dtype=torch.int64, device=device)
-    mine = torch.tensor([n], dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, mine)
-    counts = counts.tolist()
     nmax = max(counts)
     if nmax == 0:
         return np.zeros(0, dtype=IMPULSE)
@@ -74,13 +82,14 @@ def merge_images(img, keys, klen, rank, world, device):
         rec[:n, 64:64 + 4 * NUM_IMAGE_SOURCE] = np.ascontiguousarray(keys, dtype=np.uint32).reshape(n, -1).view(np.uint8)
         rec[:n, 64 + 4 * NUM_IMAGE_SOURCE:] = np.ascontiguousarray(klen, dtype=np.int32).reshape(n, 1).view(np.uint8)
     local = torch.from_numpy(rec).to(device)
-    gathered = torch.empty((world, nmax, _REC), dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(gathered, local.unsqueeze(0))
-    if rank != 0:
+    if rank == 0:
+        gathered = torch.empty((world, nmax, _REC), dtype=torch.uint8, device=device)
+        dist.gather(local.unsqueeze(0), list(gathered.unsqueeze(1).unbind(0)), dst=0)
+    else:
+        dist.gather(local.unsqueeze(0), None, dst=0)
         return np.zeros(0, dtype=IMPULSE)
     g = gathered.cpu().numpy()
-    parts = [g[r, :counts[r]] for r in range(world)]
-    allrec = np.ascontiguousarray(np.concatenate(parts))
+    allrec = np.ascontiguousarray(np.concatenate([g[r, :counts[r]] for r in range(world)]))
     gi = np.ascontiguousarray(allrec[:, :64]).view(IMPULSE).reshape(-1)
     gk = np.ascontiguousarray(allrec[:, 64:64 + 4 * NUM_IMAGE_SOURCE]).view(np.uint32).reshape(-1, NUM_IMAGE_SOURCE)
     gl = np.ascontiguousarray(allrec[:, 64 + 4 * NUM_IMAGE_SOURCE:]).view(np.int32).reshape(-1)
@@ -92,11 +101,11 @@ def sharded_histogram(shard, cfg, rank, world, device, sr, trim_predelay):
     """Stages 2-3 of the hot path on one shard + the collectives.  Returns (hist tensor on
     `device`, summed on rank 0; lengths; predelay)."""
     mn, mx = shard.render_times(cfg)
-    predelay, gmx = global_times(mn, mx, device)
-    lengths = [flatten_length(m, predelay, trim_predelay, sr) for m in gmx]
     img, keys, klen = shard.raw_images(with_keys=True)
-    shard.set_images(merge_images(img, keys, klen, rank, world, device))
-    hist = torch.zeros(sum(NBANDS * l for l in lengths), device=device, dtype=torch.float32)
+    predelay, gmx, counts = exchange_extrema(mn, mx, len(img), world, device)
+    lengths = [flatten_length(m, predelay, trim_predelay, sr) for m in gmx]
+    shard.set_images(merge_images(img, keys, klen, counts, rank, world, device))
+    hist = torch.empty(sum(NBANDS * l for l in lengths), device=device, dtype=torch.float32)   # render_histogram zero-fills
     shard.render_histogram(cfg, predelay, lengths, hist.data_ptr())
     dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
     return hist, lengths, predelay

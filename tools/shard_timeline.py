@@ -1,0 +1,40 @@
+"""Host wall-clock timeline of the sharded (multi-GPU) step on the C2 workload: where the time
+between the end of the trace and the final IR goes.  Run under torchrun, one rank per GPU."""
+import math, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "parallel-reverb-raytracer_b200", "python"))
+import numpy as np, torch, torch.distributed as dist
+from rayverb_b200 import api, scenes, sharding
+from rayverb_b200.types import NBANDS
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); api.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+api.set_stream(torch.cuda.current_stream().cuda_stream)
+tri, vtx, srf = scenes.shoebox()
+nrays = 1 << 20
+dirs = torch.from_numpy(scenes.sphere_directions(nrays * world, seed=2015)[rank * nrays:(rank + 1) * nrays].copy()).cuda()
+rt = api.Raytracer(128, tri, vtx, srf)
+kw = dict(speakers=[((0, 0, 1), 0.0)], sr=44100.0, ft="linkwitz_riley", lo_cutoff=45.0)
+cfg, keep = api.make_render_config(**kw)
+def sync(): torch.cuda.synchronize()
+for it in range(6):
+    dist.barrier(); sync(); T = [time.perf_counter()]
+    def mark(): sync(); T.append(time.perf_counter())
+    tr = rt.raytrace((7, 2, 4), (2, 1.5, 2), None, ray_offset=rank * nrays, device_ptr=dirs.data_ptr(), nrays=nrays); mark()
+    mn, mx = tr.render_times(cfg); mark()
+    img, keys, klen = tr.raw_images(with_keys=True); mark()
+    predelay, gmx, counts = sharding.exchange_extrema(mn, mx, len(img), world, "cuda"); mark()
+    lengths = [sharding.flatten_length(m, predelay, False, 44100.0) for m in gmx]
+    merged = sharding.merge_images(img, keys, klen, counts, rank, world, "cuda"); mark()
+    tr.set_images(merged); mark()
+    hist = torch.zeros(sum(NBANDS * l for l in lengths), device="cuda", dtype=torch.float32); mark()
+    tr.render_histogram(cfg, predelay, lengths, hist.data_ptr()); mark()
+    dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM); mark()
+    if rank == 0:
+        ir = api.render_finish(cfg, hist.data_ptr(), lengths)
+    mark()
+    names = ["raytrace", "render_times", "raw_images(D2H)", "exchange_extrema(allgather)", "merge_images(gather+host)", "set_images", "hist alloc", "render_histogram", "reduce(NCCL)", "finish(rank0)"]
+    d = [1e3 * (T[i + 1] - T[i]) for i in range(len(T) - 1)]
+    print(f"rank {rank} it {it} total {1e3*(T[-1]-T[0]):.2f} ms: " + ", ".join(f"{n} {v:.2f}" for n, v in zip(names, d)) + f" | images {len(img)} L {lengths}", flush=True)
+dist.destroy_process_group()
