@@ -241,39 +241,45 @@ struct BvhAccel {
     }
 };
 
-// kernel.cpp:195-214: pow(M_E, distance * AIR) * 1, with M_E narrowed to float.
-// pow(e_f, x) = 2^(x * log2(e_f)): the product is formed in double-float (hi + lo) so the
-// argument reduction is exact to ~2e-8, then ex2.approx on |r| <= 0.5 (max relative error
-// 2^-22).  Total error <= 2.6e-7 relative, i.e. ~2 ulp -- the same class as powf itself
-// (CUDA documents 4 ulp for powf); volumes are compared with a 2e-6 relative tolerance.
-__device__ __forceinline__ float pow_e_core(float x)
+// kernel.cpp:195-214: pow(M_E, distance * AIR) * 1, with M_E narrowed to float, for two bands at
+// once (packed FP32).  pow(e_f, x) = 2^(x * log2(e_f)) with log2(e_f) = L_HI + L_LO:
+//   t = fma(x, L_HI, 1.5 * 2^23)      low mantissa bits of t = n = rint(x * L_HI) (two's complement)
+//   n = t - 1.5 * 2^23
+//   r = fma(x, L_LO, fma(x, L_HI, -n))   |r| <= 0.5 (+ 1 ulp), the reduction error is ~2^-26 absolute
+//   2^r by ex2.approx (max relative error 2^-22), times 2^n through the exponent field.
+// Total error <= 2.6e-7 relative, i.e. ~2 ulp -- the same class as powf itself (CUDA documents
+// 4 ulp for powf); volumes are compared with a 2e-6 relative tolerance.  Every product feeds an
+// fma, so there is no mul + add pair that ptxas could contract differently in different kernels.
+__device__ __forceinline__ float2 pow_e_pair(float2 x)
 {
-    const float L_HI = 1.4426950216293335f;        // float(log2((float)M_E))
-    const float L_LO = -2.4551930266625277e-08f;   // log2((float)M_E) - L_HI
-    const float MAGIC = 12582912.0f;               // 1.5 * 2^23: adding it rounds to nearest-even integer
-    const float p_hi = __fmul_rn(x, L_HI);
-    const float p_lo = __fadd_rn(__fmaf_rn(x, L_HI, -p_hi), __fmul_rn(x, L_LO));
-    const float t = __fadd_rn(p_hi, MAGIC);        // low mantissa bits of t = n (two's complement), |n| < 2^22
-    const float n = __fsub_rn(t, MAGIC);           // = rintf(p_hi)
-    const float r = __fadd_rn(__fsub_rn(p_hi, n), p_lo);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r));
-    return __fmul_rn(e, __int_as_float((__float_as_int(t) << 23) + 0x3f800000));   // * 2^n
+    const float2 L_HI = bcast2(1.4426950216293335f);        // float(log2((float)M_E))
+    const float2 L_LO = bcast2(-2.4551930266625277e-08f);   // log2((float)M_E) - L_HI
+    const float MAGIC = 12582912.0f;                        // 1.5 * 2^23
+    const float2 t = __ffma2_rn(x, L_HI, bcast2(MAGIC));
+    const float2 n = __fadd2_rn(t, bcast2(-MAGIC));
+    const float2 r = __ffma2_rn(x, L_LO, __ffma2_rn(x, L_HI, neg2(n)));
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(r.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(r.y));
+    const float2 scale = make_float2(__int_as_float((__float_as_int(t.x) << 23) + 0x3f800000),
+                                     __int_as_float((__float_as_int(t.y) << 23) + 0x3f800000));   // 2^n
+    return __fmul2_rn(e, scale);
 }
 __device__ __noinline__ float pow_e_slow(float x) { return powf(RVB_M_E_F, x); }
-// All eight bands at once.  The exponents distance * AIR are <= 0 (distance >= 0, every AIR < 0,
-// rayverb.cpp:632-641) and AIR[7] is the most negative, so one test on band 7 covers the fast path's
-// range for all of them; NaN, negative distances and exponents below -83 (result < 2^-120) take the
-// library powf.
-__device__ __forceinline__ void air_attenuation(float distance, const float *air, float *att)
+// All eight bands, as four pairs.  The exponents distance * AIR are <= 0 (distance >= 0, every
+// AIR < 0, rayverb.cpp:632-641) and AIR[7] is the most negative, so one test on band 7 covers the
+// fast path's range for all of them; NaN, negative distances and exponents below -83 (result <
+// 2^-120) take the library powf.
+__device__ __forceinline__ void air_attenuation(float distance, const float *air, float2 *att)
 {
     const float worst = __fmul_rn(__fmul_rn(distance, air[RVB_NBANDS - 1]), 1.4426950216293335f);
     if (worst > -120.0f && distance >= 0.0f) {
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) att[b] = pow_e_core(__fmul_rn(distance, air[b]));
+        for (int b = 0; b < RVB_NBANDS / 2; ++b) att[b] = pow_e_pair(__fmul2_rn(bcast2(distance), make_float2(air[2 * b], air[2 * b + 1])));
     } else {
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) att[b] = pow_e_slow(__fmul_rn(distance, air[b]));
+        for (int b = 0; b < RVB_NBANDS / 2; ++b)
+            att[b] = make_float2(pow_e_slow(__fmul_rn(distance, air[2 * b])), pow_e_slow(__fmul_rn(distance, air[2 * b + 1])));
     }
 }
 
@@ -301,18 +307,18 @@ __device__ __forceinline__ f3 mirror_point(f3 p, const MirrorTri &t)
 
 // kernel.cpp:243-265
 __device__ __forceinline__ void add_image(const TraceParams &P, f3 mic, f3 mic_reflection, f3 source, size_t slot,
-                                          const float *volume, uint32_t object_index)
+                                          const float2 *volume, uint32_t object_index)
 {
     f3 diff = source - mic_reflection;
     float dist = length(diff);
-    float att[RVB_NBANDS];
+    float2 att[RVB_NBANDS / 2];
     air_attenuation(dist, P.air, att);
-    float v[RVB_NBANDS];
+    float2 v[RVB_NBANDS / 2];
 #pragma unroll
-    for (int b = 0; b < RVB_NBANDS; ++b) v[b] = __fmul_rn(volume[b], att[b]);
+    for (int b = 0; b < RVB_NBANDS / 2; ++b) v[b] = __fmul2_rn(volume[b], att[b]);
     f3 p = mic + diff;
-    P.cand_volA[slot] = make_float4(v[0], v[1], v[2], v[3]);
-    P.cand_volB[slot] = make_float4(v[4], v[5], v[6], v[7]);
+    P.cand_volA[slot] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    P.cand_volB[slot] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
     P.cand_pt[slot] = make_float4(p.x, p.y, p.z, __fmul_rn(RVB_SECONDS_PER_METER, dist));
     P.cand_idx[slot] = object_index;
 }
@@ -320,7 +326,7 @@ __device__ __forceinline__ void add_image(const TraceParams &P, f3 mic, f3 mic_r
 struct RayState {
     f3 pos, dir;
     float distance;
-    float volume[RVB_NBANDS];
+    float2 volume[RVB_NBANDS / 2];   // eight bands as four packed pairs
 };
 
 // kernel.cpp:459-501: everything a reflection does after the nearest hit is known
@@ -334,33 +340,33 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
     const f3 normal = mk3(nrm4);
     const float4 *surf = reinterpret_cast<const float4 *>(P.surfaces + __float_as_uint(nrm4.w));
     const float4 s0 = __ldg(surf), s1 = __ldg(surf + 1), d0 = __ldg(surf + 2), d1 = __ldg(surf + 3);
-    const float spec[RVB_NBANDS] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float diff[RVB_NBANDS] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    float newVol[RVB_NBANDS];
+    const float2 spec[RVB_NBANDS / 2] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+    const float2 diff[RVB_NBANDS / 2] = {make_float2(d0.x, d0.y), make_float2(d0.z, d0.w), make_float2(d1.x, d1.y), make_float2(d1.z, d1.w)};
+    float2 newVol[RVB_NBANDS / 2];
 #pragma unroll
-    for (int b = 0; b < RVB_NBANDS; ++b) newVol[b] = __fmul_rn(-R.volume[b], spec[b]);     // :461
+    for (int b = 0; b < RVB_NBANDS / 2; ++b) newVol[b] = __fmul2_rn(neg2(R.volume[b]), spec[b]);   // :461
 
     const bool vis = point_visible(acc, X, mic, c);                          // :463
     const float DIST = vis ? __fadd_rn(newDist, length(mic - X)) : 0.0f;     // :471
     const float DIFF = fabsf(dot(normal, R.dir));                            // :478
-    float out[RVB_NBANDS];
+    float2 out[RVB_NBANDS / 2];
     bool any = false;
     if (vis) {
-        float att[RVB_NBANDS];
+        float2 att[RVB_NBANDS / 2];
         air_attenuation(DIST, P.air, att);
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) {
-            out[b] = __fmul_rn(__fmul_rn(__fmul_rn(newVol[b], att[b]), diff[b]), DIFF);     // :481-485
-            any |= (out[b] != 0.0f);
+        for (int b = 0; b < RVB_NBANDS / 2; ++b) {
+            out[b] = __fmul2_rn(__fmul2_rn(__fmul2_rn(newVol[b], att[b]), diff[b]), bcast2(DIFF));   // :481-485
+            any |= (out[b].x != 0.0f) | (out[b].y != 0.0f);
         }
     } else {
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) out[b] = 0.0f;
+        for (int b = 0; b < RVB_NBANDS / 2; ++b) out[b] = make_float2(0.0f, 0.0f);
     }
     const float time = __fmul_rn(RVB_SECONDS_PER_METER, DIST);               // :489
     const size_t slot = (size_t)index * P.nrays + ray;
-    P.vol[2 * slot] = make_float4(out[0], out[1], out[2], out[3]);
-    P.vol[2 * slot + 1] = make_float4(out[4], out[5], out[6], out[7]);
+    P.vol[2 * slot] = make_float4(out[0].x, out[0].y, out[1].x, out[1].y);
+    P.vol[2 * slot + 1] = make_float4(out[2].x, out[2].y, out[3].x, out[3].y);
     P.pt[slot] = make_float4(X.x, X.y, X.z, time);
     P.tkey[slot] = any ? time : -1.0f;
     if (any) {
@@ -373,7 +379,7 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
     R.pos = X;
     R.distance = newDist;
 #pragma unroll
-    for (int b = 0; b < RVB_NBANDS; ++b) R.volume[b] = newVol[b];
+    for (int b = 0; b < RVB_NBANDS / 2; ++b) R.volume[b] = newVol[b];
 }
 
 // a ray that left the mesh keeps zero impulses in its remaining slots (rayverb.cpp:601-603)
@@ -392,8 +398,8 @@ __device__ __forceinline__ void store_state(const TraceParams &P, uint32_t ray, 
     float4 *s = P.state + 4 * (size_t)ray;
     s[0] = make_float4(R.pos.x, R.pos.y, R.pos.z, R.distance);
     s[1] = make_float4(R.dir.x, R.dir.y, R.dir.z, alive ? 1.0f : 0.0f);
-    s[2] = make_float4(R.volume[0], R.volume[1], R.volume[2], R.volume[3]);
-    s[3] = make_float4(R.volume[4], R.volume[5], R.volume[6], R.volume[7]);
+    s[2] = make_float4(R.volume[0].x, R.volume[0].y, R.volume[1].x, R.volume[1].y);
+    s[3] = make_float4(R.volume[2].x, R.volume[2].y, R.volume[3].x, R.volume[3].y);
 }
 
 // Reflections [0, P.last) WITH the image-source branch (kernel.cpp:379-457); P.last <= 9.
@@ -407,7 +413,7 @@ __device__ void image_phase_ray(const Accel &acc, const TraceParams &P, uint32_t
     R.dir = mk3(__ldg(P.dirs + ray));
     R.distance = 0.0f;
 #pragma unroll
-    for (int b = 0; b < RVB_NBANDS; ++b) R.volume[b] = 1.0f;
+    for (int b = 0; b < RVB_NBANDS / 2; ++b) R.volume[b] = make_float2(1.0f, 1.0f);
     MirrorTri prev[RVB_NUM_IMAGE_SOURCE - 1];
     f3 mic_reflection = mic;
 
@@ -479,14 +485,14 @@ __device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TracePa
         R.dir = mk3(__ldg(P.dirs + ray));
         R.distance = 0.0f;
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS; ++b) R.volume[b] = 1.0f;
+        for (int b = 0; b < RVB_NBANDS / 2; ++b) R.volume[b] = make_float2(1.0f, 1.0f);
     } else {
         const float4 *s = P.state + 4 * (size_t)ray;
         const float4 a = s[0], d = s[1], va = s[2], vb = s[3];
         if (d.w == 0.0f) return;   // left the mesh during the image phase (slots already zero-filled)
         R.pos = mk3(a); R.distance = a.w; R.dir = mk3(d);
-        R.volume[0] = va.x; R.volume[1] = va.y; R.volume[2] = va.z; R.volume[3] = va.w;
-        R.volume[4] = vb.x; R.volume[5] = vb.y; R.volume[6] = vb.z; R.volume[7] = vb.w;
+        R.volume[0] = make_float2(va.x, va.y); R.volume[1] = make_float2(va.z, va.w);
+        R.volume[2] = make_float2(vb.x, vb.y); R.volume[3] = make_float2(vb.z, vb.w);
     }
     uint32_t index = P.first;
     for (; index != P.last; ++index) {
@@ -812,8 +818,8 @@ __global__ void __launch_bounds__(256) wf_emit_kernel(const WfParams W)
             const float4 va = s[2], vb = s[3];
             RayState R;
             R.pos = mk3(a); R.distance = a.w; R.dir = mk3(d);
-            R.volume[0] = va.x; R.volume[1] = va.y; R.volume[2] = va.z; R.volume[3] = va.w;
-            R.volume[4] = vb.x; R.volume[5] = vb.y; R.volume[6] = vb.z; R.volume[7] = vb.w;
+            R.volume[0] = make_float2(va.x, va.y); R.volume[1] = make_float2(va.z, va.w);
+            R.volume[2] = make_float2(vb.x, vb.y); R.volume[3] = make_float2(vb.z, vb.w);
             const KnownVisibility vis{h.z != 0.0f};
             const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
             shade_and_reflect(vis, P, mic, ray, index, h.x, prim, R, c);
