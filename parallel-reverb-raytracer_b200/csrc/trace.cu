@@ -571,8 +571,8 @@ __global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TracePara
     flush_counters(P, c);
 }
 
-template <bool IMAGES>
-__global__ void __launch_bounds__(128) trace_bvh_kernel(const TraceParams P)
+template <bool IMAGES, int MINB>
+__global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams P)
 {
     BvhAccel acc{P.nodes, P.tri_sorted, P.order};
     Counters c;
@@ -939,14 +939,19 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         if (split > 0) {
             P.first = 0; P.last = split;
             if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
-            else RVB_TRY(launch_phase(trace_bvh_kernel<true>, P, 128, 0, st));
+            else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, 0, st));
             RVB_CUDA(cudaEventRecord(em, st));
             RVB_CUDA(cudaMemcpyAsync(hm, d_counters, sizeof hm, cudaMemcpyDeviceToHost, st));
         }
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
             if (brute) RVB_TRY(launch_bruteforce<false>(P, smem, st));
-            else if (!wavefront) RVB_TRY(launch_phase(trace_bvh_kernel<false>, P, 128, 0, st));
+            else if (!wavefront) {
+                // 7 CTAs of 128 threads per SM (<= 72 registers, a few spills) measured fastest on
+                // the C3 hall: 26.6 ms per 262 k rays against 29.1 (93 registers, 5 CTAs), 28.0 (8 CTAs),
+                // 28.6 (10) and 36.2 (12) -- gpurun_out/sweep_bvh.log
+                RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, 0, st));
+            }
             else {
                 if (split == 0) {
                     note_launch(), wf_init_state_kernel<<<(unsigned)((tr->nrays + 255) / 256), 256, 0, st>>>(P);
@@ -958,7 +963,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         // zero reflections: the reference still computes the direct path for ray 0
         P.first = 0; P.last = 0;
         if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
-        else RVB_TRY(launch_phase(trace_bvh_kernel<true>, P, 128, 0, st));
+        else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, 0, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
     unsigned long long h[5];
