@@ -231,10 +231,118 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
     }
 }
 
+// Dense responses (hundreds of impulses per bin): one CTA of eight warps per segment.  Each warp
+// takes a contiguous eighth of the segment's sorted entries (same lane striding and shuffle tree as
+// above), the eight partial sums are combined in warp order -- a fixed order, so the result is
+// still deterministic.  What this buys is LOCALITY IN TIME: only ~2 CTAs per SM are resident, so at
+// any moment the kernel works on a window of ~300 adjacent segments instead of ~9500, the two
+// reflections of a slot group (rvb_internal.cuh: slot_of) are gathered within a few tens of
+// megabytes of traffic of each other, and three of the four hit L2 instead of fetching their
+// 128-byte line from HBM again.
+template <int MODEL, bool NEED_POS, int NSUB, int MAXC, int RVB_REDUCE_WARPS>
+__global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const Source S, const ChanSpec C, const uint32_t *keys,
+                                                                          const uint32_t *vals, const uint32_t *seg_begin,
+                                                                          const uint32_t *seg_end, uint32_t nseg, uint32_t L,
+                                                                          float *hist, size_t chan_stride)
+{
+    static_assert(NSUB * MAXC * RVB_NBANDS == 32, "one lane per (sub-bin, channel, band) in the final combine");
+    __shared__ float part[RVB_REDUCE_WARPS][32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t w = blockIdx.x; w < nseg; w += gridDim.x) {
+        const uint32_t seg = nseg - 1 - w;   // from the end of the response (ascending order measured the same)
+        const uint32_t b0 = seg_begin[seg], b1 = seg_end[seg];
+        if (b0 == b1) continue;   // block-uniform
+        const uint32_t chunk = (b1 - b0 + RVB_REDUCE_WARPS - 1) / RVB_REDUCE_WARPS;
+        const uint32_t m0 = min(b1, b0 + wid * chunk), m1 = min(b1, m0 + chunk);
+        float acc[NSUB][MAXC][RVB_NBANDS];
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s)
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0f;
+        for (uint32_t j = m0 + lane; j < m1; j += 128) {
+            uint32_t idx[4], sub[4];
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                idx[u] = RVB_NO_IMPULSE; sub[u] = 0;
+                if (j + 32 * u < m1) {
+                    idx[u] = vals[j + 32 * u];
+                    if (NSUB > 1) {
+                        const uint32_t k = keys[j + 32 * u];
+                        if (k >= L) idx[u] = RVB_NO_IMPULSE;   // skipped impulses share the last segment
+                        sub[u] = k & (NSUB - 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (idx[u] != RVB_NO_IMPULSE) S.volume(idx[u], va[u], vb[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (idx[u] != RVB_NO_IMPULSE) accumulate_one<MODEL, NEED_POS, NSUB, MAXC>(S, C, idx[u], sub[u], va[u], vb[u], acc);
+        }
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s)
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS; ++b) {
+                    float x = acc[s][c][b];
+                    for (int o = 16; o; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+                    if (lane == 0) part[wid][(s * MAXC + c) * RVB_NBANDS + b] = x;
+                }
+        __syncthreads();
+        if (wid == 0) {
+            float x = part[0][lane];
+#pragma unroll
+            for (int q = 1; q < RVB_REDUCE_WARPS; ++q) x = __fadd_rn(x, part[q][lane]);
+            const uint32_t b = lane % RVB_NBANDS, c = (lane / RVB_NBANDS) % MAXC, sb = lane / (RVB_NBANDS * MAXC);
+            const uint32_t bin = seg * NSUB + sb;
+            if (c < (uint32_t)C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = x;
+        }
+        __syncthreads();
+    }
+}
+
+template <class K>
+static unsigned resident_grid(K kernel, int block)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return (unsigned)(per_sm * sm_count());
+}
+
+// `dense`: hundreds of entries per segment on average -> one CTA per segment (see reduce_cta_kernel)
+template <int MODEL, bool NEED_POS, int NSUB, int MAXC, int WARPS>
+static void launch_reduce_cta(cudaStream_t st, const Source &S, const ChanSpec &C, const uint32_t *keys, const uint32_t *vals,
+                              const uint32_t *b, const uint32_t *e, uint32_t nseg, uint32_t L, float *dst, size_t stride)
+{
+    static const int forced_grid = getenv("RVB_REDUCE_GRID") ? atoi(getenv("RVB_REDUCE_GRID")) : 0;
+    auto k = reduce_cta_kernel<MODEL, NEED_POS, NSUB, MAXC, WARPS>;
+    // two CTAs per SM: 296 segments in flight measured best on C2 (2.54 ms; 444: 2.72, 148: 3.86 --
+    // profiles/r1d_sweep_reduce.log): enough loads in flight, smallest window of bins
+    unsigned grid = forced_grid > 0 ? (unsigned)forced_grid : std::min(resident_grid(k, 32 * WARPS), 2u * (unsigned)sm_count());
+    k<<<std::min(nseg, grid), 32 * WARPS, 0, st>>>(S, C, keys, vals, b, e, nseg, L, dst, stride);
+}
 template <int MODEL, bool NEED_POS>
-static void launch_reduce(int nsub, unsigned grid, cudaStream_t st, const Source &S, const ChanSpec &C, const uint32_t *keys,
+static void launch_reduce(int nsub, unsigned grid, bool dense, cudaStream_t st, const Source &S, const ChanSpec &C, const uint32_t *keys,
                           const uint32_t *vals, const uint32_t *b, const uint32_t *e, uint32_t nseg, uint32_t L, float *dst, size_t stride)
 {
+    static const int warps = getenv("RVB_REDUCE_WARPS") ? atoi(getenv("RVB_REDUCE_WARPS")) : 8;
+    if (dense && warps == 16) {
+        if (nsub == 4) launch_reduce_cta<MODEL, NEED_POS, 4, 1, 16>(st, S, C, keys, vals, b, e, nseg, L, dst, stride);
+        else if (nsub == 2) launch_reduce_cta<MODEL, NEED_POS, 2, 2, 16>(st, S, C, keys, vals, b, e, nseg, L, dst, stride);
+        else launch_reduce_cta<MODEL, NEED_POS, 1, RVB_MAX_GROUP, 16>(st, S, C, keys, vals, b, e, nseg, L, dst, stride);
+        return;
+    }
+    if (dense) {
+        if (nsub == 4) launch_reduce_cta<MODEL, NEED_POS, 4, 1, 8>(st, S, C, keys, vals, b, e, nseg, L, dst, stride);
+        else if (nsub == 2) launch_reduce_cta<MODEL, NEED_POS, 2, 2, 8>(st, S, C, keys, vals, b, e, nseg, L, dst, stride);
+        else launch_reduce_cta<MODEL, NEED_POS, 1, RVB_MAX_GROUP, 8>(st, S, C, keys, vals, b, e, nseg, L, dst, stride);
+        return;
+    }
     if (nsub == 4) reduce_kernel<MODEL, NEED_POS, 4, 1><<<grid, 256, 0, st>>>(S, C, keys, vals, b, e, nseg, L, dst, stride);
     else if (nsub == 2) reduce_kernel<MODEL, NEED_POS, 2, 2><<<grid, 256, 0, st>>>(S, C, keys, vals, b, e, nseg, L, dst, stride);
     else reduce_kernel<MODEL, NEED_POS, 1, RVB_MAX_GROUP><<<grid, 256, 0, st>>>(S, C, keys, vals, b, e, nseg, L, dst, stride);
@@ -451,7 +559,7 @@ static int make_source(const rvb_trace *tr, const rvb_render_config *cfg, Source
     const bool diffuse = cfg->output_mode != RVB_OUTPUT_IMAGE_ONLY;
     const bool images = cfg->output_mode != RVB_OUTPUT_DIFFUSE_ONLY;
     if (diffuse) {
-        size_t n = tr->nrays * tr->nrefl;
+        size_t n = slot_count(tr->nrays, tr->nrefl);   // includes the unused (skipped) slots of a partial last group
         S.vol = tr->d_vol; S.pt = tr->d_pt; S.tkey = tr->d_tkey; S.n_diffuse = (uint32_t)n;
         S.have_ext = tr->has_time_ext; S.ext_min_nz = tr->diffuse_tmin_nz; S.ext_max = tr->diffuse_tmax;
     }
@@ -610,10 +718,12 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             for (int c = 0; c < C.nch; ++c) need_pos |= (C.coef[c] != 0.0f);
             note_launch();
             const int nsub = 1 << shift;
-            if (C.model == 0 && need_pos) launch_reduce<0, true>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
-            else if (C.model == 0) launch_reduce<0, false>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
-            else if (C.model == 1) launch_reduce<1, true>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
-            else launch_reduce<2, false>(nsub, rgrid, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            static const int force = getenv("RVB_REDUCE_DENSE") ? atoi(getenv("RVB_REDUCE_DENSE")) : -1;
+            const bool dense = force >= 0 ? force != 0 : (size_t)n >= (size_t)256 * nseg;
+            if (C.model == 0 && need_pos) launch_reduce<0, true>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else if (C.model == 0) launch_reduce<0, false>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else if (C.model == 1) launch_reduce<1, true>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else launch_reduce<2, false>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
         }
         RVB_CUDA(cudaGetLastError());
         g_stats.reduce_ms += tr_.stop();

@@ -98,6 +98,23 @@ struct Scene {
     float build_ms = 0.f;
 };
 
+// ---- impulse slots ----------------------------------------------------------------------------
+// Diffuse impulses live in a bounce-major SoA whose unit is a GROUP of four consecutive reflections
+// of one ray: slot = ((bounce / 4) * nrays + ray) * 4 + (bounce & 3), so the four 32-byte volume
+// sectors of a group fill exactly one 128-byte line.  Why: an L2 miss on B200 fetches the whole
+// 128-byte line from HBM (tools/gather_bench.cu: 125 B of DRAM traffic per random 32-byte gather),
+// and the histogram reduction gathers impulses at random while it walks the sample bins in order.
+// The four reflections of a group arrive ~500 samples apart, i.e. within a few tens of megabytes of
+// reduction traffic, so three of the four gathers of a line hit L2.  The 32 lanes of a warp (same
+// bounce, consecutive rays) still write whole 32-byte sectors.  When the reflection count is not a
+// multiple of four the unused slots of the last group are marked as skipped (tkey = -1).
+#define RVB_SLOT_GROUP 4u
+__host__ __device__ inline size_t slot_of(uint32_t ray, uint32_t bounce, size_t nrays)
+{
+    return ((size_t)(bounce / RVB_SLOT_GROUP) * nrays + ray) * RVB_SLOT_GROUP + (bounce % RVB_SLOT_GROUP);
+}
+__host__ __device__ inline size_t slot_count(size_t nrays, size_t nrefl) { return (nrefl + RVB_SLOT_GROUP - 1) / RVB_SLOT_GROUP * RVB_SLOT_GROUP * nrays; }
+
 // ---- trace results ----------------------------------------------------------------------------
 struct Trace {
     Scene *scene = nullptr;
@@ -105,7 +122,7 @@ struct Trace {
     uint64_t ray_offset = 0;
     unsigned flags = 0;
     float mic[3] = {0, 0, 0}, src[3] = {0, 0, 0};
-    // diffuse impulses, BOUNCE-major: slot = bounce * nrays + ray
+    // diffuse impulses, bounce-GROUP-major: slot_of(ray, bounce, nrays), slot_count() slots
     float4 *d_vol = nullptr;                        // [2*slots]: bands 0-3 at 2*slot, 4-7 at 2*slot+1 (one 32-B sector)
     float4 *d_pt = nullptr;                        // position xyz, time
     float *d_tkey = nullptr;                       // time if any(volume != 0) else -1 (kernel.cpp:524 skip rule)

@@ -16,8 +16,9 @@
 // lowest-index tie-break of the reference's strict '<' loop (kernel.cpp:180-188) -- equals the
 // brute-force loop.
 //
-// Output is a bounce-major SoA (slot = bounce * nrays + ray) so that the 32 lanes of a warp,
-// which sit at the same bounce, write 32 consecutive 32-byte sectors.
+// Output is a bounce-group-major SoA (slot_of, rvb_internal.cuh): the 32 lanes of a warp, which sit
+// at the same bounce, write 32 whole 32-byte sectors, and four consecutive reflections of a ray
+// share one 128-byte line for the benefit of the histogram reduction.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -364,7 +365,7 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
         for (int b = 0; b < RVB_NBANDS / 2; ++b) out[b] = make_float2(0.0f, 0.0f);
     }
     const float time = __fmul_rn(RVB_SECONDS_PER_METER, DIST);               // :489
-    const size_t slot = (size_t)index * P.nrays + ray;
+    const size_t slot = slot_of(ray, index, P.nrays);
     P.vol[2 * slot] = make_float4(out[0].x, out[0].y, out[1].x, out[1].y);
     P.vol[2 * slot + 1] = make_float4(out[2].x, out[2].y, out[3].x, out[3].y);
     P.pt[slot] = make_float4(X.x, X.y, X.z, time);
@@ -386,7 +387,7 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
 __device__ __forceinline__ void zero_fill(const TraceParams &P, uint32_t ray, uint32_t index)
 {
     for (; index != P.nrefl; ++index) {
-        const size_t slot = (size_t)index * P.nrays + ray;
+        const size_t slot = slot_of(ray, index, P.nrays);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         P.vol[2 * slot] = z; P.vol[2 * slot + 1] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
         if (P.hit) P.hit[slot] = RVB_NONE;
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(256) wf_emit_kernel(const WfParams W)
         }
         if (!alive) {
             // zero impulse in this slot (rayverb.cpp:601-603)
-            const size_t slot = (size_t)index * P.nrays + ray;
+            const size_t slot = slot_of(ray, index, P.nrays);
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             P.vol[2 * slot] = z; P.vol[2 * slot + 1] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
             if (P.hit) P.hit[slot] = RVB_NONE;

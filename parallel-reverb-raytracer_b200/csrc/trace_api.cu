@@ -21,10 +21,18 @@ __global__ void export_diffuse_kernel(const float4 *vol, const float4 *pt, uint3
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over nr*nrefl, bounce fastest
     if (i >= (size_t)nr * nrefl) return;
     uint32_t r = (uint32_t)(i / nrefl), b = (uint32_t)(i % nrefl);
-    size_t slot = (size_t)b * nrays + ray0 + r;
+    size_t slot = slot_of(ray0 + r, b, nrays);
     float4 a = vol[2 * slot], c = vol[2 * slot + 1], p = pt[slot];
     float4 *o = reinterpret_cast<float4 *>(out + i);
     o[0] = a; o[1] = c; o[2] = make_float4(p.x, p.y, p.z, 0.f); o[3] = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+
+// reflection count not a multiple of the slot group: the tail of the last group holds no impulses
+__global__ void mark_unused_slots_kernel(float *tkey, uint32_t nrays, uint32_t nrefl)
+{
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrays) return;
+    for (uint32_t b = nrefl; b % RVB_SLOT_GROUP != 0; ++b) tkey[slot_of(r, b, nrays)] = -1.0f;
 }
 
 __global__ void export_images_kernel(const float4 *volA, const float4 *volB, const float4 *pt, uint32_t n, rvb_impulse *out)
@@ -50,7 +58,7 @@ __global__ void export_hits_kernel(const uint32_t *hit, uint32_t nrays, uint32_t
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nrays * nrefl) return;
     uint32_t r = (uint32_t)(i / nrefl), b = (uint32_t)(i % nrefl);
-    out[i] = hit[(size_t)b * nrays + r];
+    out[i] = hit[slot_of(r, b, nrays)];
 }
 
 static int trace_run_impl(rvb_scene *scene, const float mic[3], const float source[3], const float4 *d_dirs, size_t nrays,
@@ -61,7 +69,7 @@ static int trace_run_impl(rvb_scene *scene, const float mic[3], const float sour
     tr->scene = scene; tr->nrays = nrays; tr->nrefl = nrefl; tr->ray_offset = ray_offset; tr->flags = flags;
     for (int i = 0; i < 3; ++i) { tr->mic[i] = mic[i]; tr->src[i] = source[i]; }
     tr->stats.nrays = nrays; tr->stats.nreflections = nrefl;
-    const size_t nslots = nrays * nrefl;
+    const size_t nslots = slot_count(nrays, nrefl);
     int rc = RVB_OK;
     float4 *cvA = nullptr, *cvB = nullptr, *cpt = nullptr;
     uint32_t *cidx = nullptr;
@@ -74,6 +82,7 @@ static int trace_run_impl(rvb_scene *scene, const float mic[3], const float sour
     if ((rc = dev_alloc(&tr->d_vol, 2 * nslots)) || (rc = dev_alloc(&tr->d_pt, nslots)) ||
         (rc = dev_alloc(&tr->d_tkey, nslots)))
         return bail(rc);
+    if ((nrefl % RVB_SLOT_GROUP) && nrays) note_launch(), mark_unused_slots_kernel<<<(unsigned)((nrays + 255) / 256), 256, 0, st>>>(tr->d_tkey, (uint32_t)nrays, (uint32_t)nrefl);
     if (flags & RVB_TRACE_DEBUG) {
         if ((rc = dev_alloc(&tr->d_hit, nslots)) || (rc = dev_alloc(&tr->d_count, nrays))) return bail(rc);
     }
