@@ -378,31 +378,63 @@ __device__ __forceinline__ M2 m2_mul(const M2 &x, const M2 &y)
     return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
 }
 
-// One CTA (1024 threads) per (channel, band) row.  The recurrence is linear in its (z1, z2) state,
-// so a sweep is split into 1024 chunks of 16 samples per shared-memory tile:
-//   pass 1  every thread runs the reference recurrence over its chunk from a ZERO state and keeps
-//           the end state e_j;
-//   scan    the true start state of chunk j is S_j = M S_{j-1} + e_{j-1}, M = A^16 (A = homogeneous
-//           transition [[-a1, 1], [-a2, 0]], obtained by running the same recurrence on the unit
-//           states).  Three levels: lane 0 of every warp composes its 32 chunks from a zero state,
-//           thread 0 composes the 32 warp totals with M^32, then every thread adds M^lane times its
-//           warp's start state.  The carry crosses tiles.
-//   pass 2  every thread re-runs the reference recurrence from S_j and stores (float)out.
-// Pass 2 is the reference's own arithmetic; only S_j is associated differently (double, ~1e-16
-// relative), so the float outputs equal the serial filter's except for vanishingly rare
-// last-bit rounding flips.  `twopass` = forward sweep then backward sweep (filters.cpp:185-191).
+// A thread-block CLUSTER of up to 8 CTAs (1024 threads each) per (channel, band) row.  The
+// recurrence is linear in its (z1, z2) state, so a sweep is split twice:
+//
+//   tiles   16384 samples each, dealt round-robin to the CTAs of the cluster.  Phase 1: every CTA
+//           runs its tiles from a ZERO state and publishes their end states; cluster barrier; every
+//           CTA folds the tile end states with M_T = A^16384 into the true start state of its own
+//           tiles (a few dozen 2x2 steps); phase 2: every CTA re-runs its tiles from those states
+//           and stores the output.  The zero-state work is done twice, but the tiles of a row now
+//           run on up to 8 SMs instead of one after the other on a single SM.
+//   chunks  inside a tile, 1024 chunks of 16 samples, one per thread:
+//     pass 1  every thread runs the reference recurrence over its chunk from a ZERO state and keeps
+//             the end state e_j;
+//     scan    the true start state of chunk j is S_j = M S_{j-1} + e_{j-1}, M = A^16 (A = homogeneous
+//             transition [[-a1, 1], [-a2, 0]], obtained by running the same recurrence on the unit
+//             states).  Three levels: lane 0 of every warp composes its 32 chunks from a zero state,
+//             thread 0 composes the 32 warp totals with M^32, then every thread adds M^lane times its
+//             warp's start state;
+//     pass 2  every thread re-runs the reference recurrence from S_j and stores (float)out.
+// Pass 2 is the reference's own arithmetic; only the start states are associated differently
+// (double, ~1e-16 relative), so the float outputs equal the serial filter's except for vanishingly
+// rare last-bit rounding flips.  `twopass` = forward sweep then backward sweep (filters.cpp:185-191).
+__device__ __forceinline__ void cluster_sync_all()
+{
+    // release/acquire at cluster scope: global writes of the other CTAs of the cluster are visible after it
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
 __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const uint32_t *row_off, const uint32_t *row_len,
-                                                              const RowFilter *filters, int mode /* 1 onepass, 2 twopass */)
+                                                              const RowFilter *filters, int mode /* 1 onepass, 2 twopass */,
+                                                              double *tile_ends /* [row][max_tiles][2] */, uint32_t max_tiles)
 {
     extern __shared__ float tile[];                       // RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1), padded rows
     __shared__ double e1[RVB_IIR_THREADS], e2[RVB_IIR_THREADS];   // pass-1 end states, then local prefixes
     __shared__ double w1[RVB_IIR_WARPS], w2[RVB_IIR_WARPS];       // warp totals, then warp start states
     __shared__ M2 pw[32];                                          // M^lane
     __shared__ M2 MW;                                              // M^32
+    __shared__ M2 MT;                                              // M^1024 = A^RVB_IIR_TILE
     __shared__ double carry[2];
-    const uint32_t row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    const uint32_t row = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *x = data + row_off[row];
     const uint32_t n = row_len[row];
+    const uint32_t ntiles = (n + RVB_IIR_TILE - 1) / RVB_IIR_TILE;
+    double *ends = tile_ends + (size_t)row * max_tiles * 2;
     const RowFilter F = filters[row];
     float *mine = tile + tid * (RVB_IIR_CHUNK + 1);
     for (int p = 0; p < F.npass; ++p) {
@@ -422,63 +454,93 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
             M2 P = M2{1.0, 0.0, 0.0, 1.0};
             for (uint32_t k = 0; k < lane; ++k) P = m2_mul(Mc, P);
             pw[lane] = P;
-            if (lane == 31) MW = m2_mul(Mc, P);
+            if (lane == 31) {
+                M2 W = m2_mul(Mc, P);      // M^32
+                MW = W;
+                for (int k = 0; k < 5; ++k) W = m2_mul(W, W);   // (M^32)^32 = M^1024
+                MT = W;
+            }
         }
         for (int dirn = 0; dirn < mode; ++dirn) {
-            if (tid == 0) { carry[0] = 0.0; carry[1] = 0.0; }
-            __syncthreads();
-            for (uint32_t t0 = 0; t0 < n; t0 += RVB_IIR_TILE) {
-                for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
-                    const uint32_t i = t0 + k;
-                    float v = 0.0f;   // zero padding past the end never feeds a stored sample
-                    if (i < n) v = dirn == 0 ? x[i] : x[n - 1 - i];
-                    tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)] = v;
-                }
+            // phase 0: zero-state end of every tile of this CTA; phase 1: the real thing
+            double fold_a = 0.0, fold_b = 0.0;   // thread 0: start state of tile fold_pos
+            uint32_t fold_pos = 0;
+            for (int phase = (ntiles > 1 ? 0 : 1); phase < 2; ++phase) {
                 __syncthreads();
-                double z1 = 0.0, z2 = 0.0;
-                biquad_chunk<false>(q, mine, z1, z2);
-                e1[tid] = z1; e2[tid] = z2;
-                __syncwarp();
-                if (lane == 0) {   // level 1: local prefixes of this warp's chunks, from a zero state
-                    const M2 M = pw[1];
-                    double a = 0.0, b = 0.0;
-                    for (int j = 0; j < 32; ++j) {
-                        const double ea = e1[tid + j], eb = e2[tid + j];
-                        e1[tid + j] = a; e2[tid + j] = b;
-                        const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
-                        a = na; b = nb;
+                for (uint32_t t = crank; t < ntiles; t += csize) {
+                    const uint32_t t0 = t * RVB_IIR_TILE;
+                    if (phase == 0 && t + 1 == ntiles) continue;   // nobody needs the end state of the last tile
+                    if (tid == 0) {
+                        if (phase == 0) { carry[0] = 0.0; carry[1] = 0.0; }
+                        else {
+                            // start state of tile t: keep folding the zero-state tile ends (published by the
+                            // whole cluster in phase 0) with M_T from where the previous tile of this CTA stopped
+                            const M2 M = MT;
+                            for (; fold_pos < t; ++fold_pos) {
+                                const double ea = __ldcg(ends + 2 * fold_pos), eb = __ldcg(ends + 2 * fold_pos + 1);
+                                const double na = M.a * fold_a + M.b * fold_b + ea, nb = M.c * fold_a + M.d * fold_b + eb;
+                                fold_a = na; fold_b = nb;
+                            }
+                            carry[0] = fold_a; carry[1] = fold_b;
+                        }
                     }
-                    w1[warp] = a; w2[warp] = b;
-                }
-                __syncthreads();
-                if (tid == 0) {    // level 2: start state of every warp
-                    const M2 M = MW;
-                    double a = carry[0], b = carry[1];
-                    for (int w = 0; w < RVB_IIR_WARPS; ++w) {
-                        const double ea = w1[w], eb = w2[w];
-                        w1[w] = a; w2[w] = b;
-                        const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
-                        a = na; b = nb;
+                    for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
+                        const uint32_t i = t0 + k;
+                        float v = 0.0f;   // zero padding past the end never feeds a stored sample
+                        // L2 loads: other CTAs of the cluster stored these samples in the previous sweep
+                        if (i < n) v = dirn == 0 ? __ldcg(x + i) : __ldcg(x + (n - 1 - i));
+                        tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)] = v;
                     }
-                    carry[0] = a; carry[1] = b;
-                }
-                __syncthreads();
-                {                  // level 3: S_j = M^lane * (warp start) + local prefix
-                    const M2 P = pw[lane];
-                    const double a = w1[warp], b = w2[warp];
-                    z1 = P.a * a + P.b * b + e1[tid];
-                    z2 = P.c * a + P.d * b + e2[tid];
-                }
-                biquad_chunk<true>(q, mine, z1, z2);
-                __syncthreads();
-                for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
-                    const uint32_t i = t0 + k;
-                    if (i < n) {
-                        const float v = tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)];
-                        if (dirn == 0) x[i] = v; else x[n - 1 - i] = v;
+                    __syncthreads();
+                    double z1 = 0.0, z2 = 0.0;
+                    biquad_chunk<false>(q, mine, z1, z2);
+                    e1[tid] = z1; e2[tid] = z2;
+                    __syncwarp();
+                    if (lane == 0) {   // level 1: local prefixes of this warp's chunks, from a zero state
+                        const M2 M = pw[1];
+                        double a = 0.0, b = 0.0;
+                        for (int j = 0; j < 32; ++j) {
+                            const double ea = e1[tid + j], eb = e2[tid + j];
+                            e1[tid + j] = a; e2[tid + j] = b;
+                            const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
+                            a = na; b = nb;
+                        }
+                        w1[warp] = a; w2[warp] = b;
                     }
+                    __syncthreads();
+                    if (tid == 0) {    // level 2: start state of every warp
+                        const M2 M = MW;
+                        double a = carry[0], b = carry[1];
+                        for (int w = 0; w < RVB_IIR_WARPS; ++w) {
+                            const double ea = w1[w], eb = w2[w];
+                            w1[w] = a; w2[w] = b;
+                            const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
+                            a = na; b = nb;
+                        }
+                        if (phase == 0) { __stcg(ends + 2 * t, a); __stcg(ends + 2 * t + 1, b); }
+                    }
+                    __syncthreads();
+                    if (phase == 0) continue;
+                    {                  // level 3: S_j = M^lane * (warp start) + local prefix
+                        const M2 P = pw[lane];
+                        const double a = w1[warp], b = w2[warp];
+                        z1 = P.a * a + P.b * b + e1[tid];
+                        z2 = P.c * a + P.d * b + e2[tid];
+                    }
+                    biquad_chunk<true>(q, mine, z1, z2);
+                    __syncthreads();
+                    for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
+                        const uint32_t i = t0 + k;
+                        if (i < n) {
+                            const float v = tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)];
+                            if (dirn == 0) x[i] = v; else x[n - 1 - i] = v;
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
+                // phase 0 -> 1: the tile ends of the whole cluster must be visible; phase 1 -> next sweep: the
+                // next sweep reads samples the other CTAs stored
+                if (csize > 1) cluster_sync_all(); else __syncthreads();
             }
         }
     }
@@ -874,10 +936,32 @@ static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nc
     RVB_CUDA(cudaMemcpyAsync(d_len, len.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     const size_t iir_smem = (size_t)RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1) * sizeof(float);
     RVB_CUDA(cudaFuncSetAttribute(iir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iir_smem));
-    note_launch(), iir_kernel<<<(unsigned)nrows, RVB_IIR_THREADS, iir_smem, st>>>(d_data, d_off, d_len, d_f, ft == RVB_FILTER_BIQUAD_ONEPASS ? 1 : 2);
+    // cluster size: as many CTAs per row as the longest row has tiles, up to the portable maximum of 8
+    size_t max_len = 0;
+    for (size_t c = 0; c < nch; ++c) max_len = std::max(max_len, lengths[c]);
+    const uint32_t max_tiles = (uint32_t)std::max<size_t>(1, (max_len + RVB_IIR_TILE - 1) / RVB_IIR_TILE);
+    unsigned csize = 1;
+    while (csize < 8 && csize * 2 <= max_tiles) csize *= 2;
+    double *d_ends = nullptr;
+    RVB_TRY(dev_alloc(&d_ends, nrows * (size_t)max_tiles * 2));
+    {
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((unsigned)nrows * csize, 1, 1);
+        lc.blockDim = dim3(RVB_IIR_THREADS, 1, 1);
+        lc.dynamicSmemBytes = iir_smem;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        const int mode = ft == RVB_FILTER_BIQUAD_ONEPASS ? 1 : 2;
+        note_launch();
+        RVB_CUDA(cudaLaunchKernelEx(&lc, iir_kernel, d_data, (const uint32_t *)d_off, (const uint32_t *)d_len, (const RowFilter *)d_f, mode,
+                                    d_ends, max_tiles));
+    }
     RVB_CUDA(cudaGetLastError());
     RVB_CUDA(cudaStreamSynchronize(st));
-    dev_free(d_f); dev_free(d_off); dev_free(d_len);
+    dev_free(d_f); dev_free(d_off); dev_free(d_len); dev_free(d_ends);
     return RVB_OK;
 }
 

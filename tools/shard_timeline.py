@@ -11,17 +11,28 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local); api.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 api.set_stream(torch.cuda.current_stream().cuda_stream)
-tri, vtx, srf = scenes.shoebox()
-nrays = 1 << 20
-dirs = torch.from_numpy(scenes.sphere_directions(nrays * world, seed=2015)[rank * nrays:(rank + 1) * nrays].copy()).cuda()
-rt = api.Raytracer(128, tri, vtx, srf)
-kw = dict(speakers=[((0, 0, 1), 0.0)], sr=44100.0, ft="linkwitz_riley", lo_cutoff=45.0)
+sys.path.insert(0, ROOT)
+import bench
+wl_name = sys.argv[1] if len(sys.argv) > 1 else "C2_shoebox_12tri_1Mx128_omni"
+wl = bench.WORKLOADS[wl_name]
+tri, vtx, srf = bench.build_scene(wl["scene"])
+if wl["scaling"] == "weak":
+    nrays, lo = wl["rays"], rank * wl["rays"]
+    all_dirs = scenes.sphere_directions(nrays * world, seed=wl["seed"])
+else:
+    lo, hi = sharding.shard_slice(wl["rays"], rank, world)
+    nrays = hi - lo
+    all_dirs = scenes.sphere_directions(wl["rays"], seed=wl["seed"])
+dirs = torch.from_numpy(all_dirs[lo:lo + nrays].copy()).cuda()
+rt = api.Raytracer(wl["refl"], tri, vtx, srf)
+kw = bench.render_kwargs(wl)
 cfg, keep = api.make_render_config(**kw)
+MIC, SRC = wl["jobs"][0]
 def sync(): torch.cuda.synchronize()
 for it in range(6):
     dist.barrier(); sync(); T = [time.perf_counter()]
     def mark(): sync(); T.append(time.perf_counter())
-    tr = rt.raytrace((7, 2, 4), (2, 1.5, 2), None, ray_offset=rank * nrays, device_ptr=dirs.data_ptr(), nrays=nrays); mark()
+    tr = rt.raytrace(MIC, SRC, None, ray_offset=lo, device_ptr=dirs.data_ptr(), nrays=nrays); mark()
     mn, mx = tr.render_times(cfg); mark()
     img, keys, klen = tr.raw_images(with_keys=True); mark()
     predelay, gmx, counts = sharding.exchange_extrema(mn, mx, len(img), world, "cuda"); mark()
