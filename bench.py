@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--workload", default="C2_shoebox_12tri_1Mx128_omni", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=None, help="override the workload's ray count (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="multi-GPU: keep equal ray shards (no measured re-cut)")
     ap.add_argument("--accel", type=int, default=None, help="0 auto, 1 brute force, 2 BVH")
     args = ap.parse_args()
     wl_name = args.workload
@@ -237,15 +238,21 @@ def main():
         jobs = wl["jobs"][rank::world]
     sharded = world > 1 and scaling != "jobs"
     all_dirs = scenes.sphere_directions(total_rays, seed=wl["seed"])
+    shard = {}
+
+    def set_shard(lo_, hi_):
+        """(Re)bind this rank's contiguous ray slice: pinned host copy + device copy."""
+        shard["lo"], shard["hi"], shard["n"] = lo_, hi_, hi_ - lo_
+        shard["h"] = torch.from_numpy(all_dirs[lo_:hi_].copy()).pin_memory()
+        shard["d"] = shard["h"].to("cuda", non_blocking=False)
+
+    set_shard(lo, hi)
     nrays = hi - lo
-    h_dirs = torch.from_numpy(all_dirs[lo:hi].copy()).pin_memory()
-    d_dirs = h_dirs.to("cuda", non_blocking=False)
     accel = args.accel if args.accel is not None else wl.get("accel", 0)
     rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
     render_kw = render_kwargs(wl)
     cfg, keep = api.make_render_config(**render_kw)
     nch = 2 if "hrtf" in wl else len(wl["speakers"])
-    h2d_bytes = h_dirs.numel() * 4 * len(jobs)
     state = {"trace": [], "render": []}
 
     # C5: independent pairs are small problems (16 k rays); several host threads, each with its own
@@ -265,9 +272,9 @@ def main():
         api.set_stream(w["stream"].cuda_stream)
         for mic, src in my_jobs:
             if resident:
-                tr = w["rt"].raytrace(mic, src, None, ray_offset=lo, device_ptr=d_dirs.data_ptr(), nrays=nrays)
+                tr = w["rt"].raytrace(mic, src, None, ray_offset=shard["lo"], device_ptr=shard["d"].data_ptr(), nrays=shard["n"])
             else:
-                tr = w["rt"].raytrace(mic, src, h_dirs.numpy(), ray_offset=lo)
+                tr = w["rt"].raytrace(mic, src, shard["h"].numpy(), ray_offset=shard["lo"])
             st_t = tr.stats()
             ir = tr.render_ir(**render_kw)
             out.append((st_t, api.render_stats(), ir))
@@ -286,20 +293,25 @@ def main():
                     irs.append(ir)
             return irs
         for mic, src in jobs:
+            t_host = time.perf_counter()
             if resident:
-                tr = rt.raytrace(mic, src, None, ray_offset=lo, device_ptr=d_dirs.data_ptr(), nrays=nrays)
+                tr = rt.raytrace(mic, src, None, ray_offset=shard["lo"], device_ptr=shard["d"].data_ptr(), nrays=shard["n"])
             else:
-                tr = rt.raytrace(mic, src, h_dirs.numpy(), ray_offset=lo)
+                tr = rt.raytrace(mic, src, shard["h"].numpy(), ray_offset=shard["lo"])
             state["trace"].append(tr.stats())
+            timing = {"local_ms": 1e3 * (time.perf_counter() - t_host)}
             if not sharded:
                 irs.append(tr.render_ir(**render_kw))
                 state["render"].append(api.render_stats())
                 continue
             # sharded: global predelay/lengths, cross-shard image merge, ONE NCCL reduce of the histogram
-            hist, lengths, _ = sharding.sharded_histogram(tr, cfg, rank, world, "cuda", SR, False)
+            hist, lengths, _ = sharding.sharded_histogram(tr, cfg, rank, world, "cuda", SR, False, timing)
             state["render"].append(api.render_stats())
             if rank == 0:
+                t_host = time.perf_counter()
                 irs.append(api.render_finish(cfg, hist.data_ptr(), lengths))
+                timing["exclusive_ms"] = timing.get("exclusive_ms", 0.0) + 1e3 * (time.perf_counter() - t_host)
+            state["timing"] = timing
         return irs
 
     def timed(resident, steps):
@@ -325,8 +337,27 @@ def main():
             ms = float(t.item())
         return ms, api.launch_count() - launches0, d2h
 
-    for _ in range(max(args.warmup, 3)):
+    # Warm-up; on a sharded run the first warm-up step also MEASURES the ranks: rank 0 merges the image
+    # sources and filters the summed histogram on top of its share of the rays, so the contiguous ray
+    # slices are re-cut once so that every rank finishes at the same time (sharding.balance_weights).
+    balance = None
+    for w_it in range(max(args.warmup, 3)):
         step(True)
+        # (only with several waves of rays per GPU: with ~1 wave the bounce kernels' time is a step
+        # function of the ray count and the linear model behind the re-cut does not hold -- measured
+        # on C3 at 8 GPUs, 131 k rays per GPU: 20.5 ms re-cut vs 19.2 ms equal shards)
+        if sharded and w_it == 1 and not args.no_balance and shard["n"] >= (1 << 19):
+            tm = state.get("timing", {})
+            mine = torch.tensor([tm.get("local_ms", 0.0), tm.get("exclusive_ms", 0.0), float(shard["n"])], device="cuda", dtype=torch.float64)
+            allm = torch.empty((world, 3), device="cuda", dtype=torch.float64)
+            dist.all_gather_into_tensor(allm, mine.unsqueeze(0))
+            allm = allm.cpu().numpy()
+            ms_per_ray = float(allm[:, 0].sum() / max(1.0, allm[:, 2].sum()))
+            weights = sharding.balance_weights(ms_per_ray, allm[:, 1], total_rays)
+            cuts = sharding.shard_bounds(total_rays, world, weights)
+            set_shard(cuts[rank], cuts[rank + 1])
+            balance = {"rank0_share": (cuts[1] - cuts[0]) / total_rays, "equal_share": 1.0 / world,
+                       "measured_exclusive_ms_rank0": float(allm[0, 1]), "measured_ms_per_kiloray": 1e3 * ms_per_ray}
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches, _ = timed(True, args.steps)
@@ -335,6 +366,8 @@ def main():
     step(False)  # warm the host-buffer path (pinned H2D)
     e2e_ms, _, d2h_bytes = timed(False, args.steps)
     clocks = sampler.stop()
+    nrays = shard["n"]   # after the shard re-cut
+    h2d_bytes = shard["h"].numel() * 4 * len(jobs)
 
     if rank == 0:
         hbm_gbs, sm_max_mhz, peak_src = load_peaks()
@@ -367,6 +400,7 @@ def main():
                        "attenuation": "hrtf" if "hrtf" in wl else "speakers", "filter": "linkwitz_riley",
                        "accel": "brute_force_smem" if brute else "bvh",
                        "sharding": ("pairs/%d" % world if scaling == "jobs" else "rays/%d" % world) if world > 1 else "none",
+                       "shard_balance": balance,
                        "l2": "inputs_larger_than_L2 (per-step working set %.2f GB per GPU)" % (nrays * nrefl * 52 / 1e9)},
             "e2e": {"value": total_rb / (e2e_ms * 1e-3), "unit": "rays*bounces/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},

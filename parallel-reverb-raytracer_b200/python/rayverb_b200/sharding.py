@@ -15,6 +15,7 @@ slice of the direction set against its own replica of the scene.  What couples t
 GPU; the CPU tests plug in an oracle-backed stand-in to check this logic under gloo).
 """
 import math
+import time
 
 import numpy as np
 import torch
@@ -33,9 +34,41 @@ def flatten_length(maxtime, predelay, fix, sr):
     return int(math.floor(float(np.float32(t * np.float32(sr))) + 0.5)) + 1
 
 
-def shard_slice(nrays_total, rank, world):
-    """Contiguous ray range [g*n/N, (g+1)*n/N) of rank g."""
-    return (nrays_total * rank) // world, (nrays_total * (rank + 1)) // world
+def shard_bounds(nrays_total, world, weights=None):
+    """Cut points b_0 = 0 <= b_1 <= ... <= b_world = n of the contiguous ray ranges.  Equal shares by
+    default; `weights` gives relative shard sizes (see balance_weights)."""
+    if weights is None:
+        return [(nrays_total * r) // world for r in range(world + 1)]
+    w = np.maximum(np.asarray(weights, dtype=np.float64), 0.0)
+    if len(w) != world or not np.isfinite(w).all() or w.sum() <= 0:
+        raise ValueError("weights must be one finite non-negative number per rank, not all zero")
+    cum = np.concatenate([[0.0], np.cumsum(w)]) / w.sum()
+    b = [int(round(c * nrays_total)) for c in cum]
+    b[0], b[-1] = 0, nrays_total
+    for i in range(1, world + 1):   # monotone
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
+def shard_slice(nrays_total, rank, world, weights=None):
+    """Contiguous ray range of rank g: [g*n/N, (g+1)*n/N) by default (contiguous slices keep
+    "lowest ray wins" == "lowest rank wins" for the image-source merge)."""
+    b = shard_bounds(nrays_total, world, weights)
+    return b[rank], b[rank + 1]
+
+
+def balance_weights(ms_per_ray, extra_ms, nrays_total):
+    """Shard weights that equalise the finish time of the ranks when rank r carries a fixed extra cost
+    extra_ms[r] on top of a common per-ray cost (rank 0 merges the image sources and filters the summed
+    histogram, so it should trace fewer rays): solve c*n_r + x_r = T with sum n_r = N."""
+    x = np.asarray(extra_ms, dtype=np.float64)
+    world = len(x)
+    c = float(ms_per_ray)
+    if c <= 0:
+        return [1.0] * world
+    T = (c * nrays_total + x.sum()) / world
+    n = np.maximum((T - x) / c, 0.0)
+    return [float(v) for v in n]
 
 
 def _fold_predelay(gmn):
@@ -68,7 +101,7 @@ def exchange_extrema(mn, mx, n_images, world, device):
 _REC = 64 + 4 * NUM_IMAGE_SOURCE + 4   # Impulse + key[10] + key length, bytes per image source
 
 
-def merge_images(img, keys, klen, counts, rank, world, device):
+def merge_images(img, keys, klen, counts, rank, world, device, timing=None):
     """Gather the per-shard unique image-source lists (one tensor collective over the padded
     records; `counts` came with exchange_extrema); rank 0 returns the global list (first occurrence
     in rank order wins), the others an empty one."""
@@ -88,24 +121,35 @@ def merge_images(img, keys, klen, counts, rank, world, device):
     else:
         dist.gather(local.unsqueeze(0), None, dst=0)
         return np.zeros(0, dtype=IMPULSE)
+    t_excl = time.perf_counter()
     g = gathered.cpu().numpy()
     allrec = np.ascontiguousarray(np.concatenate([g[r, :counts[r]] for r in range(world)]))
     gi = np.ascontiguousarray(allrec[:, :64]).view(IMPULSE).reshape(-1)
     gk = np.ascontiguousarray(allrec[:, 64:64 + 4 * NUM_IMAGE_SOURCE]).view(np.uint32).reshape(-1, NUM_IMAGE_SOURCE)
     gl = np.ascontiguousarray(allrec[:, 64 + 4 * NUM_IMAGE_SOURCE:]).view(np.int32).reshape(-1)
     merged, _, _ = api.images_merge(gi, gk, gl)
+    if timing is not None:
+        timing["exclusive_ms"] = timing.get("exclusive_ms", 0.0) + 1e3 * (time.perf_counter() - t_excl)
     return merged
 
 
-def sharded_histogram(shard, cfg, rank, world, device, sr, trim_predelay):
+def sharded_histogram(shard, cfg, rank, world, device, sr, trim_predelay, timing=None):
     """Stages 2-3 of the hot path on one shard + the collectives.  Returns (hist tensor on
-    `device`, summed on rank 0; lengths; predelay)."""
+    `device`, summed on rank 0; lengths; predelay).  `timing` (a dict) receives host wall-clock
+    milliseconds: "local_ms" for the work every rank does on its own shard, "exclusive_ms" for what
+    only this rank does (rank 0: the image-source merge) -- the inputs of balance_weights."""
+    t0 = time.perf_counter()
     mn, mx = shard.render_times(cfg)
     img, keys, klen = shard.raw_images(with_keys=True)
+    t1 = time.perf_counter()
     predelay, gmx, counts = exchange_extrema(mn, mx, len(img), world, device)
     lengths = [flatten_length(m, predelay, trim_predelay, sr) for m in gmx]
-    shard.set_images(merge_images(img, keys, klen, counts, rank, world, device))
+    shard.set_images(merge_images(img, keys, klen, counts, rank, world, device, timing))
     hist = torch.empty(sum(NBANDS * l for l in lengths), device=device, dtype=torch.float32)   # render_histogram zero-fills
+    t2 = time.perf_counter()
     shard.render_histogram(cfg, predelay, lengths, hist.data_ptr())
+    t3 = time.perf_counter()
     dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
+    if timing is not None:
+        timing["local_ms"] = timing.get("local_ms", 0.0) + 1e3 * ((t1 - t0) + (t3 - t2))
     return hist, lengths, predelay

@@ -7,6 +7,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -128,6 +129,60 @@ def test_shard_slices_cover_all_rays():
             cuts = [sharding.shard_slice(n, r, w) for r in range(w)]
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+
+
+def test_weighted_shards_cover_all_rays_and_balance():
+    """Uneven contiguous shards (rank 0 also merges + filters, so it traces fewer rays): the cut
+    points still tile [0, n) and the balance model equalises c * n_r + x_r."""
+    for n in (1, 1000, 1 << 20):
+        for w in ([1, 1], [0.5, 1, 1, 1], [0, 3, 1], [1e-9, 1]):
+            b = sharding.shard_bounds(n, len(w), w)
+            assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(len(w)))
+    c, extra, n = 1.25e-4, [1.6, 0, 0, 0, 0, 0, 0, 0], 1 << 20
+    wts = sharding.balance_weights(c, extra, n)
+    b = sharding.shard_bounds(n, 8, wts)
+    finish = [c * (b[r + 1] - b[r]) + extra[r] for r in range(8)]
+    assert max(finish) - min(finish) < 2 * c                      # within a ray or two of each other
+    assert b[1] - b[0] < n // 8 < b[2] - b[1]                      # rank 0 got the smaller shard
+    assert sharding.balance_weights(0.0, extra, n) == [1.0] * 8   # degenerate measurement: equal shares
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(10, 2, [0, 0])
+
+
+def _uneven_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    tri, vtx, srf = scenes.shoebox()
+    dirs = scenes.sphere_directions(NRAYS, seed=77)
+    b, e = sharding.shard_slice(NRAYS, rank, world, [0.3, 1.0])
+    shard = OracleShard(orc, tri, vtx, srf, dirs[b:e])
+    timing = {}
+    hist, lengths, predelay = sharding.sharded_histogram(shard, {"trim_predelay": False}, rank, world, "cpu", SR, False, timing)
+    assert timing["local_ms"] > 0 and (rank != 0 or timing["exclusive_ms"] > 0)
+    if rank == 0:
+        q.put((hist.numpy().copy(), lengths, len(shard.images)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_uneven_shards_equal_even_shards(orc):
+    """The sharded result does not depend on WHERE the contiguous cut is."""
+    ctx = mp.get_context("spawn")
+    outs = []
+    for target, args in ((_uneven_worker, ()), (_worker, (False,))):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, 2, port) + args + (q,)) for r in range(2)]
+        for p in procs:
+            p.start()
+        outs.append(q.get(timeout=120))
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    (h_a, len_a, n_a), (h_b, len_b, _, n_b) = outs[0], outs[1]
+    assert len_a == len_b and n_a == n_b
+    assert np.linalg.norm(h_a - h_b) <= 1e-6 * np.linalg.norm(h_b)
 
 
 def test_flatten_length_rounds_half_away_from_zero():
