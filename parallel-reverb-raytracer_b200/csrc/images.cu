@@ -42,6 +42,25 @@ __global__ void col_keys_kernel(const uint32_t *idx, const uint32_t *sel, const 
     if (p < n) keys[p] = key_col(idx, sel[perm[p]], j);
 }
 
+// all key columns 1..last_col packed into one 64-bit sort key, column 1 most significant
+__global__ void packed_keys_kernel(const uint32_t *idx, const uint32_t *sel, uint32_t n, uint32_t last_col, uint32_t bits,
+                                   unsigned long long *keys, uint32_t *perm)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t flat = sel[p];
+    unsigned long long k = 0;
+    for (uint32_t j = 1; j <= last_col; ++j) k = (k << bits) | key_col(idx, flat, j);
+    keys[p] = k;
+    perm[p] = p;
+}
+
+__global__ void head_flags_packed_kernel(const unsigned long long *keys, uint32_t n, uint8_t *head)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) head[p] = (p == 0 || keys[p] != keys[p - 1]) ? 1 : 0;
+}
+
 __global__ void iota_kernel(uint32_t *a, uint32_t n)
 {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,26 +120,44 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     uint32_t *d_perm[2] = {nullptr, nullptr}, *d_keys[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_perm[i], n)); RVB_TRY(dev_alloc(&d_keys[i], n)); }
     const unsigned blk = 256, grd = (n + blk - 1) / blk;
-    note_launch(), iota_kernel<<<grd, blk, 0, st>>>(d_perm[0], n);
     int end_bit = 1;
     while ((1ull << end_bit) < (unsigned long long)tr->scene->T + 2ull) ++end_bit;
-    size_t sort_bytes = 0;
-    RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys[0], d_keys[1], d_perm[0], d_perm[1], (int)n, 0, end_bit, st));
-    uint8_t *d_sort_tmp = nullptr;
-    RVB_TRY(dev_alloc(&d_sort_tmp, sort_bytes));
     int cur = 0;
     const uint32_t last_col = (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl);
-    for (uint32_t j = last_col; j >= 1; --j) {   // LSD over key columns; column 0 is constant
-        note_launch(), col_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, j, d_keys[0]);
-        RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_bytes, d_keys[0], d_keys[1], d_perm[cur], d_perm[cur ^ 1],
-                                                 (int)n, 0, end_bit, st));
-        cur ^= 1;
-    }
-    dev_free(d_sort_tmp);
-
     uint8_t *d_head = nullptr;
     RVB_TRY(dev_alloc(&d_head, n));
-    note_launch(), head_flags_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, d_head);
+    if ((uint32_t)end_bit * last_col <= 64u) {
+        // small scenes: every key fits one 64-bit word -> ONE radix sort instead of one per column
+        // (stable, so the lowest ray still comes first within equal keys)
+        unsigned long long *d_k64[2] = {nullptr, nullptr};
+        for (int i = 0; i < 2; ++i) RVB_TRY(dev_alloc(&d_k64[i], n));
+        note_launch(), packed_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, n, last_col, (uint32_t)end_bit, d_k64[0], d_perm[0]);
+        cub::DoubleBuffer<unsigned long long> kb(d_k64[0], d_k64[1]);
+        cub::DoubleBuffer<uint32_t> vb(d_perm[0], d_perm[1]);
+        size_t sort_bytes = 0;
+        RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb, vb, (int)n, 0, end_bit * (int)last_col, st));
+        uint8_t *d_sort_tmp = nullptr;
+        RVB_TRY(dev_alloc(&d_sort_tmp, sort_bytes));
+        RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_bytes, kb, vb, (int)n, 0, end_bit * (int)last_col, st));
+        cur = vb.selector;
+        note_launch(), head_flags_packed_kernel<<<grd, blk, 0, st>>>(kb.Current(), n, d_head);
+        dev_free(d_sort_tmp);
+        for (int i = 0; i < 2; ++i) dev_free(d_k64[i]);
+    } else {
+        note_launch(), iota_kernel<<<grd, blk, 0, st>>>(d_perm[0], n);
+        size_t sort_bytes = 0;
+        RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys[0], d_keys[1], d_perm[0], d_perm[1], (int)n, 0, end_bit, st));
+        uint8_t *d_sort_tmp = nullptr;
+        RVB_TRY(dev_alloc(&d_sort_tmp, sort_bytes));
+        for (uint32_t j = last_col; j >= 1; --j) {   // LSD over key columns; column 0 is constant
+            note_launch(), col_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, j, d_keys[0]);
+            RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_bytes, d_keys[0], d_keys[1], d_perm[cur], d_perm[cur ^ 1],
+                                                     (int)n, 0, end_bit, st));
+            cur ^= 1;
+        }
+        dev_free(d_sort_tmp);
+        note_launch(), head_flags_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, d_head);
+    }
     uint32_t *d_upos = d_keys[0], *d_m = d_nsel;
     size_t fl_bytes = 0;
     RVB_CUDA(cub::DeviceSelect::Flagged(nullptr, fl_bytes, it, d_head, d_upos, d_m, (int)n, st));
