@@ -106,9 +106,33 @@ __global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bo
                             uint32_t *vals)
 {
     const uint32_t n = S.size();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // Diffuse slots of the speaker / pass-through models need the 4-byte time only: four slots per
+    // thread, 16-byte loads and stores (the slot count is a multiple of four, rvb_internal.cuh).
+    uint32_t first_scalar = 0;
+    if (C.model != 1 && (S.n_diffuse & 3u) == 0) {
+        first_scalar = S.n_diffuse;
+        const uint32_t nq = S.n_diffuse >> 2;
+        const float4 *t4 = reinterpret_cast<const float4 *>(S.tkey);
+        uint4 *k4 = reinterpret_cast<uint4 *>(keys), *v4 = reinterpret_cast<uint4 *>(vals);
+        for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+            const float4 t = t4[q];
+            const float tt[4] = {t.x, t.y, t.z, t.w};
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                k[u] = L;   // sentinel: sorts behind every real bin
+                if (tt[u] >= 0.0f) {
+                    const uint32_t s = sample_index(tt[u], predelay, fix, sr);
+                    if (s < L) k[u] = s;
+                }
+            }
+            k4[q] = make_uint4(k[0], k[1], k[2], k[3]);
+            v4[q] = make_uint4(4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3);
+        }
+    }
+    for (uint32_t i = first_scalar + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float t;
-        uint32_t k = L;   // sentinel: sorts behind every real bin
+        uint32_t k = L;
         if (attenuated_time(S, C, i, t)) {
             uint32_t s = sample_index(t, predelay, fix, sr);
             if (s < L) k = s;
@@ -120,14 +144,26 @@ __global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bo
 
 // The sort may ignore the low `shift` bits of the sample index (one radix pass fewer): a segment
 // then holds 2^shift adjacent bins, interleaved in impulse order, and the reduction separates them
-// by the key's low bits.  Segment bounds in the sorted key array:
+// by the key's low bits.  Segment bounds in the sorted key array (four keys per thread, 16-byte loads):
 __global__ void bounds_kernel(const uint32_t *keys, uint32_t n, uint32_t nseg, uint32_t shift, uint32_t *seg_begin, uint32_t *seg_end)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t sg = keys[i] >> shift;
-        if (sg >= nseg) continue;   // sentinel-only tail
-        if (i == 0 || (keys[i - 1] >> shift) != sg) seg_begin[sg] = i;
-        if (i + 1 == n || (keys[i + 1] >> shift) != sg) seg_end[sg] = i + 1;
+    const uint32_t nq = (n + 3) >> 2;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const uint32_t i0 = 4 * q;
+        uint32_t k[6];   // keys i0-1 .. i0+4
+        if (i0 + 4 <= n) { const uint4 v = reinterpret_cast<const uint4 *>(keys)[q]; k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w; }
+        else for (int u = 0; u < 4; ++u) k[1 + u] = i0 + u < n ? keys[i0 + u] : 0u;
+        k[0] = i0 ? keys[i0 - 1] : 0u;
+        k[5] = i0 + 4 < n ? keys[i0 + 4] : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u;
+            if (i >= n) break;
+            const uint32_t sg = k[1 + u] >> shift;
+            if (sg >= nseg) continue;   // sentinel-only tail
+            if (i == 0 || (k[u] >> shift) != sg) seg_begin[sg] = i;
+            if (i + 1 == n || (k[2 + u] >> shift) != sg) seg_end[sg] = i + 1;
+        }
     }
 }
 
