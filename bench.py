@@ -261,7 +261,7 @@ def main():
     workers = []
     if scaling == "jobs" and len(jobs) > 1:
         from concurrent.futures import ThreadPoolExecutor
-        nworkers = min(4, len(jobs))
+        nworkers = min(int(os.environ.get("RVB_BENCH_WORKERS", "4")), len(jobs))
         pool = ThreadPoolExecutor(max_workers=nworkers)
         workers = [dict(stream=torch.cuda.Stream(), rt=api.Raytracer(nrefl, tri, vtx, srf, accel=accel)) for _ in range(nworkers)]
 

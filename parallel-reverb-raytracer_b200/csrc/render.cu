@@ -597,6 +597,13 @@ __global__ void mixdown_kernel(const float *bands, uint32_t L, float *out, int *
     if ((threadIdx.x & 31) == 0) atomicMax(maxabs_bits, __float_as_int(m));   // m >= 0 (or NaN > inf bits: propagates)
 }
 
+// normalize (generic_functions.h:56-60): x * (float)(1.0 / max|x|), the maximum read on the device
+__global__ void normalize_kernel(float *x, uint32_t L, const int *maxabs_bits)
+{
+    const float f = (float)(1.0 / (double)__int_as_float(*maxabs_bits));
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) x[k] = __fmul_rn(x[k], f);
+}
+
 __global__ void scale_kernel(float *x, uint32_t L, float f)
 {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) x[k] = __fmul_rn(x[k], f);
@@ -636,13 +643,26 @@ __global__ void ear_kernel(f3 pointing, f3 up, f3 mic, float4 *out)
 
 static thread_local rvb_render_stats g_stats;
 
+// Stage timings without host synchronisation inside the pipeline: a lap records two events on the
+// stream and is resolved (cudaEventElapsedTime) once the caller has synchronised anyway.
+struct Lap { cudaEvent_t a, b; float *acc; };
+static thread_local std::vector<Lap> g_laps;
 struct Timer {
     cudaEvent_t a, b;
     cudaStream_t st;
     explicit Timer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
-    float stop() { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
-    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    // accumulate this lap into *acc when the laps are resolved
+    void stop_into(float *acc) { cudaEventRecord(b, st); g_laps.push_back(Lap{a, b, acc}); }
 };
+static void resolve_laps()
+{
+    for (const Lap &l : g_laps) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(l.b) == cudaSuccess && cudaEventElapsedTime(&ms, l.a, l.b) == cudaSuccess) *l.acc += ms;
+        cudaEventDestroy(l.a); cudaEventDestroy(l.b);
+    }
+    g_laps.clear();
+}
 
 static int grid_for(size_t n, int block = 256)
 {
@@ -782,7 +802,7 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             L = (uint32_t)lengths[c0];
             Timer tk(st);
             note_launch(), keys_kernel<<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, d_keys[0], d_vals[0]);
-            g_stats.keys_ms += tk.stop();
+            tk.stop_into(&g_stats.keys_ms);
             Timer ts(st);
             int end_bit = 1;
             while ((1ull << end_bit) <= (unsigned long long)L) ++end_bit;   // keys in [0, L]
@@ -805,7 +825,7 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             RVB_CUDA(cudaMemsetAsync(d_begin, 0, (size_t)nseg * sizeof(uint32_t), st));
             RVB_CUDA(cudaMemsetAsync(d_end, 0, (size_t)nseg * sizeof(uint32_t), st));
             note_launch(), bounds_kernel<<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, nseg, (uint32_t)shift, d_begin, d_end);
-            g_stats.sort_ms += ts.stop();
+            ts.stop_into(&g_stats.sort_ms);
         }
         Timer tr_(st);
         const size_t stride = RVB_NBANDS * (size_t)L;
@@ -824,7 +844,7 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             else launch_reduce<2, false>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
         }
         RVB_CUDA(cudaGetLastError());
-        g_stats.reduce_ms += tr_.stop();
+        tr_.stop_into(&g_stats.reduce_ms);
     }
     for (int i = 0; i < 2; ++i) { dev_free(d_keys[i]); dev_free(d_vals[i]); }
     dev_free(d_begin); dev_free(d_end); dev_free(d_tmp);
@@ -996,7 +1016,8 @@ static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nc
                                     d_ends, max_tiles));
     }
     RVB_CUDA(cudaGetLastError());
-    RVB_CUDA(cudaStreamSynchronize(st));
+    // no synchronisation here: the small blocks are freed in stream order and every caller ends
+    // with a device -> host copy + synchronise of its own
     dev_free(d_f); dev_free(d_off); dev_free(d_len); dev_free(d_ends);
     return RVB_OK;
 }
@@ -1014,7 +1035,7 @@ static int finish_device(const rvb_render_config *cfg, float *d_hist /* modified
         float *d_out = nullptr;
         RVB_TRY(dev_alloc(&d_out, nch * RVB_NBANDS * fft_len));
         int rc = sinc_device(d_hist, lengths, nch, cfg->sample_rate, cfg->lo_cutoff, d_out, fft_len);
-        g_stats.filter_ms += tf.stop();
+        tf.stop_into(&g_stats.filter_ms);
         if (rc == RVB_OK) {
             std::vector<size_t> grown(nch, fft_len);
             rc = finish_filtered(cfg, d_out, grown.data(), nch, ir, keep_bands);
@@ -1023,7 +1044,7 @@ static int finish_device(const rvb_render_config *cfg, float *d_hist /* modified
         return rc;
     }
     RVB_TRY(filter_device(cfg->filter_type, d_hist, lengths, nch, cfg->sample_rate, cfg->lo_cutoff));
-    g_stats.filter_ms += tf.stop();
+    tf.stop_into(&g_stats.filter_ms);
     return finish_filtered(cfg, d_hist, lengths, nch, ir, keep_bands);
 }
 
@@ -1043,34 +1064,26 @@ static int finish_filtered(const rvb_render_config *cfg, float *d_hist, const si
         if (lengths[c]) note_launch(), mixdown_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_hist + ho, (uint32_t)lengths[c], d_mix + mo, d_red);
         ho += RVB_NBANDS * lengths[c]; mo += lengths[c];
     }
-    int h_red[2];
-    RVB_CUDA(cudaMemcpyAsync(h_red, d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
-    RVB_CUDA(cudaStreamSynchronize(st));
-    if (cfg->do_normalize) {   // normalize: mul(ret, 1.0 / max_amp(ret)), generic_functions.h:56-60
-        float m; memcpy(&m, &h_red[0], 4);
-        const float f = (float)(1.0 / (double)m);
-        if (total) note_launch(), scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, f);
-    }
+    // no host round trips until the very end: the normalisation factor is read on the device and
+    // the channels are copied out whole, then trimmed on the host
+    if (cfg->do_normalize && total) note_launch(), normalize_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, d_red);
     if (cfg->volume_scale != 1) { if (total) note_launch(), scale_kernel<<<grid_for(total), 256, 0, st>>>(d_mix, (uint32_t)total, cfg->volume_scale); }
-    long trimmed = -1;
     if (cfg->do_trim_tail) {
         mo = 0;
         for (size_t c = 0; c < nch; ++c) {
             if (lengths[c]) note_launch(), last_loud_kernel<<<grid_for(lengths[c]), 256, 0, st>>>(d_mix + mo, (uint32_t)lengths[c], 0.00001f, d_red + 1);
             mo += lengths[c];
         }
-        RVB_CUDA(cudaMemcpyAsync(h_red, d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
-        RVB_CUDA(cudaStreamSynchronize(st));
-        trimmed = std::max(0, h_red[1]);   // accumulate(..., 0, max(current, index)) -- the loud sample itself is dropped (Q12)
     }
+    int h_red[2] = {0, -1};
+    RVB_CUDA(cudaMemcpyAsync(h_red, d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
     ir->channels.assign(nch, {});
     ir->bands.assign(nch, {});
     ir->band_len.assign(nch, 0);
     mo = 0; ho = 0;
     for (size_t c = 0; c < nch; ++c) {
-        const size_t keep = trimmed >= 0 ? std::min<size_t>((size_t)trimmed, lengths[c]) : lengths[c];
-        ir->channels[c].assign(trimmed >= 0 ? (size_t)trimmed : lengths[c], 0.0f);   // vector::resize zero-extends short channels
-        if (keep) RVB_CUDA(cudaMemcpyAsync(ir->channels[c].data(), d_mix + mo, keep * sizeof(float), cudaMemcpyDeviceToHost, st));
+        ir->channels[c].resize(lengths[c]);
+        if (lengths[c]) RVB_CUDA(cudaMemcpyAsync(ir->channels[c].data(), d_mix + mo, lengths[c] * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (keep_bands) {
             ir->bands[c].resize(RVB_NBANDS * lengths[c]);
             ir->band_len[c] = lengths[c];
@@ -1079,8 +1092,14 @@ static int finish_filtered(const rvb_render_config *cfg, float *d_hist, const si
         mo += lengths[c]; ho += RVB_NBANDS * lengths[c];
     }
     RVB_CUDA(cudaStreamSynchronize(st));
+    if (cfg->do_trim_tail) {
+        // accumulate(..., 0, max(current, index)) -- the loud sample itself is dropped (Q12);
+        // vector::resize zero-extends channels shorter than the trimmed length
+        const size_t trimmed = (size_t)std::max(0, h_red[1]);
+        for (size_t c = 0; c < nch; ++c) ir->channels[c].resize(trimmed, 0.0f);
+    }
     dev_free(d_mix); dev_free(d_red);
-    g_stats.finish_ms += tm.stop();
+    tm.stop_into(&g_stats.finish_ms);
     return RVB_OK;
 }
 
@@ -1108,6 +1127,7 @@ int rvb_render_keep_bands(int on)
 int rvb_render_get_stats(rvb_render_stats *stats)
 {
     if (!stats) return fail(RVB_ERR_INVALID, "null argument");
+    resolve_laps();
     *stats = g_stats;
     return RVB_OK;
 }
@@ -1137,6 +1157,7 @@ int rvb_render_histogram(rvb_trace *tr, const rvb_render_config *cfg, float pred
 {
     if (!tr || !cfg || !lengths || !d_hist) return fail(RVB_ERR_INVALID, "null argument");
     RVB_CUDA(cudaSetDevice(tr->scene->device));
+    resolve_laps();   // laps of an earlier call that nobody asked about
     g_stats = rvb_render_stats{};
     Timer tt(lib_stream());
     Source S;
@@ -1145,7 +1166,9 @@ int rvb_render_histogram(rvb_trace *tr, const rvb_render_config *cfg, float pred
     RVB_TRY(make_channels(tr->mic, cfg, cs));
     g_stats.n_impulses = (uint64_t)S.n_diffuse + S.n_images;
     RVB_TRY(histogram_passes(S, cs, predelay, cfg->trim_predelay != 0, cfg->sample_rate, lengths, d_hist));
-    g_stats.total_ms = tt.stop();
+    tt.stop_into(&g_stats.total_ms);
+    RVB_CUDA(cudaStreamSynchronize(lib_stream()));
+    resolve_laps();
     return RVB_OK;
 }
 
@@ -1164,6 +1187,7 @@ int rvb_render_finish(const rvb_render_config *cfg, const float *d_hist, const s
     int rc = finish_device(cfg, d_work, lengths, nchannels, ir, g_keep_bands);
     dev_free(d_work);
     if (rc) { delete ir; return rc; }
+    resolve_laps();
     *out = ir;
     return RVB_OK;
 }
@@ -1174,6 +1198,7 @@ int rvb_render_ir(rvb_trace *tr, const rvb_render_config *cfg, rvb_ir **out)
     *out = nullptr;
     RVB_CUDA(cudaSetDevice(tr->scene->device));
     cudaStream_t st = lib_stream();
+    resolve_laps();   // laps of an earlier call that nobody asked about
     g_stats = rvb_render_stats{};
     StageTimer t_all("render.total");
     Timer tt(st);
@@ -1218,7 +1243,8 @@ int rvb_render_ir(rvb_trace *tr, const rvb_render_config *cfg, rvb_ir **out)
     }
     dev_free(d_hist);
     if (rc) { delete ir; return rc; }
-    g_stats.total_ms = tt.stop();
+    tt.stop_into(&g_stats.total_ms);
+    resolve_laps();   // finish_device ended with a stream synchronisation
     *out = ir;
     return RVB_OK;
 }
@@ -1258,6 +1284,7 @@ int rvb_flatten(const rvb_attenuated_impulse *in, size_t n, float sample_rate, f
     RVB_TRY(ensure_device());
     if (n >= 0xffffffffull) return fail(RVB_ERR_UNSUPPORTED, "too many impulses");
     cudaStream_t st = lib_stream();
+    resolve_laps();   // laps of an earlier call that nobody asked about
     g_stats = rvb_render_stats{};
     rvb_attenuated_impulse *d_in = nullptr;
     float4 *vA = nullptr, *pt = nullptr; float *tk = nullptr;
