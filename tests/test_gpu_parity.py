@@ -238,6 +238,20 @@ def test_host_array_postprocessing_vs_oracle(orc):
         assert_filter_close(a, b, "process")
 
 
+@pytest.mark.parametrize("length", [16384, 16385, 40000, 131072, 300001])
+def test_band_filters_across_tiles_and_cluster_sizes(orc, length):
+    """The IIR kernel deals 16384-sample tiles to a thread-block cluster of 1, 2, 4 or 8 CTAs per
+    row; lengths around the tile edges and up to 19 tiles, two channels of different content, against
+    the serial reference filter (Biquad / twopass / LinkwitzRiley, filters.cpp:156-266)."""
+    rng = np.random.default_rng(length)
+    x = (rng.standard_normal((2, 8, length)) * np.exp(-np.linspace(0, 8, length))[None, None, :]).astype(np.float32)
+    x[1, :, ::7] = 0.0
+    for ft in ("onepass", "twopass", "linkwitz_riley"):
+        g = api.filter_bands(ft, x, 44100.0, 45.0)
+        for c in range(2):
+            assert_filter_close(g[c], orc.filter_channel(ft, x[c], 44100.0, 45.0), (ft, length, c))
+
+
 # ---- BVH path: must equal the brute-force loop (kernel.cpp:167-192) including its tie-break -----
 def test_bvh_small_room_vs_oracle(orc):
     tri, vtx = scenes.displaced_box(8.0, 3.0, 5.0, 700, amp=0.08, fan=0.2, nsurfaces=4)

@@ -1,0 +1,6 @@
+#!/bin/bash
+# builds the sm_100a microbenchmarks next to their sources (run them on the B200 with gpurun)
+cd "$(dirname "$0")"
+for f in ffma2_bench ffma2_bench2 gather_bench; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o $f.bin $f.cu || exit 1
+done
