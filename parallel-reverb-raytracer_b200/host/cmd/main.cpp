@@ -151,6 +151,12 @@ int main (int argc, const char * argv [])
     {
         Raytracer raytracer (numImpulses, model_filename, material_filename, show_diagnostics);
         raytracer.raytrace (mic, source, directions, show_diagnostics);
+        // cmd/main.cpp:271-278 of the reference (compiled in with -DDIAGNOSTIC there)
+        bool dump_rays = getenv ("RAYVERB_DIAGNOSTIC") && string (getenv ("RAYVERB_DIAGNOSTIC")) == "1";
+#ifdef DIAGNOSTIC
+        dump_rays = true;
+#endif
+        if (dump_rays) print_diagnostic (numRays, numImpulses, raytracer.getRawDiffuse().impulses, "impulse.dump");
         processed = raytracer.renderImpulseResponse
         (   attenuationModel
         ,   output_mode

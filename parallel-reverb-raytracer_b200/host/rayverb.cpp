@@ -3,7 +3,9 @@
 #include "rayverb.h"
 #include "helpers.h"
 
+#include <charconv>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -214,6 +216,40 @@ vector <cl_float3> getRandomDirections (unsigned long num, unsigned long seed)
 vector <cl_float3> getRandomDirections (unsigned long num)
 {
     return getRandomDirections (num, (unsigned long) chrono::system_clock::now().time_since_epoch().count());
+}
+
+// ---- diagnostic ray dump (helpers.cpp:19-59) ------------------------------------------------------------
+
+// rapidjson's Writer::Double: shortest decimal that reads back as the same double, always with a
+// fraction or an exponent
+static string json_double (double v)
+{
+    char buf [64];
+    const auto r = to_chars (buf, buf + sizeof buf, v);
+    string out (buf, r.ptr);
+    if (out.find_first_of (".eE") == string::npos && isfinite (v)) out += ".0";
+    return out;
+}
+
+void print_diagnostic (unsigned long nrays, unsigned long nreflections, const vector <Impulse> & impulses, const string & fname)
+{
+    if (impulses.size() < (size_t) nrays * nreflections) throw runtime_error ("print_diagnostic: fewer impulses than rays x reflections");
+    ofstream out (fname);
+    for (unsigned long i = 0; i != nrays; ++i)
+    {
+        string line = "[";
+        for (unsigned long j = 0; j != nreflections; ++j)
+        {
+            const Impulse & reflection = impulses [i * nreflections + j];
+            float average = 0;
+            for (int k = 0; k != 8; ++k) average += reflection.volume.s [k];
+            average /= 8;
+            line += j ? ",{" : "{";
+            line += "\"position\":[" + json_double (reflection.position.s [0]) + "," + json_double (reflection.position.s [1]) + ","
+                    + json_double (reflection.position.s [2]) + "],\"volume\":" + json_double (average) + "}";
+        }
+        out << line << "]" << endl;
+    }
 }
 
 // ---- Raytracer -------------------------------------------------------------------------------------

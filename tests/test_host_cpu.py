@@ -108,3 +108,21 @@ def test_cli_fails_loudly_without_a_gpu(tmp_path):
         pytest.skip("a GPU is present")
     r = run_cli(tmp_path, GOOD)
     assert r.returncode == 1 and "no CUDA device" in r.stderr   # no CPU fallback
+
+
+def test_diagnostic_ray_dump_format(tmp_path):
+    """print_diagnostic (helpers.cpp:19-59): one JSON array per ray, {"position", "volume" = band mean}
+    per reflection -- what viewer/viewer.pde reads."""
+    out = tmp_path / "impulse.dump"
+    subprocess.run([os.path.join(BIN, "dump_scene"), "--diagnostic", str(out)], check=True)
+    lines = out.read_text().splitlines()
+    assert len(lines) == 2
+    for r, line in enumerate(lines):
+        refl = json.loads(line)
+        assert len(refl) == 3
+        for j, e in enumerate(refl):
+            i = 3 * r + j
+            assert list(e.keys()) == ["position", "volume"]
+            assert e["position"] == [float(i), 27.0, float(np.float32(-0.1) * np.float32(i))]
+            assert e["volume"] == float(np.float32(0.125 * (i + 1) * (4 * 1.0 + 4 * -0.5)) / np.float32(8))
+    assert "27.0" in lines[0]                                   # rapidjson writes integral doubles with a fraction
