@@ -4,3 +4,4 @@ cd "$(dirname "$0")"
 for f in ffma2_bench ffma2_bench2 gather_bench; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o $f.bin $f.cu || exit 1
 done
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o pair_bench.bin pair_bench.cu || exit 1
