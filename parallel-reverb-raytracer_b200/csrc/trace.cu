@@ -128,6 +128,69 @@ struct BruteSmem {
     }
 };
 
+// ---- brute force, one WARP per ray (few rays, many triangles) ----------------------------------
+// With a few thousand rays the thread-per-ray loop leaves most of the GPU idle and every query costs
+// the latency of T tests in one lane.  Here the 32 lanes of a warp carry the SAME ray (they execute
+// the per-ray code redundantly and stay converged because they compute identical values) and split
+// the triangle records: lane l tests records l, l + 32, ...  The (t, index) minimum over the lanes,
+// lexicographic, is exactly what the in-order strict '<' loop keeps (kernel.cpp:180-188).
+struct BruteSmemWarp {
+    const float4 *s;
+    uint32_t T, nquads;
+
+    __device__ __forceinline__ uint32_t my_share() const   // triangles this lane tests: the shares add up to T
+    {
+        uint32_t n = 0;
+        for (uint32_t q = threadIdx.x & 31u; q < nquads; q += 32u) n += min(4u, T - 4u * q);
+        return n;
+    }
+    __device__ __forceinline__ bool nearest(f3 pos, f3 dir, float &tbest, uint32_t &ibest, Counters &c) const
+    {
+        const BruteSmem one{s, T, nquads};
+        float tb = RVB_INF;
+        uint32_t ib = RVB_NONE;
+        for (uint32_t q = threadIdx.x & 31u; q < nquads; q += 32u) {
+            f3x2 v0a, e0a, e1a, v0b, e0b, e1b;
+            one.load(q, v0a, e0a, e1a, v0b, e0b, e1b);
+            bool ok0, ok1, ok2, ok3;
+            const float2 ta = mt_intersect_pair(v0a, e0a, e1a, pos, dir, ok0, ok1);
+            const float2 tq = mt_intersect_pair(v0b, e0b, e1b, pos, dir, ok2, ok3);
+            if (ok0 && ta.x > RVB_EPSILON && ta.x < tb) { tb = ta.x; ib = 4 * q; }
+            if (ok1 && ta.y > RVB_EPSILON && ta.y < tb) { tb = ta.y; ib = 4 * q + 1; }
+            if (ok2 && tq.x > RVB_EPSILON && tq.x < tb) { tb = tq.x; ib = 4 * q + 2; }
+            if (ok3 && tq.y > RVB_EPSILON && tq.y < tb) { tb = tq.y; ib = 4 * q + 3; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float t2 = __shfl_xor_sync(0xffffffffu, tb, o);
+            const uint32_t i2 = __shfl_xor_sync(0xffffffffu, ib, o);
+            if (t2 < tb || (t2 == tb && i2 < ib)) { tb = t2; ib = i2; }
+        }
+        tbest = tb; ibest = ib;
+        if ((threadIdx.x & 31u) == 0) c.queries++;
+        c.tri += my_share();
+        return ib != RVB_NONE;
+    }
+    __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
+    {
+        const BruteSmem one{s, T, nquads};
+        bool blocked = false;
+        for (uint32_t q = threadIdx.x & 31u; q < nquads; q += 32u) {
+            f3x2 v0a, e0a, e1a, v0b, e0b, e1b;
+            one.load(q, v0a, e0a, e1a, v0b, e0b, e1b);
+            bool ok0, ok1, ok2, ok3;
+            const float2 ta = mt_intersect_pair(v0a, e0a, e1a, pos, dir, ok0, ok1);
+            const float2 tq = mt_intersect_pair(v0b, e0b, e1b, pos, dir, ok2, ok3);
+            blocked |= (ok0 && ta.x > RVB_EPSILON && ta.x <= mag) | (ok1 && ta.y > RVB_EPSILON && ta.y <= mag)
+                     | (ok2 && tq.x > RVB_EPSILON && tq.x <= mag) | (ok3 && tq.y > RVB_EPSILON && tq.y <= mag);
+        }
+        blocked = __any_sync(0xffffffffu, blocked);
+        if ((threadIdx.x & 31u) == 0) c.queries++;
+        c.tri += my_share();
+        return blocked;
+    }
+};
+
 // ---- BVH traversal ----------------------------------------------------------------------------
 // Boxes are padded at build time and the slab test carries a relative slack, so no triangle the
 // exact test would accept at (t, index) better than the current best is ever culled; candidates
@@ -572,6 +635,24 @@ __global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TracePara
     flush_counters(P, c);
 }
 
+// One warp per ray (BruteSmemWarp): all lanes run the per-ray code on the same ray; identical values
+// are stored to identical addresses, and only lane 0's bounce count is kept.
+template <bool IMAGES>
+__global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceParams P)
+{
+    extern __shared__ float4 s_tri[];
+    stage_scene(s_tri, P);
+    BruteSmemWarp acc{s_tri, P.T, P.nquads};
+    Counters c;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < P.nrays; ray += nwarps) {
+        const uint32_t before = c.bounces;
+        if (IMAGES) image_phase_ray(acc, P, ray, c); else steady_phase_ray(acc, P, ray, c);
+        if (threadIdx.x & 31u) c.bounces = before;
+    }
+    flush_counters(P, c);
+}
+
 template <bool IMAGES, int MINB>
 __global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams P)
 {
@@ -633,9 +714,34 @@ static int try_block(const TraceParams &P, size_t smem, int &per_sm)
 {
     return occupancy_of(trace_bruteforce_kernel<IMAGES, BLOCK>, BLOCK, smem, per_sm);
 }
+// Few rays over many triangles: one warp per ray.  Cost model in units of one pair-test latency:
+// thread-per-ray needs ceil(nrays / resident threads) waves of T tests per query, warp-per-ray
+// ceil(32 nrays / resident threads) waves of ceil(nquads / 32) records (4 tests each) + a shuffle
+// reduction (~4 tests' worth).
+static bool prefer_warp_per_ray(const TraceParams &P)
+{
+    static const int forced = getenv("RVB_WARP_PER_RAY") ? atoi(getenv("RVB_WARP_PER_RAY")) : -1;
+    if (forced >= 0) return forced != 0;
+    const double resident = 1024.0 * sm_count();
+    const double thread_cost = std::ceil(P.nrays / resident) * P.T;
+    const double warp_cost = std::ceil(32.0 * P.nrays / resident) * (4.0 * std::ceil(P.nquads / 32.0) + 4.0);
+    return P.T >= 64 && warp_cost * 1.5 < thread_cost;
+}
+
 template <bool IMAGES>
 static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
 {
+    if (prefer_warp_per_ray(P)) {
+        int per_sm = 0;
+        RVB_TRY(occupancy_of(trace_bruteforce_warp_kernel<IMAGES>, 256, smem, per_sm));
+        if (per_sm >= 1) {
+            const size_t want = ((size_t)P.nrays * 32 + 255) / 256;
+            const size_t grid = std::max<size_t>(1, std::min(want, (size_t)per_sm * sm_count()));
+            note_launch(), trace_bruteforce_warp_kernel<IMAGES><<<(unsigned)grid, 256, smem, st>>>(P);
+            RVB_CUDA(cudaGetLastError());
+            return RVB_OK;
+        }
+    }
     static const int forced = getenv("RVB_BLOCK") ? atoi(getenv("RVB_BLOCK")) : 0;
     const int sizes[5] = {256, 384, 512, 768, 1024};
     const float eff[5] = {1.0f, 1.0f, 1.0f, 0.9f, 0.7f};

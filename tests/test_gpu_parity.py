@@ -167,6 +167,31 @@ def test_trace_displaced_room_vs_oracle(orc):
     check_trace_against_oracle(orc, tri, vtx, srf, (5.5, 1.2, 3.5), (2, 1.5, 2), dirs, 24, api.ACCEL_BRUTE_FORCE)
 
 
+def test_warp_per_ray_equals_thread_per_ray():
+    """Few rays over many triangles run one WARP per ray (lanes split the triangle records, shuffle
+    argmin on (t, index)); many rays run one thread per ray.  Rays are independent, so the first 1500
+    rays of a 120 000-ray trace must come out bit-identical when they are traced on their own."""
+    tri, vtx = scenes.displaced_box(8.0, 3.0, 5.0, 700, amp=0.08, fan=0.2, nsurfaces=4)
+    srf = scenes.hall_surfaces()
+    dirs = scenes.sphere_directions(120_000, seed=9)
+    mic, src, nrefl, k = (5.5, 1.2, 3.5), (2, 1.5, 2), 14, 1500
+    out = []
+    for n in (len(dirs), k):
+        rt = api.Raytracer(nrefl, tri, vtx, srf, accel=api.ACCEL_BRUTE_FORCE)
+        tr = rt.raytrace(mic, src, dirs[:n], flags=api.TRACE_DEBUG)
+        hit, cnt = tr.debug()
+        d = tr.raw_diffuse().reshape(n, nrefl)
+        st = tr.stats()
+        out.append((hit[:k].copy(), cnt[:k].copy(), d[:k].copy(), st))
+        rt.close()
+    (hit_a, cnt_a, d_a, st_a), (hit_b, cnt_b, d_b, st_b) = out
+    assert np.array_equal(hit_a, hit_b) and np.array_equal(cnt_a, cnt_b)
+    assert d_a.tobytes() == d_b.tobytes()
+    # both forms execute exactly the reference's tests: queries x triangles
+    assert st_a["tri_tests"] == st_a["queries"] * len(tri) and st_b["tri_tests"] == st_b["queries"] * len(tri)
+    assert st_b["bounces"] == int(cnt_b.sum())
+
+
 def _render_case(orc, tri, vtx, srf, mic, src, dirs, nrefl, accel, **kw):
     rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
     tr = rt.raytrace(mic, src, dirs)
