@@ -1,6 +1,7 @@
 // The bounce kernels: B200-native replacement of `kernel raytrace` (rayverb/kernel.cpp:304-503).
 //
-// One thread per ray, persistent grid-stride over rays, in two kernels:
+// One thread per ray (one WARP per ray when there are few rays and many triangles), persistent
+// grid-stride over rays, in two kernels:
 //
 //   image phase    reflections 0..8: the part of the reference loop that carries the image-source
 //                  branch (kernel.cpp:379-457: mirrored triangles, validation queries, add_image).
@@ -10,9 +11,10 @@
 //                  lanes of a warp stay in lock step.
 //
 // The ray state (position, direction, path length, 8-band volume) passes between them through a
-// 64-byte record per ray.  The scene is staged once per CTA in shared memory in intersection form
-// (v0, e0, e1 -- 3 x float4 per triangle, read as warp-wide broadcasts) for the brute-force path,
-// or traversed through the GPU-built BVH (bvh.cu) whose nearest-hit result -- including the
+// 64-byte record per ray.  The scene is staged once per CTA in shared memory in pair-interleaved
+// intersection form (v0, e0, e1 of two triangles component-wise, 144 bytes per four triangles, read
+// as warp-wide broadcasts and tested two triangles per packed-FP32 instruction) for the brute-force
+// path, or traversed through the GPU-built BVH (bvh.cu) whose nearest-hit result -- including the
 // lowest-index tie-break of the reference's strict '<' loop (kernel.cpp:180-188) -- equals the
 // brute-force loop.
 //
