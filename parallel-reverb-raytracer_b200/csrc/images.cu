@@ -112,8 +112,7 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     RVB_TRY(dev_alloc(&d_tmp, tmp_bytes));
     RVB_CUDA(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_sel, d_nsel, (int)nflat, pred, st));
     uint32_t n = 0;
-    RVB_CUDA(cudaMemcpyAsync(&n, d_nsel, sizeof n, cudaMemcpyDeviceToHost, st));
-    RVB_CUDA(cudaStreamSynchronize(st));
+    RVB_TRY(read_back(&n, d_nsel, sizeof n));
     dev_free(d_tmp);
     if (n == 0) { dev_free(d_sel); dev_free(d_nsel); return RVB_OK; }
 
@@ -165,8 +164,7 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     RVB_TRY(dev_alloc(&d_fl_tmp, fl_bytes));
     RVB_CUDA(cub::DeviceSelect::Flagged(d_fl_tmp, fl_bytes, it, d_head, d_upos, d_m, (int)n, st));
     uint32_t m = 0;
-    RVB_CUDA(cudaMemcpyAsync(&m, d_m, sizeof m, cudaMemcpyDeviceToHost, st));
-    RVB_CUDA(cudaStreamSynchronize(st));
+    RVB_TRY(read_back(&m, d_m, sizeof m));
     dev_free(d_fl_tmp);
 
     RVB_TRY(dev_alloc(&tr->d_img_volA, m));
@@ -181,9 +179,8 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     RVB_CUDA(cudaGetLastError());
     tr->img_keys.resize((size_t)m * RVB_NUM_IMAGE_SOURCE);
     tr->img_len.resize(m);
-    RVB_CUDA(cudaMemcpyAsync(tr->img_keys.data(), d_okeys, tr->img_keys.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    RVB_CUDA(cudaMemcpyAsync(tr->img_len.data(), d_olen, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RVB_CUDA(cudaStreamSynchronize(st));
+    RVB_TRY(read_back(tr->img_keys.data(), d_okeys, tr->img_keys.size() * sizeof(uint32_t)));
+    RVB_TRY(read_back(tr->img_len.data(), d_olen, m * sizeof(int32_t)));
     tr->n_images = m;
     tr->first_is_direct = (m > 0 && tr->img_len[0] == 1);   // key {0} sorts first when present
     dev_free(d_okeys); dev_free(d_olen); dev_free(d_head);

@@ -664,6 +664,8 @@ static void resolve_laps()
     g_laps.clear();
 }
 
+static int pinned_stage(float **p, size_t n) { return pinned_scratch(reinterpret_cast<void **>(p), n * sizeof(float)); }
+
 static int grid_for(size_t n, int block = 256)
 {
     size_t g = (n + block - 1) / block;
@@ -716,8 +718,7 @@ static int make_channels(const float mic[3], const rvb_render_config *cfg, Chann
         RVB_TRY(dev_alloc(&d, 2 * cs.nch));
         RVB_CUDA(cudaMemcpyAsync(d, h.data(), cs.nch * sizeof(float4), cudaMemcpyHostToDevice, st));
         note_launch(), normalize_dirs_kernel<<<1, 1024, 0, st>>>(d, (int)cs.nch, d + cs.nch);
-        RVB_CUDA(cudaMemcpyAsync(h.data(), d + cs.nch, cs.nch * sizeof(float4), cudaMemcpyDeviceToHost, st));
-        RVB_CUDA(cudaStreamSynchronize(st));
+        RVB_TRY(read_back(h.data(), d + cs.nch, cs.nch * sizeof(float4)));
         dev_free(d);
         for (size_t c0 = 0; c0 < cs.nch; c0 += RVB_MAX_GROUP) {
             ChanSpec C{};
@@ -733,7 +734,7 @@ static int make_channels(const float mic[3], const rvb_render_config *cfg, Chann
         RVB_TRY(dev_alloc(&d_ear, 2));
         const f3 f = {cfg->facing[0], cfg->facing[1], cfg->facing[2]}, u = {cfg->up[0], cfg->up[1], cfg->up[2]};
         note_launch(), ear_kernel<<<1, 2, 0, st>>>(f, u, m, d_ear);
-        RVB_CUDA(cudaMemcpyAsync(h_ear, d_ear, sizeof h_ear, cudaMemcpyDeviceToHost, st));
+        RVB_TRY(read_back(h_ear, d_ear, sizeof h_ear));
         for (int ch = 0; ch < 2; ++ch) {
             RVB_TRY(dev_alloc(&cs.d_table[ch], 2 * (cells + 180)));
             RVB_CUDA(cudaMemsetAsync(cs.d_table[ch] + 2 * cells, 0, 2 * 180 * sizeof(float4), st));
@@ -765,8 +766,7 @@ static int times_for_spec(const Source &S_all, const ChanSpec &C, float &mn, flo
     const int init[2] = {0x7f800000, 0};   // ordered(+inf), ordered(0)
     RVB_CUDA(cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, st));
     if (S.n_diffuse + S.n_images) note_launch(), times_kernel<<<grid_for(S.n_diffuse + S.n_images), 256, 0, st>>>(S, C, d);
-    RVB_CUDA(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st));
-    RVB_CUDA(cudaStreamSynchronize(st));
+    RVB_TRY(read_back(h, d, sizeof h));
     dev_free(d);
     mn = unordered(h[0]); mx = unordered(h[1]);
     if (use_ext) { mn = std::min(mn, S_all.ext_min_nz); mx = std::max(mx, S_all.ext_max); }
@@ -1075,15 +1075,20 @@ static int finish_filtered(const rvb_render_config *cfg, float *d_hist, const si
             mo += lengths[c];
         }
     }
-    int h_red[2] = {0, -1};
-    RVB_CUDA(cudaMemcpyAsync(h_red, d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
+    // The mixed channels go to the host through a pinned staging buffer: a copy into pageable memory
+    // is staged by the driver in small pieces under its context lock, which is slow and stalls the
+    // other host threads of a parameter sweep.
+    float *h_stage = nullptr;
+    RVB_TRY(pinned_stage(&h_stage, total + 2));
+    int *h_red = reinterpret_cast<int *>(h_stage + total);
+    h_red[0] = 0; h_red[1] = -1;
+    RVB_CUDA(cudaMemcpyAsync(h_red, d_red, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (total) RVB_CUDA(cudaMemcpyAsync(h_stage, d_mix, total * sizeof(float), cudaMemcpyDeviceToHost, st));
     ir->channels.assign(nch, {});
     ir->bands.assign(nch, {});
     ir->band_len.assign(nch, 0);
     mo = 0; ho = 0;
     for (size_t c = 0; c < nch; ++c) {
-        ir->channels[c].resize(lengths[c]);
-        if (lengths[c]) RVB_CUDA(cudaMemcpyAsync(ir->channels[c].data(), d_mix + mo, lengths[c] * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (keep_bands) {
             ir->bands[c].resize(RVB_NBANDS * lengths[c]);
             ir->band_len[c] = lengths[c];
@@ -1092,11 +1097,14 @@ static int finish_filtered(const rvb_render_config *cfg, float *d_hist, const si
         mo += lengths[c]; ho += RVB_NBANDS * lengths[c];
     }
     RVB_CUDA(cudaStreamSynchronize(st));
-    if (cfg->do_trim_tail) {
-        // accumulate(..., 0, max(current, index)) -- the loud sample itself is dropped (Q12);
+    mo = 0;
+    for (size_t c = 0; c < nch; ++c) {
+        // trimTail: accumulate(..., 0, max(current, index)) -- the loud sample itself is dropped (Q12);
         // vector::resize zero-extends channels shorter than the trimmed length
-        const size_t trimmed = (size_t)std::max(0, h_red[1]);
-        for (size_t c = 0; c < nch; ++c) ir->channels[c].resize(trimmed, 0.0f);
+        const size_t want = cfg->do_trim_tail ? (size_t)std::max(0, h_red[1]) : lengths[c];
+        ir->channels[c].assign(h_stage + mo, h_stage + mo + std::min(want, lengths[c]));
+        ir->channels[c].resize(want, 0.0f);
+        mo += lengths[c];
     }
     dev_free(d_mix); dev_free(d_red);
     tm.stop_into(&g_stats.finish_ms);

@@ -65,6 +65,13 @@ inline void dev_free(T *&p)
 __host__ __device__ inline int ordered_key(float f) { int i; memcpy(&i, &f, 4); return i ^ ((i >> 31) & 0x7fffffff); }
 __host__ __device__ inline float unordered_key(int i) { i = i ^ ((i >> 31) & 0x7fffffff); float f; memcpy(&f, &i, 4); return f; }
 
+// Device -> host read-backs on the hot path go through a per-thread PINNED scratch buffer.  A
+// cudaMemcpyAsync into pageable memory blocks inside the driver, holding its context lock, until the
+// stream has drained -- which serialises every other host thread of the process (a parameter sweep
+// with one stream per thread ran its pairs strictly one after the other because of it).
+int pinned_scratch(void **p, size_t bytes);                       // grown on demand, valid until the next call of this thread
+int read_back(void *dst, const void *d_src, size_t bytes);        // copy + synchronise the library stream of this thread
+
 // ---- BVH node (see bvh.cu) ------------------------------------------------------------------
 // 4-wide node, one 128-byte line: the boxes of up to four children in SoA form (slot k of every
 // float4), so one visit decides four descents and the dependent-load chain is half as long as with

@@ -8,6 +8,8 @@
 //   d_nrm    normalize(cross(e0, e1)), surface  -- kernel.cpp:110-116 evaluated once
 // The subtraction / normal are the same IEEE operations the reference performs per test, so the
 // staged values carry the same bits.
+#include <algorithm>
+#include <cstring>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -45,34 +47,75 @@ cudaStream_t lib_stream()
 }
 
 // ---- exact-size block cache ----------------------------------------------------------------------
-struct CachedBlock { void *p; cudaStream_t stream; };
+// `ready` is recorded on the freeing stream: a later owner on another stream waits for it ON THE
+// DEVICE (cudaStreamWaitEvent) -- host threads that drive different streams never block each other
+struct CachedBlock { void *p; cudaStream_t stream; cudaEvent_t ready; };
 static std::multimap<size_t, CachedBlock> g_free_blocks[64];
 static std::unordered_map<void *, size_t> g_live_blocks[64];
 static size_t g_cached_bytes[64] = {};
 static const size_t kCacheThreshold = (size_t)1 << 20;
 static const size_t kCacheLimit = (size_t)48 << 30;   // beyond this, idle blocks go back to the driver
 
+// Small blocks: a stream-ordered memory pool PER HOST THREAD (and device).  With the device's default
+// pool, a block freed on one thread's stream and re-used on another's makes the driver chain the two
+// streams together, and the worker threads of a parameter sweep end up running one after the other.
+struct ThreadPools {
+    cudaMemPool_t pool[64] = {};
+    bool own[64] = {};
+    ~ThreadPools()   // the thread is gone: give its cached blocks back (outstanding blocks stay valid until freed)
+    {
+        for (int d = 0; d < 64; ++d) if (pool[d] && own[d]) cudaMemPoolDestroy(pool[d]);
+    }
+};
+static thread_local ThreadPools g_tp;
+static cudaMemPool_t thread_pool(int dev)
+{
+    cudaMemPool_t *g_thread_pool = g_tp.pool;
+    if (!g_thread_pool[dev]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&g_thread_pool[dev], &props) != cudaSuccess) {
+            cudaGetLastError();
+            cudaDeviceGetDefaultMemPool(&g_thread_pool[dev], dev);
+        } else {
+            g_tp.own[dev] = true;
+            uint64_t keep = UINT64_MAX;   // keep freed blocks cached
+            cudaMemPoolSetAttribute(g_thread_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return g_thread_pool[dev];
+}
+
 int alloc_bytes(void **p, size_t bytes)
 {
     cudaStream_t st = lib_stream();
     if (bytes < kCacheThreshold) {
-        cudaError_t e = cudaMallocAsync(p, bytes, st);
+        int pool_dev = 0;
+        cudaGetDevice(&pool_dev);
+        cudaError_t e = cudaMallocFromPoolAsync(p, bytes, thread_pool(pool_dev), st);
         if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RVB_ERR_NOMEM : RVB_ERR_CUDA,
-                                          std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+                                          std::string("cudaMallocFromPoolAsync: ") + cudaGetErrorString(e));
         return RVB_OK;
     }
     int dev = 0;
     cudaGetDevice(&dev);
     {
         std::lock_guard<std::mutex> lk(g_mutex);
-        auto it = g_free_blocks[dev].find(bytes);
-        if (it != g_free_blocks[dev].end()) {
+        auto range = g_free_blocks[dev].equal_range(bytes);
+        auto it = range.first;
+        for (auto j = range.first; j != range.second; ++j)
+            if (j->second.stream == st) { it = j; break; }          // a block last used on this very stream needs no wait
+        if (it != range.second) {
             CachedBlock b = it->second;
             g_free_blocks[dev].erase(it);
             g_cached_bytes[dev] -= bytes;
             g_live_blocks[dev][b.p] = bytes;
             *p = b.p;
-            if (b.stream != st) cudaStreamSynchronize(b.stream);   // freed on another stream: wait for its last use
+            if (b.stream != st) cudaStreamWaitEvent(st, b.ready, 0);   // freed on another stream: order after its last use
+            cudaEventDestroy(b.ready);
             return RVB_OK;
         }
     }
@@ -82,7 +125,7 @@ int alloc_bytes(void **p, size_t bytes)
         std::vector<void *> drop;
         {
             std::lock_guard<std::mutex> lk(g_mutex);
-            for (auto &kv : g_free_blocks[dev]) drop.push_back(kv.second.p);
+            for (auto &kv : g_free_blocks[dev]) { drop.push_back(kv.second.p); cudaEventDestroy(kv.second.ready); }
             g_free_blocks[dev].clear();
             g_cached_bytes[dev] = 0;
         }
@@ -112,11 +155,15 @@ void free_bytes(void *p)
         }
         const size_t bytes = it->second;
         g_live_blocks[dev].erase(it);
-        g_free_blocks[dev].emplace(bytes, CachedBlock{p, st});
+        cudaEvent_t ready;
+        cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+        cudaEventRecord(ready, st);
+        g_free_blocks[dev].emplace(bytes, CachedBlock{p, st, ready});
         g_cached_bytes[dev] += bytes;
         while (g_cached_bytes[dev] > kCacheLimit && !g_free_blocks[dev].empty()) {
             auto big = std::prev(g_free_blocks[dev].end());
             drop.push_back(big->second.p);
+            cudaEventDestroy(big->second.ready);
             g_cached_bytes[dev] -= big->first;
             g_free_blocks[dev].erase(big);
         }
@@ -125,6 +172,32 @@ void free_bytes(void *p)
         cudaDeviceSynchronize();
         for (void *q : drop) cudaFree(q);
     }
+}
+
+static thread_local void *g_scratch = nullptr;
+static thread_local size_t g_scratch_bytes = 0;
+int pinned_scratch(void **p, size_t bytes)
+{
+    if (bytes > g_scratch_bytes) {
+        if (g_scratch) cudaFreeHost(g_scratch);
+        g_scratch = nullptr; g_scratch_bytes = 0;
+        const size_t cap = std::max<size_t>(bytes, (size_t)1 << 20);
+        RVB_CUDA(cudaHostAlloc(&g_scratch, cap, cudaHostAllocDefault));
+        g_scratch_bytes = cap;
+    }
+    *p = g_scratch;
+    return RVB_OK;
+}
+int read_back(void *dst, const void *d_src, size_t bytes)
+{
+    if (bytes == 0) return RVB_OK;
+    void *h = nullptr;
+    RVB_TRY(pinned_scratch(&h, bytes));
+    cudaStream_t st = lib_stream();
+    RVB_CUDA(cudaMemcpyAsync(h, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    memcpy(dst, h, bytes);
+    return RVB_OK;
 }
 
 static int g_sm_count[64] = {};

@@ -1041,7 +1041,10 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
     RVB_CUDA(cudaEventCreate(&em));
-    unsigned long long hm[4] = {0, 0, 0, 0};
+    unsigned long long *h_pin = nullptr;   // [0..5) final counters, [5..9) counters after the image phase
+    RVB_TRY(pinned_scratch(reinterpret_cast<void **>(&h_pin), 9 * sizeof(unsigned long long)));
+    for (int i = 0; i < 9; ++i) h_pin[i] = 0;
+    unsigned long long *hm = h_pin + 5;
     RVB_CUDA(cudaEventRecord(e0, st));
     RVB_CUDA(cudaEventRecord(em, st));
     if (tr->nrays > 0 && tr->nrefl > 0) {
@@ -1050,7 +1053,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
             if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
             else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, 0, st));
             RVB_CUDA(cudaEventRecord(em, st));
-            RVB_CUDA(cudaMemcpyAsync(hm, d_counters, sizeof hm, cudaMemcpyDeviceToHost, st));
+            RVB_CUDA(cudaMemcpyAsync(hm, d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         }
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
@@ -1075,8 +1078,8 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, 0, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
-    unsigned long long h[5];
-    RVB_CUDA(cudaMemcpyAsync(h, d_counters, sizeof h, cudaMemcpyDeviceToHost, st));
+    unsigned long long *h = h_pin;
+    RVB_CUDA(cudaMemcpyAsync(h, d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f, ms_image = 0.f, ms_steady = 0.f;
     RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
