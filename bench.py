@@ -155,6 +155,11 @@ def cpu_leg(wl, tri, vtx, srf, steps, warmup):
     from oracle import oracle as orc
     from rayverb_b200 import scenes
     orc.build()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its ranks)
+    try:
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        orc.set_num_threads(os.cpu_count() or 1)
     n = cpu_sample_rays(wl)
     dirs = scenes.sphere_directions(n, seed=wl["seed"])
     job = wl["jobs"][0]

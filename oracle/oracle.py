@@ -82,6 +82,8 @@ def lib():
         L.orc_sphere_point.restype = None
         L.orc_sphere_point.argtypes = [f32, f32, vp]
         L.orc_num_threads.restype = i32
+        L.orc_set_num_threads.restype = None
+        L.orc_set_num_threads.argtypes = [i32]
         _lib = L
     return _lib
 
@@ -96,6 +98,11 @@ def _f3(v):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle's ray loop (torchrun sets OMP_NUM_THREADS=1 for its ranks)."""
+    lib().orc_set_num_threads(int(n))
 
 
 def raytrace(triangles, vertices, surfaces, mic, source, directions, nreflections, debug=True):

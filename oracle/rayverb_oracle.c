@@ -718,6 +718,16 @@ void orc_sphere_point(float z, float theta, float *out)
     out[0] = ztemp * cosf(theta); out[1] = ztemp * sinf(theta); out[2] = z; out[3] = 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline legs ask for the host's cores */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP
