@@ -14,6 +14,7 @@
 #include <cub/cub.cuh>
 
 #include <cmath>
+#include <type_traits>
 
 #include "attenuate.cuh"
 #include "rvb_internal.cuh"
@@ -102,9 +103,33 @@ __device__ __forceinline__ uint32_t sample_index(float t, float predelay, bool f
     return (uint32_t)roundf(__fmul_rn(t, sr));
 }
 
-__global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bool fix, float sr, uint32_t L, uint32_t *keys,
-                            uint32_t *vals)
+// Two key formats.  Wide (uint32): key = sample index (sentinel L), value = impulse id; the sort skips
+// the low `shift` bits.  Compact (uint16, when there are fewer than 65535 segments and fewer than 2^30
+// impulses): key = segment id = sample index >> shift (sentinel nseg), value = impulse id with the
+// dropped low bits (the sub-bin inside the segment) in bits 30-31 -- a quarter less sort traffic, and
+// the reduction reads 4 bytes per entry instead of 8.
+#define RVB_ID_MASK 0x3fffffffu
+template <bool COMPACT>
+__device__ __forceinline__ void make_key(bool valid, float t, float predelay, bool fix, float sr, uint32_t L, uint32_t shift,
+                                         uint32_t nseg, uint32_t i, uint32_t &k, uint32_t &v)
 {
+    k = COMPACT ? nseg : L;   // sentinel: sorts behind every real bin
+    v = i;
+    if (valid) {
+        const uint32_t s = sample_index(t, predelay, fix, sr);
+        if (s < L) {
+            if (COMPACT) { k = s >> shift; v = i | ((s & ((1u << shift) - 1u)) << 30); }
+            else k = s;
+        }
+    }
+}
+
+template <bool COMPACT>
+__global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bool fix, float sr, uint32_t L, uint32_t shift,
+                            uint32_t nseg, void *keys_out, uint32_t *vals)
+{
+    using KeyT = typename std::conditional<COMPACT, uint16_t, uint32_t>::type;
+    KeyT *keys = static_cast<KeyT *>(keys_out);
     const uint32_t n = S.size();
     // Diffuse slots of the speaker / pass-through models need the 4-byte time only: four slots per
     // thread, 16-byte loads and stores (the slot count is a multiple of four, rvb_internal.cuh).
@@ -113,48 +138,44 @@ __global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bo
         first_scalar = S.n_diffuse;
         const uint32_t nq = S.n_diffuse >> 2;
         const float4 *t4 = reinterpret_cast<const float4 *>(S.tkey);
-        uint4 *k4 = reinterpret_cast<uint4 *>(keys), *v4 = reinterpret_cast<uint4 *>(vals);
+        uint4 *v4 = reinterpret_cast<uint4 *>(vals);
         for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
             const float4 t = t4[q];
             const float tt[4] = {t.x, t.y, t.z, t.w};
-            uint32_t k[4];
+            uint32_t k[4], v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                k[u] = L;   // sentinel: sorts behind every real bin
-                if (tt[u] >= 0.0f) {
-                    const uint32_t s = sample_index(tt[u], predelay, fix, sr);
-                    if (s < L) k[u] = s;
-                }
-            }
-            k4[q] = make_uint4(k[0], k[1], k[2], k[3]);
-            v4[q] = make_uint4(4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3);
+            for (int u = 0; u < 4; ++u) make_key<COMPACT>(tt[u] >= 0.0f, tt[u], predelay, fix, sr, L, shift, nseg, 4 * q + u, k[u], v[u]);
+            if (COMPACT) reinterpret_cast<ushort4 *>(keys)[q] = make_ushort4((unsigned short)k[0], (unsigned short)k[1], (unsigned short)k[2], (unsigned short)k[3]);
+            else reinterpret_cast<uint4 *>(keys)[q] = make_uint4(k[0], k[1], k[2], k[3]);
+            v4[q] = make_uint4(v[0], v[1], v[2], v[3]);
         }
     }
     for (uint32_t i = first_scalar + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float t;
-        uint32_t k = L;
-        if (attenuated_time(S, C, i, t)) {
-            uint32_t s = sample_index(t, predelay, fix, sr);
-            if (s < L) k = s;
-        }
-        keys[i] = k;
-        vals[i] = i;
+        float t = 0.0f;
+        const bool valid = attenuated_time(S, C, i, t);
+        uint32_t k, v;
+        make_key<COMPACT>(valid, t, predelay, fix, sr, L, shift, nseg, i, k, v);
+        keys[i] = (KeyT)k;
+        vals[i] = v;
     }
 }
 
 // The sort may ignore the low `shift` bits of the sample index (one radix pass fewer): a segment
 // then holds 2^shift adjacent bins, interleaved in impulse order, and the reduction separates them
 // by the key's low bits.  Segment bounds in the sorted key array (four keys per thread, 16-byte loads):
-__global__ void bounds_kernel(const uint32_t *keys, uint32_t n, uint32_t nseg, uint32_t shift, uint32_t *seg_begin, uint32_t *seg_end)
+template <class KeyT>
+__global__ void bounds_kernel(const KeyT *keys, uint32_t n, uint32_t nseg, uint32_t shift, uint32_t *seg_begin, uint32_t *seg_end)
 {
     const uint32_t nq = (n + 3) >> 2;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
         const uint32_t i0 = 4 * q;
         uint32_t k[6];   // keys i0-1 .. i0+4
-        if (i0 + 4 <= n) { const uint4 v = reinterpret_cast<const uint4 *>(keys)[q]; k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w; }
-        else for (int u = 0; u < 4; ++u) k[1 + u] = i0 + u < n ? keys[i0 + u] : 0u;
-        k[0] = i0 ? keys[i0 - 1] : 0u;
-        k[5] = i0 + 4 < n ? keys[i0 + 4] : 0u;
+        if (i0 + 4 <= n) {
+            if (sizeof(KeyT) == 4) { const uint4 v = reinterpret_cast<const uint4 *>(keys)[q]; k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w; }
+            else { const ushort4 v = reinterpret_cast<const ushort4 *>(keys)[q]; k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w; }
+        } else for (int u = 0; u < 4; ++u) k[1 + u] = i0 + u < n ? (uint32_t)keys[i0 + u] : 0u;
+        k[0] = i0 ? (uint32_t)keys[i0 - 1] : 0u;
+        k[5] = i0 + 4 < n ? (uint32_t)keys[i0 + 4] : 0u;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const uint32_t i = i0 + u;
@@ -237,7 +258,10 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
                 idx[u] = RVB_NO_IMPULSE; sub[u] = 0;
                 if (j + 32 * u < b1) {
                     idx[u] = vals[j + 32 * u];
-                    if (NSUB > 1) {
+                    if (keys == nullptr) {                     // compact format: sub-bin in the value's top bits
+                        sub[u] = (idx[u] >> 30) & (NSUB - 1);
+                        idx[u] &= RVB_ID_MASK;
+                    } else if (NSUB > 1) {
                         const uint32_t k = keys[j + 32 * u];
                         if (k >= L) idx[u] = RVB_NO_IMPULSE;   // skipped impulses share the last segment
                         sub[u] = k & (NSUB - 1);
@@ -305,7 +329,10 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
                 idx[u] = RVB_NO_IMPULSE; sub[u] = 0;
                 if (j + 32 * u < m1) {
                     idx[u] = vals[j + 32 * u];
-                    if (NSUB > 1) {
+                    if (keys == nullptr) {                     // compact format: sub-bin in the value's top bits
+                        sub[u] = (idx[u] >> 30) & (NSUB - 1);
+                        idx[u] &= RVB_ID_MASK;
+                    } else if (NSUB > 1) {
                         const uint32_t k = keys[j + 32 * u];
                         if (k >= L) idx[u] = RVB_NO_IMPULSE;   // skipped impulses share the last segment
                         sub[u] = k & (NSUB - 1);
@@ -790,6 +817,7 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
     int last_group = -1;
     uint32_t L = 0, nseg = 0;
     int cur = 0, shift = 0;
+    bool compact = false;
     for (size_t p = 0; p < cs.passes.size(); ++p) {
         const ChanSpec &C = cs.passes[p];
         const size_t c0 = cs.pass_first_channel[p];
@@ -800,10 +828,6 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
         if (cs.pass_key_group[p] != last_group) {
             last_group = cs.pass_key_group[p];
             L = (uint32_t)lengths[c0];
-            Timer tk(st);
-            note_launch(), keys_kernel<<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, d_keys[0], d_vals[0]);
-            tk.stop_into(&g_stats.keys_ms);
-            Timer ts(st);
             int end_bit = 1;
             while ((1ull << end_bit) <= (unsigned long long)L) ++end_bit;   // keys in [0, L]
             // drop low key bits from the sort when that saves an 8-bit radix pass (see bounds_kernel)
@@ -812,19 +836,42 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             for (int sft = 1; sft <= max_shift; ++sft)
                 if ((end_bit - sft + 7) / 8 < (end_bit + 7) / 8) { shift = sft; break; }
             nseg = ((L - 1) >> shift) + 1;
-            cub::DoubleBuffer<uint32_t> kb(d_keys[0], d_keys[1]), vb(d_vals[0], d_vals[1]);
+            // compact format (see make_key): 16-bit segment ids, sub-bin in the value's top bits
+            static const bool allow_compact = !(getenv("RVB_WIDE_KEYS") && atoi(getenv("RVB_WIDE_KEYS")) != 0);
+            compact = allow_compact && nseg < 65535u && n < (1u << 30);
+            Timer tk(st);
+            note_launch();
+            if (compact) keys_kernel<true><<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, (uint32_t)shift, nseg, d_keys[0], d_vals[0]);
+            else keys_kernel<false><<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, (uint32_t)shift, nseg, d_keys[0], d_vals[0]);
+            tk.stop_into(&g_stats.keys_ms);
+            Timer ts(st);
+            cub::DoubleBuffer<uint32_t> vb(d_vals[0], d_vals[1]);
             size_t bytes = 0;
-            RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, shift, end_bit, st));
-            dev_free(d_tmp);
-            RVB_TRY(dev_alloc(&d_tmp, bytes));
-            RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, shift, end_bit, st));
-            cur = kb.selector;
+            if (compact) {
+                int seg_bits = 1;
+                while ((1u << seg_bits) <= nseg) ++seg_bits;   // segment ids in [0, nseg]
+                cub::DoubleBuffer<uint16_t> kb(reinterpret_cast<uint16_t *>(d_keys[0]), reinterpret_cast<uint16_t *>(d_keys[1]));
+                RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, 0, seg_bits, st));
+                dev_free(d_tmp);
+                RVB_TRY(dev_alloc(&d_tmp, bytes));
+                RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, 0, seg_bits, st));
+                cur = kb.selector;
+            } else {
+                cub::DoubleBuffer<uint32_t> kb(d_keys[0], d_keys[1]);
+                RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, shift, end_bit, st));
+                dev_free(d_tmp);
+                RVB_TRY(dev_alloc(&d_tmp, bytes));
+                RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, shift, end_bit, st));
+                cur = kb.selector;
+            }
             if (vb.selector != cur) return fail(RVB_ERR_CUDA, "radix sort buffers diverged");
             dev_free(d_begin); dev_free(d_end);
             RVB_TRY(dev_alloc(&d_begin, (size_t)nseg)); RVB_TRY(dev_alloc(&d_end, (size_t)nseg));
             RVB_CUDA(cudaMemsetAsync(d_begin, 0, (size_t)nseg * sizeof(uint32_t), st));
             RVB_CUDA(cudaMemsetAsync(d_end, 0, (size_t)nseg * sizeof(uint32_t), st));
-            note_launch(), bounds_kernel<<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, nseg, (uint32_t)shift, d_begin, d_end);
+            note_launch();
+            if (compact) bounds_kernel<uint16_t><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const uint16_t *>(d_keys[cur]), n, nseg, 0u, d_begin, d_end);
+            else bounds_kernel<uint32_t><<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, nseg, (uint32_t)shift, d_begin, d_end);
             ts.stop_into(&g_stats.sort_ms);
         }
         Timer tr_(st);
@@ -836,12 +883,13 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             for (int c = 0; c < C.nch; ++c) need_pos |= (C.coef[c] != 0.0f);
             note_launch();
             const int nsub = 1 << shift;
+            const uint32_t *rkeys = compact ? nullptr : d_keys[cur];   // compact: the values carry the sub-bin
             static const int force = getenv("RVB_REDUCE_DENSE") ? atoi(getenv("RVB_REDUCE_DENSE")) : -1;
             const bool dense = force >= 0 ? force != 0 : (size_t)n >= (size_t)256 * nseg;
-            if (C.model == 0 && need_pos) launch_reduce<0, true>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
-            else if (C.model == 0) launch_reduce<0, false>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
-            else if (C.model == 1) launch_reduce<1, true>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
-            else launch_reduce<2, false>(nsub, rgrid, dense, st, S, C, d_keys[cur], d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            if (C.model == 0 && need_pos) launch_reduce<0, true>(nsub, rgrid, dense, st, S, C, rkeys, d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else if (C.model == 0) launch_reduce<0, false>(nsub, rgrid, dense, st, S, C, rkeys, d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else if (C.model == 1) launch_reduce<1, true>(nsub, rgrid, dense, st, S, C, rkeys, d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
+            else launch_reduce<2, false>(nsub, rgrid, dense, st, S, C, rkeys, d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
         }
         RVB_CUDA(cudaGetLastError());
         tr_.stop_into(&g_stats.reduce_ms);
