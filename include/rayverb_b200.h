@@ -126,6 +126,11 @@ typedef struct {
     float steady_phase_ms;     /* reflections 9.. (the dominant kernel)                         */
     uint64_t steady_tri_tests; /* ray-triangle tests executed by the steady-phase kernel        */
     uint64_t steady_box_tests;
+    uint64_t emitted;          /* diffuse impulses with a non-zero volume (the rest are skipped
+                                  by the attenuators, kernel.cpp:524,607)                        */
+    uint64_t micmap_entries;   /* BVH scenes: triangle references in the microphone visibility map */
+    uint32_t micmap_cells;     /* ... and its cells per cube-face edge (0: no map)               */
+    uint32_t reserved_;
 } rvb_trace_stats;
 int rvb_trace_get_stats(const rvb_trace *trace, rvb_trace_stats *stats);
 

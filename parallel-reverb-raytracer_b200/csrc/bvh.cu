@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 #include "rvb_internal.cuh"
+#include "rvb_scan.cuh"
 
 namespace rvb {
 
@@ -136,25 +137,79 @@ struct Slot { int ref; Aabb box; };
 
 // reference + box of binary child c as seen from a 4-wide parent: a single triangle, a collapsed
 // subtree (<= RVB_LEAF_MAX triangles, contiguous in sorted order) or an inner node
-__device__ __forceinline__ Slot make_slot(int c, const int2 *ranges, const Aabb *tri_boxes, const uint32_t *ids, const Aabb *node_boxes)
+__device__ __forceinline__ Slot make_slot(int c, const int2 *ranges, const Aabb *tri_boxes, const uint32_t *ids, const Aabb *node_boxes,
+                                          const uint32_t *rec_of)
 {
     Slot s;
     if (c < 0) {
         s.box = tri_boxes[ids[~c]];
-        s.ref = c;                                             // leaf: first = position, count 1
+        s.ref = ~(int)rec_of[~c];                              // leaf record of a single triangle (count - 1 = 0)
     } else {
         s.box = node_boxes[c];
         const int2 r = ranges[c];
         const int cnt = r.y - r.x + 1;
-        s.ref = cnt <= RVB_LEAF_MAX ? ~(int)((uint32_t)r.x | ((uint32_t)(cnt - 1) << 28)) : c;
+        s.ref = cnt <= RVB_LEAF_MAX ? ~(int)(rec_of[r.x] | ((uint32_t)(cnt - 1) << 28)) : c;
     }
     return s;
+}
+
+// Leaves: a subtree of <= RVB_LEAF_MAX triangles whose parent holds more.  They partition the sorted
+// triangle order into consecutive runs; flag[p] = 1 marks the first position of a run, cnt_at[p] its
+// length.  (One thread per binary inner node; nodes inside a collapsed subtree mark nothing.)
+__global__ void mark_leaves_kernel(int n, const int2 *children, const int2 *ranges, uint32_t *flag, uint32_t *cnt_at)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int2 r = ranges[i];
+    if (i != 0 && r.y - r.x + 1 <= RVB_LEAF_MAX) return;   // inside a collapsed subtree (the root is never collapsed)
+    const int2 c = children[i];
+    const int kids[2] = {c.x, c.y};
+    for (int k = 0; k < 2; ++k) {
+        if (kids[k] < 0) { flag[~kids[k]] = 1u; cnt_at[~kids[k]] = 1u; }
+        else {
+            const int2 q = ranges[kids[k]];
+            if (q.y - q.x + 1 <= RVB_LEAF_MAX) { flag[q.x] = 1u; cnt_at[q.x] = (uint32_t)(q.y - q.x + 1); }
+        }
+    }
+}
+
+// Leaf records in the pair-interleaved form of the brute-force loop (scene.cu: pack_quads_kernel):
+// 36 floats = two component-wise pairs (v0, e0, e1) of up to four triangles, zero triangles pad
+// (det = 0 rejects them, kernel.cpp:72); leaf_ids holds the callers' triangle indices.
+__global__ void fill_leaves_kernel(uint32_t T, const uint32_t *flag, const uint32_t *rec_of, const uint32_t *cnt_at, const uint32_t *ids,
+                                   const float4 *tri, float *leaf_quads, uint4 *leaf_ids)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= T || !flag[p]) return;
+    const uint32_t r = rec_of[p], cnt = cnt_at[p];
+    const float *src = reinterpret_cast<const float *>(tri);
+    uint32_t id[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    for (uint32_t k = 0; k < 4; ++k) {
+        float v[9];
+        for (int j = 0; j < 9; ++j) v[j] = 0.f;
+        if (k < cnt) {
+            id[k] = ids[p + k];
+            for (int j = 0; j < 9; ++j) v[j] = src[12 * (size_t)id[k] + j];
+        }
+        for (int j = 0; j < 9; ++j) leaf_quads[36 * (size_t)r + 18 * (k >> 1) + 2 * j + (k & 1)] = v[j];
+    }
+    leaf_ids[r] = make_uint4(id[0], id[1], id[2], id[3]);
+}
+
+// depth of every triangle in the binary hierarchy (the traversal stack is sized from the maximum)
+__global__ void depth_kernel(int n, const int *parent_inner, const int *parent_leaf, int *max_depth)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int d = 0;
+    if (p < n) for (int node = parent_leaf[p]; node >= 0; node = parent_inner[node]) ++d;
+    for (int o = 16; o; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_depth, d);
 }
 
 // 4-wide node of binary inner node i: its two children, each replaced by ITS two children when it
 // is a (non-collapsed) inner node.  Only nodes reachable from the root this way are ever visited.
 __global__ void emit_nodes_kernel(int n, const int2 *children, const int2 *ranges, const Aabb *tri_boxes, const uint32_t *ids,
-                                  const Aabb *node_boxes, float pad, BvhNode *out)
+                                  const Aabb *node_boxes, const uint32_t *rec_of, float pad, BvhNode *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -163,11 +218,11 @@ __global__ void emit_nodes_kernel(int n, const int2 *children, const int2 *range
     const int2 c = children[i];
     const int kids[2] = {c.x, c.y};
     for (int k = 0; k < 2; ++k) {
-        const Slot s = make_slot(kids[k], ranges, tri_boxes, ids, node_boxes);
+        const Slot s = make_slot(kids[k], ranges, tri_boxes, ids, node_boxes, rec_of);
         if (s.ref >= 0) {   // inner: expand
             const int2 g = children[s.ref];
-            slots[ns++] = make_slot(g.x, ranges, tri_boxes, ids, node_boxes);
-            slots[ns++] = make_slot(g.y, ranges, tri_boxes, ids, node_boxes);
+            slots[ns++] = make_slot(g.x, ranges, tri_boxes, ids, node_boxes, rec_of);
+            slots[ns++] = make_slot(g.y, ranges, tri_boxes, ids, node_boxes, rec_of);
         } else slots[ns++] = s;
     }
     float lo[3][4], hi[3][4];
@@ -190,14 +245,6 @@ __global__ void emit_nodes_kernel(int n, const int2 *children, const int2 *range
     nd.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
     nd.pad = make_float4(0.f, 0.f, 0.f, 0.f);
     out[i] = nd;
-}
-
-__global__ void permute_tris_kernel(const float4 *tri, const uint32_t *ids, uint32_t T, float4 *tri_sorted)
-{
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= T) return;
-    uint32_t i = ids[p];
-    tri_sorted[3 * p] = tri[3 * i]; tri_sorted[3 * p + 1] = tri[3 * i + 1]; tri_sorted[3 * p + 2] = tri[3 * i + 2];
 }
 
 int scene_build_bvh(Scene *sc)
@@ -246,14 +293,34 @@ int scene_build_bvh(Scene *sc)
     note_launch(), refit_kernel<<<grd, blk, 0, st>>>(d_tri_boxes, ids, (int)T, d_children, d_parent_inner, d_parent_leaf, d_node_boxes, d_visits);
     sc->n_nodes = T - 1;
     RVB_TRY(dev_alloc(&sc->d_nodes, sc->n_nodes));
-    RVB_TRY(dev_alloc(&sc->d_order, T));
-    RVB_TRY(dev_alloc(&sc->d_tri_sorted, 3 * (size_t)T));
-    note_launch(), emit_nodes_kernel<<<grd, blk, 0, st>>>((int)T, d_children, d_ranges, d_tri_boxes, ids, d_node_boxes, pad, sc->d_nodes);
-    note_launch(), permute_tris_kernel<<<grd, blk, 0, st>>>(sc->d_tri, ids, T, sc->d_tri_sorted);
-    RVB_CUDA(cudaMemcpyAsync(sc->d_order, ids, T * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    // leaves: mark the runs, number them (exclusive scan of the start flags), pack their records
+    uint32_t *d_flag = nullptr, *d_rec_of = nullptr, *d_cnt_at = nullptr, *d_scan_tmp = nullptr;
+    int *d_depth = nullptr;
+    RVB_TRY(dev_alloc(&d_flag, (size_t)T + 1)); RVB_TRY(dev_alloc(&d_rec_of, (size_t)T + 1)); RVB_TRY(dev_alloc(&d_cnt_at, T));
+    RVB_TRY(dev_alloc(&d_scan_tmp, scan_blocks(T))); RVB_TRY(dev_alloc(&d_depth, 1));
+    RVB_CUDA(cudaMemsetAsync(d_flag, 0, ((size_t)T + 1) * sizeof(uint32_t), st));
+    RVB_CUDA(cudaMemsetAsync(d_depth, 0, sizeof(int), st));
+    note_launch(), mark_leaves_kernel<<<grd, blk, 0, st>>>((int)T, d_children, d_ranges, d_flag, d_cnt_at);
+    RVB_TRY(exclusive_scan_u32(d_flag, d_rec_of, T, d_scan_tmp, d_rec_of + T, st));
+    note_launch(), depth_kernel<<<grd, blk, 0, st>>>((int)T, d_parent_inner, d_parent_leaf, d_depth);
+    uint32_t n_leaves = 0;
+    int depth = 0;
+    RVB_TRY(read_back(&n_leaves, d_rec_of + T, sizeof n_leaves));
+    RVB_TRY(read_back(&depth, d_depth, sizeof depth));
+    // a 4-wide visit descends two binary levels and pushes at most three entries
+    if (3 * (depth / 2 + 2) + 2 > RVB_BVH_STACK)
+        return fail(RVB_ERR_UNSUPPORTED, "BVH of depth " + std::to_string(depth) + " exceeds the traversal stack (near-coincident triangles?)");
+    sc->n_leaves = n_leaves;
+    sc->bvh_depth = depth;
+    RVB_TRY(dev_alloc(&sc->d_leaf_quads, 9 * (size_t)n_leaves));
+    RVB_TRY(dev_alloc(&sc->d_leaf_ids, (size_t)n_leaves));
+    note_launch(), fill_leaves_kernel<<<grd, blk, 0, st>>>(T, d_flag, d_rec_of, d_cnt_at, ids, sc->d_tri, reinterpret_cast<float *>(sc->d_leaf_quads), sc->d_leaf_ids);
+    note_launch(), emit_nodes_kernel<<<grd, blk, 0, st>>>((int)T, d_children, d_ranges, d_tri_boxes, ids, d_node_boxes, d_rec_of, pad, sc->d_nodes);
     RVB_CUDA(cudaGetLastError());
     RVB_CUDA(cudaEventRecord(e1, st));
     RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_flag); dev_free(d_rec_of); dev_free(d_cnt_at); dev_free(d_scan_tmp); dev_free(d_depth);
+    sc->diag = diag;
     cudaEventElapsedTime(&sc->build_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     dev_free(d_tri_boxes); dev_free(d_node_boxes); dev_free(d_centroids); dev_free(d_scene);

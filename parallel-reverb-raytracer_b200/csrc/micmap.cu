@@ -1,0 +1,158 @@
+// Build of the microphone visibility map (see micmap.cuh for what it is and why it is exact).
+//
+// One thread per triangle, two passes (count, fill) around a device-wide exclusive scan.  For each
+// cube face the triangle is clipped against w >= wc (w = depth along the face axis), its vertices
+// are grown by `delta` in world space, projected to (u, v) = (b / w, c / w) and the bounding
+// rectangle of the result -- plus an absolute slack for the rounding of the query's own cell
+// computation -- is registered in every cell it touches.  Entries inside a cell are in no
+// particular order: a visibility query is an OR over its cell's triangles.
+//
+// tools/bvh_lab/micmap_lab.cpp runs this very construction on the CPU against the brute-force loop
+// (canonical float arithmetic) for traced and adversarial queries, including a microphone a few
+// centimetres above a wall: no accepted hit was ever missing from its cell.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "micmap.cuh"
+#include "rvb_internal.cuh"
+#include "rvb_scan.cuh"
+
+namespace rvb {
+
+struct MicMapParams {
+    const float4 *verts;   // [3T] v0, v1, v2
+    uint32_t T, N;
+    float half_n, delta, r_near, wc;
+    float mic[3];
+    uint32_t near_cap;
+};
+
+struct FaceRect { uint32_t i0, i1, j0, j1; };
+
+__device__ __forceinline__ void grow_uv(float W, float U, float V, float delta, float &ulo, float &uhi, float &vlo, float &vhi)
+{
+    const float wn = W - delta, wf = W + delta;   // wn > 0: W >= wc = 20 delta
+    const float u0 = U - delta, u1 = U + delta, v0 = V - delta, v1 = V + delta;
+    ulo = fminf(ulo, fminf(u0 / wn, u0 / wf)); uhi = fmaxf(uhi, fmaxf(u1 / wn, u1 / wf));
+    vlo = fminf(vlo, fminf(v0 / wn, v0 / wf)); vhi = fmaxf(vhi, fmaxf(v1 / wn, v1 / wf));
+}
+
+// p: the triangle's vertices relative to the microphone
+__device__ __forceinline__ bool face_rect(const float (&p)[3][3], int face, const MicMapParams &M, FaceRect &r)
+{
+    const int a = face >> 1, b = (a + 1) % 3, c = (a + 2) % 3;
+    const float s = (face & 1) ? -1.0f : 1.0f;
+    float w[3], ub[3], vc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { w[k] = s * p[k][a]; ub[k] = p[k][b]; vc[k] = p[k][c]; }
+    if (w[0] < M.wc && w[1] < M.wc && w[2] < M.wc) return false;
+    float ulo = 3e38f, uhi = -3e38f, vlo = 3e38f, vhi = -3e38f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int k1 = (k + 1) % 3;
+        if (w[k] >= M.wc) grow_uv(w[k], ub[k], vc[k], M.delta, ulo, uhi, vlo, vhi);
+        if ((w[k] < M.wc) != (w[k1] < M.wc)) {   // the edge crosses the clip plane
+            const float t = (M.wc - w[k]) / (w[k1] - w[k]);
+            grow_uv(M.wc, ub[k] + t * (ub[k1] - ub[k]), vc[k] + t * (vc[k1] - vc[k]), M.delta, ulo, uhi, vlo, vhi);
+        }
+    }
+    const float slack = 1e-5f;   // rounding of the query's (u, v)
+    ulo -= slack; uhi += slack; vlo -= slack; vhi += slack;
+    if (uhi < -1.0f || ulo > 1.0f || vhi < -1.0f || vlo > 1.0f) return false;
+    r.i0 = micmap_coord(fmaxf(ulo, -1.0f), M.half_n, M.N); r.i1 = micmap_coord(fminf(uhi, 1.0f), M.half_n, M.N);
+    r.j0 = micmap_coord(fmaxf(vlo, -1.0f), M.half_n, M.N); r.j1 = micmap_coord(fminf(vhi, 1.0f), M.half_n, M.N);
+    return true;
+}
+
+// FILL = false: count entries per cell (counts[cell]) and near triangles (near_count)
+// FILL = true : write them (cursor[cell] starts at 0; offsets from the scan)
+template <bool FILL>
+__global__ void micmap_bin_kernel(const MicMapParams M, uint32_t *counts_or_cursor, const uint32_t *cell_off, uint32_t *cell_ent,
+                                  uint32_t *near_count, uint32_t *near_ent)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M.T) return;
+    float p[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 v = M.verts[3 * i + k];
+        p[k][0] = v.x - M.mic[0]; p[k][1] = v.y - M.mic[1]; p[k][2] = v.z - M.mic[2];
+    }
+    // distance from the microphone to the triangle's bounding box: a lower bound of the distance to the triangle
+    float d2 = 0.0f;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const float mn = fminf(p[0][ax], fminf(p[1][ax], p[2][ax])), mx = fmaxf(p[0][ax], fmaxf(p[1][ax], p[2][ax]));
+        const float d = mn > 0.0f ? mn : (mx < 0.0f ? -mx : 0.0f);
+        d2 += d * d;
+    }
+    if (!(d2 >= M.r_near * M.r_near)) {   // near (or NaN): tested by every query
+        const uint32_t k = atomicAdd(near_count, 1u);
+        if (FILL && k < M.near_cap) near_ent[k] = i;
+        return;
+    }
+    for (int f = 0; f < 6; ++f) {
+        FaceRect r;
+        if (!face_rect(p, f, M, r)) continue;
+        for (uint32_t j = r.j0; j <= r.j1; ++j)
+            for (uint32_t ii = r.i0; ii <= r.i1; ++ii) {
+                const uint32_t cell = ((uint32_t)f * M.N + j) * M.N + ii;
+                const uint32_t k = atomicAdd(counts_or_cursor + cell, 1u);
+                if (FILL) cell_ent[cell_off[cell] + k] = i;
+            }
+    }
+}
+
+void micmap_free(MicMapStorage *s)
+{
+    dev_free(s->d_cell_off); dev_free(s->d_cell_ent); dev_free(s->d_near);
+    s->map = MicMap{};
+}
+
+int micmap_build(const Scene *sc, const float mic[3], MicMapStorage *out)
+{
+    *out = MicMapStorage{};
+    static const int enabled = getenv("RVB_MICMAP") ? atoi(getenv("RVB_MICMAP")) : 1;
+    if (!enabled || sc->accel != RVB_ACCEL_BVH || !(sc->diag > 0.0f)) return RVB_OK;
+    static const double cells_per_tri = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 8.0;
+    cudaStream_t st = lib_stream();
+    MicMapParams M{};
+    M.verts = sc->d_verts; M.T = sc->T;
+    M.N = (uint32_t)std::min(512.0, std::max(8.0, std::round(std::sqrt(cells_per_tri * sc->T / 6.0))));
+    M.half_n = 0.5f * (float)M.N;
+    M.delta = 1e-4f * sc->diag + 1e-6f;
+    M.r_near = 40.0f * M.delta;
+    M.wc = 0.5f * M.r_near;
+    for (int k = 0; k < 3; ++k) M.mic[k] = mic[k];
+    M.near_cap = 4096;
+    const size_t ncell = (size_t)6 * M.N * M.N;
+    uint32_t *d_cursor = nullptr, *d_block = nullptr, *d_near_count = nullptr;
+    int rc = RVB_OK;
+    auto done = [&](int code) { dev_free(d_cursor); dev_free(d_block); dev_free(d_near_count); if (code) micmap_free(out); return code; };
+    if ((rc = dev_alloc(&out->d_cell_off, ncell + 1)) || (rc = dev_alloc(&d_cursor, ncell)) || (rc = dev_alloc(&d_block, scan_blocks(ncell))) ||
+        (rc = dev_alloc(&d_near_count, 2)) || (rc = dev_alloc(&out->d_near, (size_t)M.near_cap)))
+        return done(rc);
+    RVB_CUDA(cudaMemsetAsync(out->d_cell_off, 0, (ncell + 1) * sizeof(uint32_t), st));
+    RVB_CUDA(cudaMemsetAsync(d_cursor, 0, ncell * sizeof(uint32_t), st));
+    RVB_CUDA(cudaMemsetAsync(d_near_count, 0, 2 * sizeof(uint32_t), st));
+    const unsigned grd = (M.T + 127) / 128;
+    note_launch(), micmap_bin_kernel<false><<<grd, 128, 0, st>>>(M, out->d_cell_off, nullptr, nullptr, d_near_count, nullptr);
+    if ((rc = exclusive_scan_u32(out->d_cell_off, out->d_cell_off, ncell, d_block, out->d_cell_off + ncell, st))) return done(rc);
+    uint32_t h[2] = {0, 0};   // total entries, near triangles
+    RVB_CUDA(cudaMemcpyAsync(d_near_count + 1, out->d_cell_off + ncell, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if ((rc = read_back(h, d_near_count, sizeof h))) return done(rc);
+    const uint32_t n_near = h[0], total = h[1];
+    if (n_near > M.near_cap) return done(RVB_OK), micmap_free(out), RVB_OK;   // microphone inside dense geometry: generic queries
+    if ((rc = dev_alloc(&out->d_cell_ent, (size_t)std::max(1u, total)))) return done(rc);
+    RVB_CUDA(cudaMemsetAsync(d_near_count, 0, sizeof(uint32_t), st));
+    note_launch(), micmap_bin_kernel<true><<<grd, 128, 0, st>>>(M, d_cursor, out->d_cell_off, out->d_cell_ent, d_near_count, out->d_near);
+    RVB_CUDA(cudaGetLastError());
+    out->map.cell_off = out->d_cell_off; out->map.cell_ent = out->d_cell_ent; out->map.near_ent = out->d_near;
+    out->map.n_near = n_near; out->map.N = M.N; out->map.half_n = M.half_n;
+    for (int k = 0; k < 3; ++k) out->map.mic[k] = mic[k];
+    out->entries = total;
+    return done(RVB_OK);
+}
+
+}  // namespace rvb

@@ -8,6 +8,7 @@
 
 #include "../../include/rayverb_b200.h"
 #include "rvb_math.cuh"
+#include "micmap.cuh"
 
 namespace rvb {
 
@@ -79,6 +80,7 @@ int read_back(void *dst, const void *d_src, size_t bytes);        // copy + sync
 // ~ref = first position in the sorted triangle order | (count - 1) << 28.  Unused slots carry
 // RVB_BVH_EMPTY and an inverted box.
 #define RVB_BVH_EMPTY ((int)0x80000001)
+#define RVB_BVH_STACK 96             // traversal stack entries per thread (bvh.cu refuses deeper hierarchies)
 struct __align__(16) BvhNode {
     float4 lox, loy, loz, hix, hiy, hiz;
     int4 ref;
@@ -100,8 +102,11 @@ struct Scene {
     // BVH (accel == RVB_ACCEL_BVH)
     BvhNode *d_nodes = nullptr;       // [n_nodes]
     uint32_t n_nodes = 0;
-    uint32_t *d_order = nullptr;      // [T] sorted position -> original triangle index
-    float4 *d_tri_sorted = nullptr;   // [3T] d_tri permuted into BVH order
+    float4 *d_leaf_quads = nullptr;   // [9*n_leaves] leaf records: <= 4 triangles in the pair-interleaved form of d_quad
+    uint4 *d_leaf_ids = nullptr;      // [n_leaves] the callers' triangle indices of the four slots (0xffffffff = unused)
+    uint32_t n_leaves = 0;
+    int bvh_depth = 0;                // binary depth of the hierarchy (bounds the traversal stack)
+    float diag = 0.f;                 // scene diagonal (sizes the conservative paddings)
     float build_ms = 0.f;
 };
 
@@ -152,6 +157,15 @@ struct Ir {
     std::vector<std::vector<float>> bands;         // [channel] -> [8][band_len] filtered, before mixdown
     std::vector<size_t> band_len;
 };
+
+// ---- microphone visibility map (micmap.cu) ----------------------------------------------------------
+struct MicMapStorage {
+    MicMap map;                       // what the kernels see (N == 0: no map, generic occlusion queries)
+    uint32_t *d_cell_off = nullptr, *d_cell_ent = nullptr, *d_near = nullptr;
+    uint32_t entries = 0;
+};
+int micmap_build(const Scene *sc, const float mic[3], MicMapStorage *out);
+void micmap_free(MicMapStorage *s);
 
 // ---- stage entry points (defined in the .cu files) ----------------------------------------------
 int scene_build_bvh(Scene *sc);                                                       // bvh.cu

@@ -384,7 +384,7 @@ int rvb_scene_destroy(rvb_scene *sc)
     if (!sc) return RVB_OK;
     cudaSetDevice(sc->device);
     dev_free(sc->d_verts); dev_free(sc->d_tri); dev_free(sc->d_quad); dev_free(sc->d_nrm); dev_free(sc->d_surfaces);
-    dev_free(sc->d_nodes); dev_free(sc->d_order); dev_free(sc->d_tri_sorted);
+    dev_free(sc->d_nodes); dev_free(sc->d_leaf_quads); dev_free(sc->d_leaf_ids);
     cudaStreamSynchronize(lib_stream());
     delete sc;
     return RVB_OK;

@@ -41,8 +41,9 @@ struct TraceParams {
     uint32_t T;
     // BVH
     const BvhNode *nodes;
-    const float4 *tri_sorted;
-    const uint32_t *order;
+    const float4 *leaf_quads;
+    const uint4 *leaf_ids;
+    MicMap micmap;            // visibility map around the microphone (N == 0: none)
     const float4 *dirs;
     const uint32_t *ray_perm;  // image phase: processing order (rays sorted by direction), or null
     uint32_t nrays, nrefl;
@@ -56,13 +57,13 @@ struct TraceParams {
     float4 *state;            // [4*nrays] (pos, distance) (dir, alive) volA volB
     float4 *cand_volA, *cand_volB, *cand_pt;   // [nrays*10] image-source candidates
     uint32_t *cand_idx;                        // [nrays*10] triangle+1, 0 = none (pre-zeroed)
-    unsigned long long *counters;              // [0] queries [1] tri tests [2] box tests [3] bounces
+    unsigned long long *counters;              // [0] queries [1] tri tests [2] box tests [3] bounces [5] emitted impulses
     int *time_ext;                             // [0] ordered min non-zero, [1] ordered max time of the emitted diffuse impulses
     uint32_t flags;
 };
 
 struct Counters {
-    uint32_t queries = 0, bounces = 0;
+    uint32_t queries = 0, bounces = 0, emitted = 0;
     unsigned long long tri = 0, box = 0;
     // extrema of the emitted (non-skipped) impulse times: what findPredelay / flattenImpulses need
     // (rayverb.h:47-76, rayverb.cpp:54-57), gathered here so the renderer does not re-read 4 B per impulse
@@ -112,7 +113,7 @@ struct BruteSmem {
         return ibest != RVB_NONE;
     }
     // point_intersection (kernel.cpp:274-296): visible unless some hit has EPS < t <= mag
-    __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
+    __device__ __forceinline__ bool occluded_to_mic(f3 pos, f3 dir, float mag, Counters &c) const
     {
         bool blocked = false;
 #pragma unroll 2
@@ -173,7 +174,7 @@ struct BruteSmemWarp {
         c.tri += my_share();
         return ib != RVB_NONE;
     }
-    __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
+    __device__ __forceinline__ bool occluded_to_mic(f3 pos, f3 dir, float mag, Counters &c) const
     {
         const BruteSmem one{s, T, nquads};
         bool blocked = false;
@@ -197,10 +198,18 @@ struct BruteSmemWarp {
 // Boxes are padded at build time and the slab test carries a relative slack, so no triangle the
 // exact test would accept at (t, index) better than the current best is ever culled; candidates
 // are compared lexicographically on (t, original index) to reproduce the in-order strict '<' loop.
+// Leaves are records of up to four triangles in the pair-interleaved form of the brute-force loop
+// (bvh.cu: fill_leaves_kernel): one burst of nine 16-byte loads, two packed tests.
+// Visibility queries towards the microphone go through the visibility map (micmap.cuh) when the
+// trace has one.
+#define RVB_SENTINEL ((int)0x80000000)   // bottom of the traversal stack; leaf refs are >= -2^30, inner nodes >= 0
+
 struct BvhAccel {
     const BvhNode *nodes;
-    const float4 *tri;       // sorted (v0,e0,e1)
-    const uint32_t *order;   // sorted position -> original index
+    const float4 *leaf_quads;   // [9 * n_leaves]
+    const uint4 *leaf_ids;      // [n_leaves]
+    const float4 *tri;          // [3T] (v0, e0, e1) in the callers' order: what the visibility map indexes
+    MicMap mm;
 
     __device__ __forceinline__ static bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, f3 o, f3 inv,
                                                 float tmax, float &tnear)
@@ -214,6 +223,16 @@ struct BvhAccel {
         // fminf/fmaxf drop NaNs (0 * inf on a face-parallel ray exactly on the slab plane), which
         // widens the interval: conservative.  1.00001f covers the rounding of the six products.
         return tn <= tf * 1.00001f + 1e-6f;
+    }
+
+    // 1/0 = inf is what the slab test wants for axis-parallel rays
+    __device__ __forceinline__ static f3 inverse_dir(f3 dir)
+    {
+        f3 inv = mk3(__fdividef(1.0f, dir.x), __fdividef(1.0f, dir.y), __fdividef(1.0f, dir.z));
+        if (dir.x == 0.0f) inv.x = RVB_INF;
+        if (dir.y == 0.0f) inv.y = RVB_INF;
+        if (dir.z == 0.0f) inv.z = RVB_INF;
+        return inv;
     }
 
     // One visit of a 4-wide node: test the four child boxes, continue with the nearest hit child
@@ -247,50 +266,64 @@ struct BvhAccel {
         return t0 < INF ? r0 : stack[--sp];
     }
 
+    // The (<= 4) triangles of one leaf record against the ray: the packed pair test of the
+    // brute-force loop (same per-lane operation sequence as mt_intersect_pred => same bits).
+    // Nearest: lexicographic (t, callers' index) minimum; ANY: is there a hit with EPS < t <= tlimit.
+    template <bool ANY>
+    __device__ __forceinline__ void leaf(int node, f3 pos, f3 dir, float tlimit, float &tbest, uint32_t &ibest, bool &found, uint32_t &ntri) const
+    {
+        const uint32_t ref = ~(uint32_t)node;
+        const uint32_t rec = ref & 0x0fffffffu;
+        ntri += (ref >> 28) + 1;
+        const float4 *r = leaf_quads + 9 * (size_t)rec;
+        const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5),
+                     r6 = __ldg(r + 6), r7 = __ldg(r + 7), r8 = __ldg(r + 8);
+        f3x2 v0a, e0a, e1a, v0b, e0b, e1b;
+        v0a.x = make_float2(r0.x, r0.y); v0a.y = make_float2(r0.z, r0.w); v0a.z = make_float2(r1.x, r1.y);
+        e0a.x = make_float2(r1.z, r1.w); e0a.y = make_float2(r2.x, r2.y); e0a.z = make_float2(r2.z, r2.w);
+        e1a.x = make_float2(r3.x, r3.y); e1a.y = make_float2(r3.z, r3.w); e1a.z = make_float2(r4.x, r4.y);
+        v0b.x = make_float2(r4.z, r4.w); v0b.y = make_float2(r5.x, r5.y); v0b.z = make_float2(r5.z, r5.w);
+        e0b.x = make_float2(r6.x, r6.y); e0b.y = make_float2(r6.z, r6.w); e0b.z = make_float2(r7.x, r7.y);
+        e1b.x = make_float2(r7.z, r7.w); e1b.y = make_float2(r8.x, r8.y); e1b.z = make_float2(r8.z, r8.w);
+        bool ok0, ok1, ok2, ok3;
+        const float2 ta = mt_intersect_pair(v0a, e0a, e1a, pos, dir, ok0, ok1);
+        const float2 tb = mt_intersect_pair(v0b, e0b, e1b, pos, dir, ok2, ok3);
+        ok0 = ok0 && ta.x > RVB_EPSILON; ok1 = ok1 && ta.y > RVB_EPSILON;
+        ok2 = ok2 && tb.x > RVB_EPSILON; ok3 = ok3 && tb.y > RVB_EPSILON;
+        if (ANY) {
+            found |= (ok0 && ta.x <= tlimit) | (ok1 && ta.y <= tlimit) | (ok2 && tb.x <= tlimit) | (ok3 && tb.y <= tlimit);
+        } else if (ok0 | ok1 | ok2 | ok3) {
+            const uint4 id = __ldg(leaf_ids + rec);
+            if (ok0 && (ta.x < tbest || (ta.x == tbest && id.x < ibest))) { tbest = ta.x; ibest = id.x; }
+            if (ok1 && (ta.y < tbest || (ta.y == tbest && id.y < ibest))) { tbest = ta.y; ibest = id.y; }
+            if (ok2 && (tb.x < tbest || (tb.x == tbest && id.z < ibest))) { tbest = tb.x; ibest = id.z; }
+            if (ok3 && (tb.y < tbest || (tb.y == tbest && id.w < ibest))) { tbest = tb.y; ibest = id.w; }
+        }
+    }
+
     template <bool ANY>
     __device__ __forceinline__ bool traverse(f3 pos, f3 dir, float tlimit, float &tbest, uint32_t &ibest, Counters &c) const
     {
-        // 1/0 = inf is what the slab test wants for axis-parallel rays
-        f3 inv = mk3(__fdividef(1.0f, dir.x), __fdividef(1.0f, dir.y), __fdividef(1.0f, dir.z));
-        if (dir.x == 0.0f) inv.x = RVB_INF;
-        if (dir.y == 0.0f) inv.y = RVB_INF;
-        if (dir.z == 0.0f) inv.z = RVB_INF;
+        const f3 inv = inverse_dir(dir);
         tbest = tlimit;
         ibest = RVB_NONE;
         // while-while traversal: every lane first walks inner nodes until it holds a leaf (or is
         // done), then the leaves are intersected together -- inner-node code and triangle code are
         // never interleaved inside a warp.
-        const int SENTINEL = (int)0x80000000;   // leaf refs are >= -2^30, inner nodes >= 0
-        int stack[64];
+        int stack[RVB_BVH_STACK];
         int sp = 0;
-        stack[sp++] = SENTINEL;
+        stack[sp++] = RVB_SENTINEL;
         int node = 0;
         uint32_t nbox = 0, ntri = 0;
         bool found = false;
-        while (node != SENTINEL) {
+        while (node != RVB_SENTINEL) {
             while (node >= 0) {
                 node = visit(nodes, node, pos, inv, tbest, stack, sp);
                 nbox += 4;
             }
-            while (node < 0 && node != SENTINEL) {
-                const uint32_t ref = ~(uint32_t)node;
-                const uint32_t first = ref & 0x0fffffffu, cnt = (ref >> 28) + 1;
-                for (uint32_t k = 0; k < cnt; ++k) {
-                    const uint32_t p = first + k;
-                    const float4 A = __ldg(tri + 3 * p), B = __ldg(tri + 3 * p + 1), C = __ldg(tri + 3 * p + 2);
-                    bool ok;
-                    const float t = mt_intersect_pred(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), mk3(B.z, B.w, C.x), pos, dir, ok);
-                    ++ntri;
-                    if (ok && t > RVB_EPSILON) {
-                        if (ANY) {
-                            if (t <= tlimit) found = true;
-                        } else {
-                            const uint32_t oi = __ldg(order + p);
-                            if (t < tbest || (t == tbest && oi < ibest)) { tbest = t; ibest = oi; }
-                        }
-                    }
-                }
-                node = (ANY && found) ? SENTINEL : stack[--sp];
+            while (node < 0 && node != RVB_SENTINEL) {
+                leaf<ANY>(node, pos, dir, tlimit, tbest, ibest, found, ntri);
+                node = (ANY && found) ? RVB_SENTINEL : stack[--sp];
             }
         }
         c.queries++; c.tri += ntri; c.box += nbox;
@@ -300,10 +333,48 @@ struct BvhAccel {
     {
         return traverse<false>(pos, dir, RVB_INF, tbest, ibest, c);
     }
-    __device__ __forceinline__ bool occluded(f3 pos, f3 dir, float mag, Counters &c) const
+    // any-hit traversal for traces without a visibility map; out of line so that the hot kernels do
+    // not carry a second traversal loop
+    __device__ __noinline__ static bool occluded_generic(const BvhNode *nodes, const float4 *leaf_quads, const uint4 *leaf_ids, f3 begin,
+                                                         f3 dir, float mag, Counters &c)
     {
+        const BvhAccel a{nodes, leaf_quads, leaf_ids, nullptr, MicMap{}};
         float t; uint32_t i;
-        return traverse<true>(pos, dir, mag, t, i, c);
+        return a.traverse<true>(begin, dir, mag, t, i, c);
+    }
+    // point_intersection(begin, mic) (kernel.cpp:274-296): dir = normalize(mic - begin), mag = |mic - begin|
+    __device__ __forceinline__ bool occluded_to_mic(f3 begin, f3 dir, float mag, Counters &c) const
+    {
+        if (mm.N == 0) return occluded_generic(nodes, leaf_quads, leaf_ids, begin, dir, mag, c);
+        bool blocked = false;
+        const f3 w = mk3(begin.x - mm.mic[0], begin.y - mm.mic[1], begin.z - mm.mic[2]);
+        const uint32_t cell = micmap_cell(w, mm.half_n, mm.N);
+        const uint32_t e0 = __ldg(mm.cell_off + cell), ne = __ldg(mm.cell_off + cell + 1) - e0;
+        const uint32_t ntri = ne + mm.n_near;
+        // Four candidates at a time: their index loads, then their triangle loads, are issued together
+        // (two memory latencies per group instead of two per triangle).  Past the end the last
+        // candidate is simply tested again -- the answer is an OR -- so every load is unconditional.
+        for (uint32_t k0 = 0; k0 < ntri; k0 += 4) {
+            const uint32_t ka = k0, kb = min(k0 + 1, ntri - 1), kc = min(k0 + 2, ntri - 1), kd = min(k0 + 3, ntri - 1);
+            const uint32_t ia = ka < ne ? __ldg(mm.cell_ent + e0 + ka) : __ldg(mm.near_ent + (ka - ne));
+            const uint32_t ib = kb < ne ? __ldg(mm.cell_ent + e0 + kb) : __ldg(mm.near_ent + (kb - ne));
+            const uint32_t ic = kc < ne ? __ldg(mm.cell_ent + e0 + kc) : __ldg(mm.near_ent + (kc - ne));
+            const uint32_t id = kd < ne ? __ldg(mm.cell_ent + e0 + kd) : __ldg(mm.near_ent + (kd - ne));
+            const float4 *pa = tri + 3 * (size_t)ia, *pb = tri + 3 * (size_t)ib, *pc = tri + 3 * (size_t)ic, *pd = tri + 3 * (size_t)id;
+            const float4 Aa = __ldg(pa), Ba = __ldg(pa + 1), Ab = __ldg(pb), Bb = __ldg(pb + 1);
+            const float4 Ac = __ldg(pc), Bc = __ldg(pc + 1), Ad = __ldg(pd), Bd = __ldg(pd + 1);
+            const float Ca = __ldg(reinterpret_cast<const float *>(pa + 2)), Cb = __ldg(reinterpret_cast<const float *>(pb + 2));
+            const float Cc = __ldg(reinterpret_cast<const float *>(pc + 2)), Cd = __ldg(reinterpret_cast<const float *>(pd + 2));
+            bool oka, okb, okc, okd;
+            const float ta = mt_intersect_pred(mk3(Aa.x, Aa.y, Aa.z), mk3(Aa.w, Ba.x, Ba.y), mk3(Ba.z, Ba.w, Ca), begin, dir, oka);
+            const float tb = mt_intersect_pred(mk3(Ab.x, Ab.y, Ab.z), mk3(Ab.w, Bb.x, Bb.y), mk3(Bb.z, Bb.w, Cb), begin, dir, okb);
+            const float tc = mt_intersect_pred(mk3(Ac.x, Ac.y, Ac.z), mk3(Ac.w, Bc.x, Bc.y), mk3(Bc.z, Bc.w, Cc), begin, dir, okc);
+            const float td = mt_intersect_pred(mk3(Ad.x, Ad.y, Ad.z), mk3(Ad.w, Bd.x, Bd.y), mk3(Bd.z, Bd.w, Cd), begin, dir, okd);
+            blocked |= (oka && ta > RVB_EPSILON && ta <= mag) | (okb && tb > RVB_EPSILON && tb <= mag)
+                     | (okc && tc > RVB_EPSILON && tc <= mag) | (okd && td > RVB_EPSILON && td <= mag);
+        }
+        c.queries++; c.tri += ntri;
+        return blocked;
     }
 };
 
@@ -349,14 +420,15 @@ __device__ __forceinline__ void air_attenuation(float distance, const float *air
     }
 }
 
-// kernel.cpp:274-296
+// kernel.cpp:274-296.  Every call site of the reference passes the microphone as `point`
+// (:335, :431, :463), which is what lets the BVH path answer from the visibility map.
 template <class Accel>
 __device__ __forceinline__ bool point_visible(const Accel &acc, f3 begin, f3 point, Counters &c)
 {
     f3 btp = point - begin;
     float mag = length(btp);
     f3 dir = normalize(btp);
-    return !acc.occluded(begin, dir, mag, c);
+    return !acc.occluded_to_mic(begin, dir, mag, c);
 }
 
 // TriVerts with its normal cached: triangle_verts_normal (kernel.cpp:110-116) is a pure function
@@ -436,6 +508,7 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
     P.pt[slot] = make_float4(X.x, X.y, X.z, time);
     P.tkey[slot] = any ? time : -1.0f;
     if (any) {
+        c.emitted++;
         if (time != 0.0f) c.tmin_nz = fminf(c.tmin_nz, time);
         c.tmax = fmaxf(c.tmax, time);
     }
@@ -575,16 +648,17 @@ __device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TracePa
 __device__ __forceinline__ void flush_counters(const TraceParams &P, const Counters &c)
 {
     // warp-aggregate, then one atomic per warp (integer adds: order-independent)
-    unsigned long long q = c.queries, t = c.tri, b = c.box, n = c.bounces;
+    unsigned long long q = c.queries, t = c.tri, b = c.box, n = c.bounces, em = c.emitted;
     float mn = c.tmin_nz, mx = c.tmax;
     for (int o = 16; o; o >>= 1) {
         q += __shfl_down_sync(0xffffffffu, q, o); t += __shfl_down_sync(0xffffffffu, t, o);
         b += __shfl_down_sync(0xffffffffu, b, o); n += __shfl_down_sync(0xffffffffu, n, o);
+        em += __shfl_down_sync(0xffffffffu, em, o);
         mn = fminf(mn, __shfl_down_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(P.counters + 0, q); atomicAdd(P.counters + 1, t);
-        atomicAdd(P.counters + 2, b); atomicAdd(P.counters + 3, n);
+        atomicAdd(P.counters + 2, b); atomicAdd(P.counters + 3, n); atomicAdd(P.counters + 5, em);
         // order-preserving integer keys: min / max are order-independent, so this is deterministic
         atomicMin(P.time_ext, ordered_key(mn)); atomicMax(P.time_ext + 1, ordered_key(mx));
     }
@@ -658,7 +732,7 @@ __global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceP
 template <bool IMAGES, int MINB>
 __global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams P)
 {
-    BvhAccel acc{P.nodes, P.tri_sorted, P.order};
+    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap};
     Counters c;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrays; i += gridDim.x * blockDim.x) {
         if (IMAGES) image_phase_ray(acc, P, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, i, c);
@@ -773,77 +847,125 @@ static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
 }
 
 // =================================================================================================
-// Wavefront form of the steady phase for the BVH path.
+// Persistent wavefront form of the steady phase for the BVH path.
 //
-// Thread-per-ray traversal leaves most lanes idle: traversal lengths differ from ray to ray and a
-// warp runs until its slowest lane is done (ncu: 10.8 of 32 threads active per instruction).  Here
-// every reflection is three launches over the ray-state records in HBM:
-//   wf_traverse<false>  persistent warps, dynamic ray fetch: a lane that finishes its query pulls
-//                       the next ray from a global counter, so lanes stay busy; nearest hit
-//   wf_traverse<true>   same, any-hit visibility query from the hit point to the microphone
-//   wf_emit             one thread per ray: shade, emit the impulse, reflect (kernel.cpp:459-501)
-// The arithmetic is the same device code as the per-ray kernels (same bits).
+// Thread-per-ray traversal leaves most lanes idle: traversal lengths differ from ray to ray and the
+// lanes of a warp wait for the slowest one at the end of EVERY query (ncu, round 1: 13 of 32 threads
+// active per instruction).  Here a warp is a persistent worker whose lanes are independent state
+// machines that only share the instruction stream:
+//
+//   serve     lanes whose nearest-hit query is complete shade it (visibility through the microphone
+//             map, emit the impulse, reflect: kernel.cpp:459-501) and begin the next reflection's
+//             query; a ray that has left the mesh (kernel.cpp:372-375) or finished its last
+//             reflection frees its lane
+//   refill    free lanes pull the next ray from a global counter (one atomic per warp): terminated
+//             rays are compacted away and the warp stays full until the ray set is exhausted
+//   traverse  while-while over the 4-wide BVH, all lanes with a pending query; the warp goes back to
+//             `serve` once RVB_WF_SERVICE lanes are waiting (or nobody is traversing)
+//
+// The arithmetic of a ray is the same device code as in the per-ray kernel (same bits); every ray
+// owns its output slots, so the order in which lanes pick up rays does not show in the results.
 // =================================================================================================
-struct WfParams {
-    TraceParams P;
-    float4 *hit;              // [nrays] x = t, y = triangle (bits), z = blocked (0/1)
-    unsigned int *fetch;      // one work counter per launch
+#define RVB_WF_SERVICE 8      // lanes that must be waiting before the warp leaves the traversal loop
+
+// Per-lane state that only the `serve` step touches (band volumes, path length, ray id, counters)
+// lives in shared memory so that the traversal loop keeps a small register set:
+// [k][thread] -- conflict-free.
+struct WfShared {
+    float volume[RVB_NBANDS][128];
+    float distance[128], tmin_nz[128], tmax[128];
+    uint32_t ray[128], index[128], queries[128], bounces[128], emitted[128], tri[128];
 };
 
-#define RVB_WF_REFETCH 20     // go back for more rays when fewer lanes than this are still traversing
-
-template <bool ANY>
-__global__ void __launch_bounds__(128) wf_traverse_kernel(const WfParams W)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const TraceParams P, unsigned int *fetch)
 {
-    const TraceParams &P = W.P;
+    __shared__ WfShared S;
     const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31;
-    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
-    const int SENTINEL = (int)0x80000000;
-    int stack[64];
-    int sp = 0, node = SENTINEL;
-    bool has = false, exhausted = false, found = false;
-    uint32_t ray = 0, ibest = RVB_NONE, nbox = 0, ntri = 0, nq = 0;
-    float tbest = 0.f, tlimit = 0.f;
+    const unsigned lane = threadIdx.x & 31u, tid = threadIdx.x;
+    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap};
+    int stack[RVB_BVH_STACK];
+    int sp = 0, node = RVB_SENTINEL;
+    bool has = false, exhausted = false;
+    uint32_t ibest = RVB_NONE, nbox = 0, ntri = 0;
+    float tbest = RVB_INF;
     f3 pos = mk3(0.f, 0.f, 0.f), dir = pos, inv = pos;
+    S.tmin_nz[tid] = RVB_INF; S.tmax[tid] = 0.0f;
+    S.queries[tid] = 0; S.bounces[tid] = 0; S.emitted[tid] = 0; S.tri[tid] = 0;
 
     while (true) {
-        // ---- refill idle lanes ---------------------------------------------------------------
+        // ---- serve: completed queries -------------------------------------------------------
+        if (has && node == RVB_SENTINEL) {
+            const uint32_t ray = S.ray[tid];
+            uint32_t index = S.index[tid];
+            bool more = false;
+            if (ibest != RVB_NONE) {
+                const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+                RayState R;
+                R.pos = pos; R.dir = dir; R.distance = S.distance[tid];
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS / 2; ++b) R.volume[b] = make_float2(S.volume[2 * b][tid], S.volume[2 * b + 1][tid]);
+                Counters c;
+                c.tmin_nz = S.tmin_nz[tid]; c.tmax = S.tmax[tid];
+                shade_and_reflect(acc, P, mic, ray, index, tbest, ibest, R, c);
+                pos = R.pos; dir = R.dir; S.distance[tid] = R.distance;
+#pragma unroll
+                for (int b = 0; b < RVB_NBANDS / 2; ++b) { S.volume[2 * b][tid] = R.volume[b].x; S.volume[2 * b + 1][tid] = R.volume[b].y; }
+                S.tmin_nz[tid] = c.tmin_nz; S.tmax[tid] = c.tmax;
+                S.queries[tid] += 1u + c.queries; S.emitted[tid] += c.emitted; S.tri[tid] += (uint32_t)c.tri;
+                ++index;
+                more = index != P.last;
+            } else {
+                S.queries[tid] += 1u;
+                zero_fill(P, ray, index);                                    // left the mesh, kernel.cpp:372-375
+            }
+            if (more) {
+                S.index[tid] = index;
+                inv = BvhAccel::inverse_dir(dir);
+                tbest = RVB_INF; ibest = RVB_NONE;
+                sp = 0; stack[sp++] = RVB_SENTINEL; node = 0;
+            } else {
+                S.bounces[tid] += index - P.first;
+                if (P.count) P.count[ray] = (P.first ? P.count[ray] : 0u) + (index - P.first);
+                has = false;
+            }
+        }
+        // ---- refill: free lanes take the next rays -----------------------------------------------
         bool want = !has && !exhausted;
         while (true) {
             const unsigned m = __ballot_sync(FULL, want);
             if (!m) break;
             const int leader = __ffs(m) - 1;
             unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(W.fetch, (unsigned)__popc(m));
+            if ((int)lane == leader) base = atomicAdd(fetch, (unsigned)__popc(m));
             base = __shfl_sync(FULL, base, leader);
             if (want) {
                 const uint32_t r = base + __popc(m & ((1u << lane) - 1u));
                 if (r >= P.nrays) { want = false; exhausted = true; }
                 else {
-                    const float4 s0 = P.state[4 * (size_t)r], s1 = P.state[4 * (size_t)r + 1];
-                    bool live = s1.w != 0.0f;
-                    f3 o = mk3(s0), d = mk3(s1);
-                    float lim = RVB_INF;
-                    if (ANY && live) {   // visibility from the hit point to the microphone (kernel.cpp:274-296)
-                        const float4 h = W.hit[r];
-                        live = __float_as_uint(h.y) != RVB_NONE;
+                    bool live = true;
+                    if (P.first == 0) {
+                        pos = mk3(P.src[0], P.src[1], P.src[2]);
+                        dir = mk3(__ldg(P.dirs + r));
+                        S.distance[tid] = 0.0f;
+#pragma unroll
+                        for (int b = 0; b < RVB_NBANDS; ++b) S.volume[b][tid] = 1.0f;
+                    } else {
+                        const float4 *s = P.state + 4 * (size_t)r;
+                        const float4 a = s[0], d = s[1];
+                        live = d.w != 0.0f;   // dead: left the mesh during the image phase (slots already zero-filled)
                         if (live) {
-                            const f3 X = madd(o, d, h.x);
-                            const f3 btp = mic - X;
-                            lim = length(btp);
-                            d = normalize(btp);
-                            o = X;
+                            const float4 va = s[2], vb = s[3];
+                            pos = mk3(a); dir = mk3(d); S.distance[tid] = a.w;
+                            S.volume[0][tid] = va.x; S.volume[1][tid] = va.y; S.volume[2][tid] = va.z; S.volume[3][tid] = va.w;
+                            S.volume[4][tid] = vb.x; S.volume[5][tid] = vb.y; S.volume[6][tid] = vb.z; S.volume[7][tid] = vb.w;
                         }
                     }
                     if (live) {
-                        ray = r; pos = o; dir = d; tlimit = lim;
-                        inv = mk3(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
-                        if (d.x == 0.0f) inv.x = RVB_INF;
-                        if (d.y == 0.0f) inv.y = RVB_INF;
-                        if (d.z == 0.0f) inv.z = RVB_INF;
-                        tbest = lim; ibest = RVB_NONE; found = false;
-                        sp = 0; stack[sp++] = SENTINEL; node = 0;
+                        S.ray[tid] = r; S.index[tid] = P.first;
+                        inv = BvhAccel::inverse_dir(dir);
+                        tbest = RVB_INF; ibest = RVB_NONE;
+                        sp = 0; stack[sp++] = RVB_SENTINEL; node = 0;
                         has = true; want = false;
                     }
                     // dead rays are skipped: keep asking
@@ -852,136 +974,56 @@ __global__ void __launch_bounds__(128) wf_traverse_kernel(const WfParams W)
         }
         if (!__any_sync(FULL, has)) break;
 
-        // ---- traverse (same loops as BvhAccel::traverse) -------------------------------------------
-        while (node != SENTINEL) {
-            while (node >= 0) {
-                node = BvhAccel::visit(P.nodes, node, pos, inv, tbest, stack, sp);
-                nbox += 4;
+        // ---- traverse ------------------------------------------------------------------------------
+        while (true) {
+            while (true) {                                   // inner nodes, until no lane holds one
+                const bool in = has && node >= 0;
+                if (!__any_sync(FULL, in)) break;
+                if (in) { node = BvhAccel::visit(P.nodes, node, pos, inv, tbest, stack, sp); nbox += 4; }
             }
-            while (node < 0 && node != SENTINEL) {
-                const uint32_t ref = ~(uint32_t)node;
-                const uint32_t first = ref & 0x0fffffffu, cnt = (ref >> 28) + 1;
-                for (uint32_t k = 0; k < cnt; ++k) {
-                    const uint32_t p = first + k;
-                    const float4 A = __ldg(P.tri_sorted + 3 * p), B = __ldg(P.tri_sorted + 3 * p + 1), C = __ldg(P.tri_sorted + 3 * p + 2);
-                    bool ok;
-                    const float t = mt_intersect_pred(mk3(A.x, A.y, A.z), mk3(A.w, B.x, B.y), mk3(B.z, B.w, C.x), pos, dir, ok);
-                    ++ntri;
-                    if (ok && t > RVB_EPSILON) {
-                        if (ANY) {
-                            if (t <= tlimit) found = true;
-                        } else {
-                            const uint32_t oi = __ldg(P.order + p);
-                            if (t < tbest || (t == tbest && oi < ibest)) { tbest = t; ibest = oi; }
-                        }
-                    }
-                }
-                node = (ANY && found) ? SENTINEL : stack[--sp];
+            if (has && node != RVB_SENTINEL) {               // one leaf per lane
+                bool found = false;
+                acc.leaf<false>(node, pos, dir, RVB_INF, tbest, ibest, found, ntri);
+                node = stack[--sp];
             }
-            if (__popc(__activemask()) < RVB_WF_REFETCH) break;   // heuristic only: results do not depend on it
-        }
-        if (has && node == SENTINEL) {
-            float4 h = ANY ? W.hit[ray] : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ANY) h.z = found ? 1.0f : 0.0f;
-            else { h.x = tbest; h.y = __uint_as_float(ibest); }
-            W.hit[ray] = h;
-            has = false;
-            ++nq;
+            const bool trav = has && node != RVB_SENTINEL;
+            const unsigned mt = __ballot_sync(FULL, trav);
+            const unsigned ms = __ballot_sync(FULL, (has && !trav) || (!has && !exhausted));
+            if (mt == 0u || __popc(ms) >= RVB_WF_SERVICE) break;
         }
     }
     Counters c;
-    c.queries = nq; c.tri = ntri; c.box = nbox;
+    c.queries = S.queries[tid]; c.bounces = S.bounces[tid]; c.emitted = S.emitted[tid];
+    c.tri = (unsigned long long)S.tri[tid] + ntri; c.box = nbox;
+    c.tmin_nz = S.tmin_nz[tid]; c.tmax = S.tmax[tid];
     flush_counters(P, c);
 }
 
-// the visibility answer was computed by wf_traverse<true>
-struct KnownVisibility {
-    bool blocked;
-    __device__ __forceinline__ bool occluded(f3, f3, float, Counters &) const { return blocked; }
-};
-
-__global__ void __launch_bounds__(256) wf_emit_kernel(const WfParams W)
+static int launch_wavefront(const TraceParams &P, cudaStream_t st)
 {
-    const TraceParams &P = W.P;
-    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
-    Counters c;
-    if (ray < P.nrays) {
-        const uint32_t index = P.first;
-        float4 *s = P.state + 4 * (size_t)ray;
-        const float4 a = s[0], d = s[1];
-        bool alive = d.w != 0.0f;
-        uint32_t prim = RVB_NONE;
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (alive) {
-            h = W.hit[ray];
-            prim = __float_as_uint(h.y);
-            if (prim == RVB_NONE) { alive = false; s[1] = make_float4(d.x, d.y, d.z, 0.0f); }   // left the mesh (kernel.cpp:372-375)
-        }
-        if (!alive) {
-            // zero impulse in this slot (rayverb.cpp:601-603)
-            const size_t slot = slot_of(ray, index, P.nrays);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            P.vol[2 * slot] = z; P.vol[2 * slot + 1] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
-            if (P.hit) P.hit[slot] = RVB_NONE;
-        } else {
-            const float4 va = s[2], vb = s[3];
-            RayState R;
-            R.pos = mk3(a); R.distance = a.w; R.dir = mk3(d);
-            R.volume[0] = make_float2(va.x, va.y); R.volume[1] = make_float2(va.z, va.w);
-            R.volume[2] = make_float2(vb.x, vb.y); R.volume[3] = make_float2(vb.z, vb.w);
-            const KnownVisibility vis{h.z != 0.0f};
-            const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
-            shade_and_reflect(vis, P, mic, ray, index, h.x, prim, R, c);
-            store_state(P, ray, R, true);
-            c.bounces = 1;
-            if (P.count) P.count[ray] += 1;
-        }
+    static const int minb = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 6;
+    unsigned int *d_fetch = nullptr;
+    RVB_TRY(dev_alloc(&d_fetch, 1));
+    RVB_CUDA(cudaMemsetAsync(d_fetch, 0, sizeof(unsigned int), st));
+    auto go = [&](auto kernel) -> int {
+        int per_sm = 0;
+        RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0));
+        const size_t want = ((size_t)P.nrays + 127) / 128;
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min(want, (size_t)std::max(per_sm, 1) * sm_count()));
+        note_launch(), kernel<<<grid, 128, 0, st>>>(P, d_fetch);
+        RVB_CUDA(cudaGetLastError());
+        return RVB_OK;
+    };
+    int rc;
+    switch (minb) {
+    case 4: rc = go(trace_bvh_wavefront_kernel<4>); break;
+    case 5: rc = go(trace_bvh_wavefront_kernel<5>); break;
+    case 7: rc = go(trace_bvh_wavefront_kernel<7>); break;
+    case 8: rc = go(trace_bvh_wavefront_kernel<8>); break;
+    default: rc = go(trace_bvh_wavefront_kernel<6>); break;
     }
-    c.queries = 0;
-    flush_counters(P, c);
-}
-
-// reflections [first, last) of the BVH path, three launches each
-static int launch_wavefront(TraceParams P, uint32_t first, uint32_t last, bool fresh, cudaStream_t st)
-{
-    WfParams W{};
-    W.P = P;
-    const uint32_t nb = last - first;
-    RVB_TRY(dev_alloc(&W.hit, (size_t)P.nrays));
-    RVB_TRY(dev_alloc(&W.fetch, 2 * (size_t)nb));
-    RVB_CUDA(cudaMemsetAsync(W.fetch, 0, 2 * (size_t)nb * sizeof(unsigned), st));
-    unsigned *fetch0 = W.fetch;
-    int per_sm = 0;
-    RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_traverse_kernel<false>, 128, 0));
-    const unsigned tgrid = (unsigned)std::min<size_t>(((size_t)P.nrays + 127) / 128, (size_t)std::max(per_sm, 1) * sm_count());
-    const unsigned egrid = (unsigned)(((size_t)P.nrays + 255) / 256);
-    (void)fresh;
-    for (uint32_t b = first; b < last; ++b) {
-        W.P.first = b; W.P.last = b + 1;
-        W.fetch = fetch0 + 2 * (b - first);
-        note_launch(), wf_traverse_kernel<false><<<tgrid, 128, 0, st>>>(W);
-        W.fetch = fetch0 + 2 * (b - first) + 1;
-        note_launch(), wf_traverse_kernel<true><<<tgrid, 128, 0, st>>>(W);
-        note_launch(), wf_emit_kernel<<<egrid, 256, 0, st>>>(W);
-    }
-    RVB_CUDA(cudaGetLastError());
-    W.fetch = fetch0;
-    dev_free(W.hit); dev_free(W.fetch);
-    return RVB_OK;
-}
-
-// ray state for a trace that starts in the steady phase (RVB_TRACE_NO_IMAGES)
-__global__ void wf_init_state_kernel(const TraceParams P)
-{
-    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= P.nrays) return;
-    const float4 d = __ldg(P.dirs + ray);
-    float4 *s = P.state + 4 * (size_t)ray;
-    s[0] = make_float4(P.src[0], P.src[1], P.src[2], 0.0f);
-    s[1] = make_float4(d.x, d.y, d.z, 1.0f);
-    s[2] = make_float4(1.f, 1.f, 1.f, 1.f);
-    s[3] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (P.count) P.count[ray] = 0;
+    dev_free(d_fetch);
+    return rc;
 }
 
 int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB, float4 *d_cand_pt,
@@ -991,7 +1033,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     cudaStream_t st = lib_stream();
     TraceParams P{};
     P.verts = sc->d_verts; P.tri = sc->d_tri; P.quad = sc->d_quad; P.nquads = sc->nquads; P.nrm = sc->d_nrm; P.surfaces = sc->d_surfaces; P.T = sc->T;
-    P.nodes = sc->d_nodes; P.tri_sorted = sc->d_tri_sorted; P.order = sc->d_order;
+    P.nodes = sc->d_nodes; P.leaf_quads = sc->d_leaf_quads; P.leaf_ids = sc->d_leaf_ids;
     P.dirs = d_dirs; P.nrays = (uint32_t)tr->nrays; P.nrefl = (uint32_t)tr->nrefl; P.ray_offset = tr->ray_offset;
     for (int i = 0; i < 3; ++i) { P.mic[i] = tr->mic[i]; P.src[i] = tr->src[i]; }
     // AIR_COEFFICIENT: doubles narrowed to float (rayverb.cpp:632-641)
@@ -1003,9 +1045,9 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     P.cand_volA = d_cand_volA; P.cand_volB = d_cand_volB; P.cand_pt = d_cand_pt; P.cand_idx = d_cand_idx;
     P.flags = tr->flags;
     unsigned long long *d_counters = nullptr;
-    RVB_TRY(dev_alloc(&d_counters, 5));
+    RVB_TRY(dev_alloc(&d_counters, 6));
     {   // [4] holds the two ordered time keys: ordered(+inf), ordered(0)
-        const unsigned long long init[5] = {0, 0, 0, 0, 0x000000007f800000ull};
+        const unsigned long long init[6] = {0, 0, 0, 0, 0x000000007f800000ull, 0};
         RVB_CUDA(cudaMemcpyAsync(d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
     }
     P.counters = d_counters;
@@ -1015,11 +1057,10 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
     float4 *d_state = nullptr;
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
-    // The wavefront form (see launch_wavefront) measured SLOWER than one thread per ray on B200
-    // (C3, 1 Mi rays: 126 ms vs 106 ms): the traversal is bound by dependent L1/L2 round trips, not
-    // by idle lanes.  It stays available for experiments behind RVB_WAVEFRONT=1.
-    static const bool wavefront = getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '1';
-    if (split < tr->nrefl && (split > 0 || (!brute && wavefront))) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
+    // BVH scenes: the steady phase runs as the persistent wavefront kernel (launch_wavefront);
+    // RVB_WAVEFRONT=0 selects the one-thread-per-ray kernel for comparison.
+    static const bool wavefront = !(getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '0');
+    if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
     P.state = d_state;
     const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : 0;
 
@@ -1041,11 +1082,17 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
     RVB_CUDA(cudaEventCreate(&em));
-    unsigned long long *h_pin = nullptr;   // [0..5) final counters, [5..9) counters after the image phase
-    RVB_TRY(pinned_scratch(reinterpret_cast<void **>(&h_pin), 9 * sizeof(unsigned long long)));
-    for (int i = 0; i < 9; ++i) h_pin[i] = 0;
-    unsigned long long *hm = h_pin + 5;
+    unsigned long long *h_pin = nullptr;   // [0..6) final counters, [6..10) counters after the image phase
+    RVB_TRY(pinned_scratch(reinterpret_cast<void **>(&h_pin), 10 * sizeof(unsigned long long)));
+    for (int i = 0; i < 10; ++i) h_pin[i] = 0;
+    unsigned long long *hm = h_pin + 6;
     RVB_CUDA(cudaEventRecord(e0, st));
+    // BVH scenes: the visibility map around this trace's microphone (rebuilt for every trace: it is
+    // part of the measured work, not a cache)
+    MicMapStorage mm;
+    if (!brute && tr->nrays > 0) RVB_TRY(micmap_build(sc, tr->mic, &mm));
+    P.micmap = mm.map;
+    tr->stats.micmap_cells = mm.map.N; tr->stats.micmap_entries = mm.entries;
     RVB_CUDA(cudaEventRecord(em, st));
     if (tr->nrays > 0 && tr->nrefl > 0) {
         if (split > 0) {
@@ -1058,18 +1105,8 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
             if (brute) RVB_TRY(launch_bruteforce<false>(P, smem, st));
-            else if (!wavefront) {
-                // 7 CTAs of 128 threads per SM (<= 72 registers, a few spills) measured fastest on
-                // the C3 hall: 26.6 ms per 262 k rays against 29.1 (93 registers, 5 CTAs), 28.0 (8 CTAs),
-                // 28.6 (10) and 36.2 (12) -- gpurun_out/sweep_bvh.log
-                RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, 0, st));
-            }
-            else {
-                if (split == 0) {
-                    note_launch(), wf_init_state_kernel<<<(unsigned)((tr->nrays + 255) / 256), 256, 0, st>>>(P);
-                }
-                RVB_TRY(launch_wavefront(P, split, (uint32_t)tr->nrefl, split == 0, st));
-            }
+            else if (!wavefront) RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, 0, st));
+            else RVB_TRY(launch_wavefront(P, st));
         }
     } else if (tr->nrays > 0 && images && tr->ray_offset == 0) {
         // zero reflections: the reference still computes the direct path for ray 0
@@ -1079,7 +1116,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     }
     RVB_CUDA(cudaEventRecord(e1, st));
     unsigned long long *h = h_pin;
-    RVB_CUDA(cudaMemcpyAsync(h, d_counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaMemcpyAsync(h, d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f, ms_image = 0.f, ms_steady = 0.f;
     RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -1090,6 +1127,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     tr->stats.steady_tri_tests = h[1] - hm[1]; tr->stats.steady_box_tests = h[2] - hm[2];
     dev_free(d_counters);
     dev_free(d_state);
+    micmap_free(&mm);
     for (int i = 0; i < 2; ++i) { dev_free(d_perm_keys[i]); dev_free(d_perm_ids[i]); }
     dev_free(d_perm_tmp);
     {
@@ -1100,6 +1138,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         tr->has_time_ext = true;
     }
     tr->stats.queries = h[0]; tr->stats.tri_tests = h[1]; tr->stats.box_tests = h[2]; tr->stats.bounces = h[3];
+    tr->stats.emitted = h[5];
     tr->stats.trace_kernel_ms = ms;
     return RVB_OK;
 }

@@ -31,7 +31,9 @@ class TraceStats(C.Structure):
     _fields_ = [("nrays", C.c_uint64), ("nreflections", C.c_uint64), ("tri_tests", C.c_uint64),
                 ("box_tests", C.c_uint64), ("queries", C.c_uint64), ("bounces", C.c_uint64),
                 ("trace_kernel_ms", C.c_float), ("total_ms", C.c_float), ("image_phase_ms", C.c_float),
-                ("steady_phase_ms", C.c_float), ("steady_tri_tests", C.c_uint64), ("steady_box_tests", C.c_uint64)]
+                ("steady_phase_ms", C.c_float), ("steady_tri_tests", C.c_uint64), ("steady_box_tests", C.c_uint64),
+                ("emitted", C.c_uint64), ("micmap_entries", C.c_uint64), ("micmap_cells", C.c_uint32),
+                ("reserved_", C.c_uint32)]
 
 
 class RenderStats(C.Structure):

@@ -124,6 +124,41 @@ def displaced_box(lx, ly, lz, target_triangles, amp=0.05, fan=0.0, nsurfaces=1, 
     return tri, vtx
 
 
+def _box_mesh(lo, hi, n):
+    """Closed axis-aligned box [lo, hi], every face an n x n quad grid (12 n^2 triangles)."""
+    lo = np.asarray(lo, dtype=np.float64); hi = np.asarray(hi, dtype=np.float64)
+    d = hi - lo
+    ex, ey, ez = np.array([d[0], 0, 0]), np.array([0, d[1], 0]), np.array([0, 0, d[2]])
+    faces_spec = [(lo, ey, ez), (lo + ex, ey, ez), (lo, ex, ez), (lo + ey, ex, ez), (lo, ex, ey), (lo + ez, ex, ey)]
+    verts, faces, base = [], [], 0
+    ident = lambda p: p  # noqa: E731
+    for o, du, dv in faces_spec:
+        p, f = _grid_face(o, du, dv, n, n, (0, 0, 0), 0.0, 1, 1, ident)
+        verts.append(p); faces.append(f + base); base += len(p)
+    return np.concatenate(verts), np.concatenate(faces)
+
+
+def pillar_room(target_triangles=4000, npillars=6, pillar_grid=6):
+    """A displaced box with free-standing pillars between typical source / microphone positions:
+    unlike the closed halls, many hit points here do NOT see the microphone (occluded visibility
+    queries, kernel.cpp:463-471) and rays reach the pillars from all sides."""
+    room_tris = max(200, target_triangles - npillars * 12 * pillar_grid * pillar_grid)
+    tri, vtx = displaced_box(16.0, 6.0, 12.0, room_tris, amp=0.06, fan=0.15, nsurfaces=4)
+    verts = [vtx[:, :3].astype(np.float64)]
+    faces = [np.stack([tri["v0"], tri["v1"], tri["v2"]], 1).astype(np.int64)]
+    sids = [tri["surface"].astype(np.int64)]
+    base = len(vtx)
+    for k in range(npillars):
+        cx = 3.0 + 2.0 * k
+        cz = 4.0 + (1.7 * k) % 4.5
+        w = 0.35 + 0.05 * (k % 3)
+        p, f = _box_mesh((cx - w, 0.02, cz - w), (cx + w, 5.2 - 0.3 * (k % 2), cz + w), pillar_grid)
+        verts.append(p); faces.append(f + base); base += len(p)
+        sids.append(np.full(len(f), (k + 1) % 4, dtype=np.int64))
+    t, v = _pack(np.concatenate(verts), np.concatenate(faces), np.concatenate(sids))
+    return t, v, hall_surfaces()
+
+
 def hall_surfaces():
     """Four surfaces in the value ranges of the shipped material files (specular 0.12-0.99,
     diffuse 0.6-0.99)."""
