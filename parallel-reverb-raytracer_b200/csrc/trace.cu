@@ -57,6 +57,7 @@ struct TraceParams {
     float4 *state;            // [4*nrays] (pos, distance) (dir, alive) volA volB
     float4 *cand_volA, *cand_volB, *cand_pt;   // [nrays*10] image-source candidates
     uint32_t *cand_idx;                        // [nrays*10] triangle+1, 0 = none (pre-zeroed)
+    uint32_t wf_service, wf_leaf_min;          // wavefront kernel: lanes that must wait before `serve` / hold a leaf before the triangle step
     unsigned long long *counters;              // [0] queries [1] tri tests [2] box tests [3] bounces [5] emitted impulses
     int *time_ext;                             // [0] ordered min non-zero, [1] ordered max time of the emitted diffuse impulses
     uint32_t flags;
@@ -211,33 +212,36 @@ struct BvhAccel {
     const float4 *tri;          // [3T] (v0, e0, e1) in the callers' order: what the visibility map indexes
     MicMap mm;
 
-    __device__ __forceinline__ static bool slab(float lox, float loy, float loz, float hix, float hiy, float hiz, f3 o, f3 inv,
-                                                float tmax, float &tnear)
+    // Per-query constants of the slab test: t = plane * inv + oinv with oinv = -origin * inv (one fma
+    // per plane).  |inv| is clamped to 1e30 so that an axis-parallel ray gives huge finite values of
+    // the right sign instead of inf - inf; the rounding of the fma form moves a plane by ~6e-8 * |origin|,
+    // three orders of magnitude less than the padding of the boxes.
+    struct SlabRay { f3 inv, oinv; };
+    __device__ __forceinline__ static SlabRay slab_ray(f3 pos, f3 dir)
     {
-        float tx0 = (lox - o.x) * inv.x, tx1 = (hix - o.x) * inv.x;
-        float ty0 = (loy - o.y) * inv.y, ty1 = (hiy - o.y) * inv.y;
-        float tz0 = (loz - o.z) * inv.z, tz1 = (hiz - o.z) * inv.z;
-        float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-        float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-        tnear = tn;
-        // fminf/fmaxf drop NaNs (0 * inf on a face-parallel ray exactly on the slab plane), which
-        // widens the interval: conservative.  1.00001f covers the rounding of the six products.
-        return tn <= tf * 1.00001f + 1e-6f;
+        SlabRay r;
+        r.inv = mk3(fminf(fmaxf(__fdividef(1.0f, dir.x), -1e30f), 1e30f), fminf(fmaxf(__fdividef(1.0f, dir.y), -1e30f), 1e30f),
+                    fminf(fmaxf(__fdividef(1.0f, dir.z), -1e30f), 1e30f));
+        if (dir.x == 0.0f) r.inv.x = 1e30f;   // 1/0 = inf is clamped by fminf, but 1/-0 and NaN are not worth a thought: be explicit
+        if (dir.y == 0.0f) r.inv.y = 1e30f;
+        if (dir.z == 0.0f) r.inv.z = 1e30f;
+        r.oinv = mk3(-pos.x * r.inv.x, -pos.y * r.inv.y, -pos.z * r.inv.z);
+        return r;
     }
 
-    // 1/0 = inf is what the slab test wants for axis-parallel rays
-    __device__ __forceinline__ static f3 inverse_dir(f3 dir)
+    // entry distance of one child box (inf when missed); the six plane distances are already computed
+    __device__ __forceinline__ static float slab_hit(float tx0, float tx1, float ty0, float ty1, float tz0, float tz1, float lim)
     {
-        f3 inv = mk3(__fdividef(1.0f, dir.x), __fdividef(1.0f, dir.y), __fdividef(1.0f, dir.z));
-        if (dir.x == 0.0f) inv.x = RVB_INF;
-        if (dir.y == 0.0f) inv.y = RVB_INF;
-        if (dir.z == 0.0f) inv.z = RVB_INF;
-        return inv;
+        const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+        const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), lim));
+        // 1.00001f covers the rounding of the plane distances; NaNs are dropped by fminf / fmaxf, which widens the interval
+        return tn <= tf * 1.00001f + 1e-6f ? tn : RVB_INF;
     }
 
-    // One visit of a 4-wide node: test the four child boxes, continue with the nearest hit child
-    // and push the others so that the nearer ones are popped first.  Returns the next node.
-    __device__ __forceinline__ static int visit(const BvhNode *nodes, int node, f3 pos, f3 inv, float tbest, int *stack, int &sp)
+    // One visit of a 4-wide node: test the four child boxes (two children per packed fma), continue
+    // with the nearest hit child and push the others so that the nearer ones are popped first.
+    // Returns the next node.
+    __device__ __forceinline__ static int visit(const BvhNode *nodes, int node, const SlabRay &sr, float tbest, int *stack, int &sp)
     {
         const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
         const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
@@ -246,11 +250,18 @@ struct BvhAccel {
         // candidates farther than the best are useless; equal t must still be visited (tie-break)
         const float lim = tbest * 1.00001f + 1e-6f;
         const float INF = RVB_INF;
-        float t0, t1, t2, t3;
-        if (!slab(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, pos, inv, lim, t0)) t0 = INF;
-        if (!slab(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, pos, inv, lim, t1)) t1 = INF;
-        if (!slab(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, pos, inv, lim, t2)) t2 = INF;
-        if (!slab(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, pos, inv, lim, t3)) t3 = INF;
+        const float2 ix = bcast2(sr.inv.x), iy = bcast2(sr.inv.y), iz = bcast2(sr.inv.z);
+        const float2 ox = bcast2(sr.oinv.x), oy = bcast2(sr.oinv.y), oz = bcast2(sr.oinv.z);
+        const float2 ax0 = __ffma2_rn(make_float2(lox.x, lox.y), ix, ox), bx0 = __ffma2_rn(make_float2(lox.z, lox.w), ix, ox);
+        const float2 ax1 = __ffma2_rn(make_float2(hix.x, hix.y), ix, ox), bx1 = __ffma2_rn(make_float2(hix.z, hix.w), ix, ox);
+        const float2 ay0 = __ffma2_rn(make_float2(loy.x, loy.y), iy, oy), by0 = __ffma2_rn(make_float2(loy.z, loy.w), iy, oy);
+        const float2 ay1 = __ffma2_rn(make_float2(hiy.x, hiy.y), iy, oy), by1 = __ffma2_rn(make_float2(hiy.z, hiy.w), iy, oy);
+        const float2 az0 = __ffma2_rn(make_float2(loz.x, loz.y), iz, oz), bz0 = __ffma2_rn(make_float2(loz.z, loz.w), iz, oz);
+        const float2 az1 = __ffma2_rn(make_float2(hiz.x, hiz.y), iz, oz), bz1 = __ffma2_rn(make_float2(hiz.z, hiz.w), iz, oz);
+        float t0 = slab_hit(ax0.x, ax1.x, ay0.x, ay1.x, az0.x, az1.x, lim);
+        float t1 = slab_hit(ax0.y, ax1.y, ay0.y, ay1.y, az0.y, az1.y, lim);
+        float t2 = slab_hit(bx0.x, bx1.x, by0.x, by1.x, bz0.x, bz1.x, lim);
+        float t3 = slab_hit(bx0.y, bx1.y, by0.y, by1.y, bz0.y, bz1.y, lim);
         int r0 = ref.x, r1 = ref.y, r2 = ref.z, r3 = ref.w;
         // slots 0 and 1 always exist; the min/max slab form would accept an unused slot's box
         if (r2 == RVB_BVH_EMPTY) t2 = INF;
@@ -304,7 +315,7 @@ struct BvhAccel {
     template <bool ANY>
     __device__ __forceinline__ bool traverse(f3 pos, f3 dir, float tlimit, float &tbest, uint32_t &ibest, Counters &c) const
     {
-        const f3 inv = inverse_dir(dir);
+        const SlabRay sr = slab_ray(pos, dir);
         tbest = tlimit;
         ibest = RVB_NONE;
         // while-while traversal: every lane first walks inner nodes until it holds a leaf (or is
@@ -318,7 +329,7 @@ struct BvhAccel {
         bool found = false;
         while (node != RVB_SENTINEL) {
             while (node >= 0) {
-                node = visit(nodes, node, pos, inv, tbest, stack, sp);
+                node = visit(nodes, node, sr, tbest, stack, sp);
                 nbox += 4;
             }
             while (node < 0 && node != RVB_SENTINEL) {
@@ -503,10 +514,12 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
     }
     const float time = __fmul_rn(RVB_SECONDS_PER_METER, DIST);               // :489
     const size_t slot = slot_of(ray, index, P.nrays);
-    P.vol[2 * slot] = make_float4(out[0].x, out[0].y, out[1].x, out[1].y);
-    P.vol[2 * slot + 1] = make_float4(out[2].x, out[2].y, out[3].x, out[3].y);
-    P.pt[slot] = make_float4(X.x, X.y, X.z, time);
-    P.tkey[slot] = any ? time : -1.0f;
+    // streaming stores: the impulses are read back much later (flatten), they should not push the
+    // scene out of L2
+    __stcs(P.vol + 2 * slot, make_float4(out[0].x, out[0].y, out[1].x, out[1].y));
+    __stcs(P.vol + 2 * slot + 1, make_float4(out[2].x, out[2].y, out[3].x, out[3].y));
+    __stcs(P.pt + slot, make_float4(X.x, X.y, X.z, time));
+    __stcs(P.tkey + slot, any ? time : -1.0f);
     if (any) {
         c.emitted++;
         if (time != 0.0f) c.tmin_nz = fminf(c.tmin_nz, time);
@@ -722,9 +735,9 @@ __global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceP
     Counters c;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < P.nrays; ray += nwarps) {
-        const uint32_t before = c.bounces;
+        const uint32_t before = c.bounces, emitted_before = c.emitted;
         if (IMAGES) image_phase_ray(acc, P, ray, c); else steady_phase_ray(acc, P, ray, c);
-        if (threadIdx.x & 31u) c.bounces = before;
+        if (threadIdx.x & 31u) { c.bounces = before; c.emitted = emitted_before; }
     }
     flush_counters(P, c);
 }
@@ -866,8 +879,6 @@ static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
 // The arithmetic of a ray is the same device code as in the per-ray kernel (same bits); every ray
 // owns its output slots, so the order in which lanes pick up rays does not show in the results.
 // =================================================================================================
-#define RVB_WF_SERVICE 8      // lanes that must be waiting before the warp leaves the traversal loop
-
 // Per-lane state that only the `serve` step touches (band volumes, path length, ray id, counters)
 // lives in shared memory so that the traversal loop keeps a small register set:
 // [k][thread] -- conflict-free.
@@ -889,7 +900,9 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
     bool has = false, exhausted = false;
     uint32_t ibest = RVB_NONE, nbox = 0, ntri = 0;
     float tbest = RVB_INF;
-    f3 pos = mk3(0.f, 0.f, 0.f), dir = pos, inv = pos;
+    f3 pos = mk3(0.f, 0.f, 0.f), dir = pos;
+    BvhAccel::SlabRay sr;
+    sr.inv = pos; sr.oinv = pos;
     S.tmin_nz[tid] = RVB_INF; S.tmax[tid] = 0.0f;
     S.queries[tid] = 0; S.bounces[tid] = 0; S.emitted[tid] = 0; S.tri[tid] = 0;
 
@@ -921,7 +934,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
             }
             if (more) {
                 S.index[tid] = index;
-                inv = BvhAccel::inverse_dir(dir);
+                sr = BvhAccel::slab_ray(pos, dir);
                 tbest = RVB_INF; ibest = RVB_NONE;
                 sp = 0; stack[sp++] = RVB_SENTINEL; node = 0;
             } else {
@@ -963,7 +976,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                     }
                     if (live) {
                         S.ray[tid] = r; S.index[tid] = P.first;
-                        inv = BvhAccel::inverse_dir(dir);
+                        sr = BvhAccel::slab_ray(pos, dir);
                         tbest = RVB_INF; ibest = RVB_NONE;
                         sp = 0; stack[sp++] = RVB_SENTINEL; node = 0;
                         has = true; want = false;
@@ -975,21 +988,26 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
         if (!__any_sync(FULL, has)) break;
 
         // ---- traverse ------------------------------------------------------------------------------
+        // Every iteration runs ONE of the two code paths for all lanes that are in that state: the
+        // triangle path once enough lanes hold a leaf (or nobody holds an inner node), the box path
+        // otherwise -- the two never share an iteration, so neither executes with the other's lanes
+        // masked off.  The loop ends when enough lanes wait for `serve` (or nothing is left to do).
         while (true) {
-            while (true) {                                   // inner nodes, until no lane holds one
-                const bool in = has && node >= 0;
-                if (!__any_sync(FULL, in)) break;
-                if (in) { node = BvhAccel::visit(P.nodes, node, pos, inv, tbest, stack, sp); nbox += 4; }
+            const bool in = has && node >= 0;
+            const bool lf = has && node < 0 && node != RVB_SENTINEL;
+            const unsigned m_in = __ballot_sync(FULL, in), m_lf = __ballot_sync(FULL, lf);
+            const unsigned m_sv = __ballot_sync(FULL, has && node == RVB_SENTINEL);
+            if ((m_in | m_lf) == 0u || (uint32_t)__popc(m_sv) >= P.wf_service) break;
+            if (m_in == 0u || (uint32_t)__popc(m_lf) >= P.wf_leaf_min) {
+                if (lf) {
+                    bool found = false;
+                    acc.leaf<false>(node, pos, dir, RVB_INF, tbest, ibest, found, ntri);
+                    node = stack[--sp];
+                }
+            } else if (in) {
+                node = BvhAccel::visit(P.nodes, node, sr, tbest, stack, sp);
+                nbox += 4;
             }
-            if (has && node != RVB_SENTINEL) {               // one leaf per lane
-                bool found = false;
-                acc.leaf<false>(node, pos, dir, RVB_INF, tbest, ibest, found, ntri);
-                node = stack[--sp];
-            }
-            const bool trav = has && node != RVB_SENTINEL;
-            const unsigned mt = __ballot_sync(FULL, trav);
-            const unsigned ms = __ballot_sync(FULL, (has && !trav) || (!has && !exhausted));
-            if (mt == 0u || __popc(ms) >= RVB_WF_SERVICE) break;
         }
     }
     Counters c;
@@ -999,9 +1017,19 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
     flush_counters(P, c);
 }
 
-static int launch_wavefront(const TraceParams &P, cudaStream_t st)
+static int launch_wavefront(const TraceParams &P_in, cudaStream_t st)
 {
-    static const int minb = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 6;
+    static const int minb_env = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 0;
+    static const int service = getenv("RVB_WF_SERVICE") ? atoi(getenv("RVB_WF_SERVICE")) : 16;
+    static const int leaf_min = getenv("RVB_WF_LEAF_MIN") ? atoi(getenv("RVB_WF_LEAF_MIN")) : 8;
+    TraceParams P = P_in;
+    P.wf_service = (uint32_t)std::max(1, std::min(32, service));
+    P.wf_leaf_min = (uint32_t)std::max(1, std::min(32, leaf_min));
+    // Few rays (a ray shard of a strong-scaling run): a lane keeps a ray for all its reflections, so the
+    // kernel is as long as the slowest lane's chain of rays -- make sure every ray finds a free lane
+    // at the start (7 CTAs of 128 threads per SM hold 132 k rays on 148 SMs).
+    int minb = minb_env ? minb_env : 6;
+    if (!minb_env && (size_t)P.nrays > (size_t)6 * 128 * sm_count() && (size_t)P.nrays <= (size_t)7 * 128 * sm_count()) minb = 7;
     unsigned int *d_fetch = nullptr;
     RVB_TRY(dev_alloc(&d_fetch, 1));
     RVB_CUDA(cudaMemsetAsync(d_fetch, 0, sizeof(unsigned int), st));
