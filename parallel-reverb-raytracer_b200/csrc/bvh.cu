@@ -191,9 +191,9 @@ __global__ void fill_leaves_kernel(uint32_t T, const uint32_t *flag, const uint3
             id[k] = ids[p + k];
             for (int j = 0; j < 9; ++j) v[j] = src[12 * (size_t)id[k] + j];
         }
-        for (int j = 0; j < 9; ++j) leaf_quads[36 * (size_t)r + 18 * (k >> 1) + 2 * j + (k & 1)] = v[j];
+        for (int j = 0; j < 9; ++j) leaf_quads[4 * RVB_LEAF_STRIDE * (size_t)r + 18 * (k >> 1) + 2 * j + (k & 1)] = v[j];
     }
-    leaf_ids[r] = make_uint4(id[0], id[1], id[2], id[3]);
+    reinterpret_cast<uint4 *>(leaf_quads)[RVB_LEAF_STRIDE * (size_t)r + 9] = make_uint4(id[0], id[1], id[2], id[3]);
 }
 
 // depth of every triangle in the binary hierarchy (the traversal stack is sized from the maximum)
@@ -312,8 +312,7 @@ int scene_build_bvh(Scene *sc)
         return fail(RVB_ERR_UNSUPPORTED, "BVH of depth " + std::to_string(depth) + " exceeds the traversal stack (near-coincident triangles?)");
     sc->n_leaves = n_leaves;
     sc->bvh_depth = depth;
-    RVB_TRY(dev_alloc(&sc->d_leaf_quads, 9 * (size_t)n_leaves));
-    RVB_TRY(dev_alloc(&sc->d_leaf_ids, (size_t)n_leaves));
+    RVB_TRY(dev_alloc(&sc->d_leaf_quads, RVB_LEAF_STRIDE * (size_t)n_leaves));
     note_launch(), fill_leaves_kernel<<<grd, blk, 0, st>>>(T, d_flag, d_rec_of, d_cnt_at, ids, sc->d_tri, reinterpret_cast<float *>(sc->d_leaf_quads), sc->d_leaf_ids);
     note_launch(), emit_nodes_kernel<<<grd, blk, 0, st>>>((int)T, d_children, d_ranges, d_tri_boxes, ids, d_node_boxes, d_rec_of, pad, sc->d_nodes);
     RVB_CUDA(cudaGetLastError());

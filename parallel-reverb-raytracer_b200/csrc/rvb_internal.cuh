@@ -80,6 +80,7 @@ int read_back(void *dst, const void *d_src, size_t bytes);        // copy + sync
 // ~ref = first position in the sorted triangle order | (count - 1) << 28.  Unused slots carry
 // RVB_BVH_EMPTY and an inverted box.
 #define RVB_BVH_EMPTY ((int)0x80000001)
+#define RVB_LEAF_STRIDE 10           // float4 per leaf record: 9 of triangle data + 1 of triangle indices (160 bytes)
 #define RVB_BVH_STACK 96             // traversal stack entries per thread (bvh.cu refuses deeper hierarchies)
 struct __align__(16) BvhNode {
     float4 lox, loy, loz, hix, hiy, hiz;
@@ -102,8 +103,9 @@ struct Scene {
     // BVH (accel == RVB_ACCEL_BVH)
     BvhNode *d_nodes = nullptr;       // [n_nodes]
     uint32_t n_nodes = 0;
-    float4 *d_leaf_quads = nullptr;   // [9*n_leaves] leaf records: <= 4 triangles in the pair-interleaved form of d_quad
-    uint4 *d_leaf_ids = nullptr;      // [n_leaves] the callers' triangle indices of the four slots (0xffffffff = unused)
+    float4 *d_leaf_quads = nullptr;   // [RVB_LEAF_STRIDE*n_leaves] leaf records: <= 4 triangles in the pair-interleaved form of
+                                      //   d_quad (36 floats), then the callers' indices of the four slots (0xffffffff = unused)
+    uint4 *d_leaf_ids = nullptr;      // (unused)
     uint32_t n_leaves = 0;
     int bvh_depth = 0;                // binary depth of the hierarchy (bounds the traversal stack)
     float diag = 0.f;                 // scene diagonal (sizes the conservative paddings)

@@ -203,12 +203,28 @@ struct BruteSmemWarp {
 // (bvh.cu: fill_leaves_kernel): one burst of nine 16-byte loads, two packed tests.
 // Visibility queries towards the microphone go through the visibility map (micmap.cuh) when the
 // trace has one.
-#define RVB_SENTINEL ((int)0x80000000)   // bottom of the traversal stack; leaf refs are >= -2^30, inner nodes >= 0
+#define RVB_SENTINEL ((int)0x80000000)
+
+// 32-byte load (LDG.E.256 on sm_100): the L1 data pipe charges a divergent load per (instruction,
+// 128-byte line), not per byte, so a 128-byte node costs four of these instead of seven 16-byte loads.
+struct f8 { float4 a, b; };
+__device__ __forceinline__ f8 ldg256(const void *p)
+{
+    // (as four 64-bit halves: ptxas 12.9 crashes on ld.global.nc.v8.f32 under --fmad=false)
+    unsigned long long x, y, z, w;
+    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(x), "=l"(y), "=l"(z), "=l"(w) : "l"(p));
+    f8 r;
+    r.a.x = __uint_as_float((unsigned)x); r.a.y = __uint_as_float((unsigned)(x >> 32));
+    r.a.z = __uint_as_float((unsigned)y); r.a.w = __uint_as_float((unsigned)(y >> 32));
+    r.b.x = __uint_as_float((unsigned)z); r.b.y = __uint_as_float((unsigned)(z >> 32));
+    r.b.z = __uint_as_float((unsigned)w); r.b.w = __uint_as_float((unsigned)(w >> 32));
+    return r;
+}   // bottom of the traversal stack; leaf refs are >= -2^30, inner nodes >= 0
 
 struct BvhAccel {
     const BvhNode *nodes;
-    const float4 *leaf_quads;   // [9 * n_leaves]
-    const uint4 *leaf_ids;      // [n_leaves]
+    const float4 *leaf_quads;   // [RVB_LEAF_STRIDE * n_leaves]: 36 floats of triangle data + the four triangle indices
+    const uint4 *leaf_ids;      // unused (the indices ride in the record)
     const float4 *tri;          // [3T] (v0, e0, e1) in the callers' order: what the visibility map indexes
     MicMap mm;
 
@@ -243,10 +259,10 @@ struct BvhAccel {
     // Returns the next node.
     __device__ __forceinline__ static int visit(const BvhNode *nodes, int node, const SlabRay &sr, float tbest, int *stack, int &sp)
     {
-        const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-        const float4 lox = __ldg(np), loy = __ldg(np + 1), loz = __ldg(np + 2);
-        const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
-        const int4 ref = __ldg(reinterpret_cast<const int4 *>(np + 6));
+        const char *np = reinterpret_cast<const char *>(nodes + node);
+        const f8 n0 = ldg256(np), n1 = ldg256(np + 32), n2 = ldg256(np + 64), n3 = ldg256(np + 96);
+        const float4 lox = n0.a, loy = n0.b, loz = n1.a, hix = n1.b, hiy = n2.a, hiz = n2.b;
+        const int4 ref = make_int4(__float_as_int(n3.a.x), __float_as_int(n3.a.y), __float_as_int(n3.a.z), __float_as_int(n3.a.w));
         // candidates farther than the best are useless; equal t must still be visited (tie-break)
         const float lim = tbest * 1.00001f + 1e-6f;
         const float INF = RVB_INF;
@@ -286,9 +302,9 @@ struct BvhAccel {
         const uint32_t ref = ~(uint32_t)node;
         const uint32_t rec = ref & 0x0fffffffu;
         ntri += (ref >> 28) + 1;
-        const float4 *r = leaf_quads + 9 * (size_t)rec;
-        const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5),
-                     r6 = __ldg(r + 6), r7 = __ldg(r + 7), r8 = __ldg(r + 8);
+        const char *r = reinterpret_cast<const char *>(leaf_quads + RVB_LEAF_STRIDE * (size_t)rec);
+        const f8 q0 = ldg256(r), q1 = ldg256(r + 32), q2 = ldg256(r + 64), q3 = ldg256(r + 96), q4 = ldg256(r + 128);
+        const float4 r0 = q0.a, r1 = q0.b, r2 = q1.a, r3 = q1.b, r4 = q2.a, r5 = q2.b, r6 = q3.a, r7 = q3.b, r8 = q4.a;
         f3x2 v0a, e0a, e1a, v0b, e0b, e1b;
         v0a.x = make_float2(r0.x, r0.y); v0a.y = make_float2(r0.z, r0.w); v0a.z = make_float2(r1.x, r1.y);
         e0a.x = make_float2(r1.z, r1.w); e0a.y = make_float2(r2.x, r2.y); e0a.z = make_float2(r2.z, r2.w);
@@ -304,7 +320,7 @@ struct BvhAccel {
         if (ANY) {
             found |= (ok0 && ta.x <= tlimit) | (ok1 && ta.y <= tlimit) | (ok2 && tb.x <= tlimit) | (ok3 && tb.y <= tlimit);
         } else if (ok0 | ok1 | ok2 | ok3) {
-            const uint4 id = __ldg(leaf_ids + rec);
+            const uint4 id = make_uint4(__float_as_uint(q4.b.x), __float_as_uint(q4.b.y), __float_as_uint(q4.b.z), __float_as_uint(q4.b.w));
             if (ok0 && (ta.x < tbest || (ta.x == tbest && id.x < ibest))) { tbest = ta.x; ibest = id.x; }
             if (ok1 && (ta.y < tbest || (ta.y == tbest && id.y < ibest))) { tbest = ta.y; ibest = id.y; }
             if (ok2 && (tb.x < tbest || (tb.x == tbest && id.z < ibest))) { tbest = tb.x; ibest = id.z; }
