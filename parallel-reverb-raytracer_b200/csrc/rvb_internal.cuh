@@ -107,7 +107,8 @@ struct Scene {
                                       //   d_quad (36 floats), then the callers' indices of the four slots (0xffffffff = unused)
     uint4 *d_leaf_ids = nullptr;      // (unused)
     uint32_t n_leaves = 0;
-    int bvh_depth = 0;                // binary depth of the hierarchy (bounds the traversal stack)
+    int bvh_depth = 0;                // binary depth of the hierarchy
+    int bvh_stack = 0;                // traversal stack entries a query can need (<= RVB_BVH_STACK)
     float diag = 0.f;                 // scene diagonal (sizes the conservative paddings)
     float build_ms = 0.f;
 };

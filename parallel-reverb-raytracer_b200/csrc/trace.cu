@@ -221,12 +221,26 @@ __device__ __forceinline__ f8 ldg256(const void *p)
     return r;
 }   // bottom of the traversal stack; leaf refs are >= -2^30, inner nodes >= 0
 
+// The traversal stack lives in shared memory, one column per thread (entry k of thread t at
+// [k * 128 + t]: conflict-free whatever the lanes' stack depths are).  In local memory every push /
+// pop of a warp whose lanes sit at different depths touches up to 32 different lines, and the L1
+// data pipe -- which is what bounds these kernels (ncu: l1tex data-pipe wavefronts 85-90 % of peak)
+// -- serves them one after the other.  All BVH kernels run 128-thread CTAs; the number of entries
+// comes from the depth of the hierarchy (Scene::bvh_stack).
+#define RVB_BVH_CTA 128
+struct TravStack {
+    int *col;
+    __device__ __forceinline__ void push(int &sp, int v) const { col[sp * RVB_BVH_CTA] = v; ++sp; }
+    __device__ __forceinline__ int pop(int &sp) const { --sp; return col[sp * RVB_BVH_CTA]; }
+};
+
 struct BvhAccel {
     const BvhNode *nodes;
     const float4 *leaf_quads;   // [RVB_LEAF_STRIDE * n_leaves]: 36 floats of triangle data + the four triangle indices
     const uint4 *leaf_ids;      // unused (the indices ride in the record)
     const float4 *tri;          // [3T] (v0, e0, e1) in the callers' order: what the visibility map indexes
     MicMap mm;
+    TravStack stk;
 
     // Per-query constants of the slab test: t = plane * inv + oinv with oinv = -origin * inv (one fma
     // per plane).  |inv| is clamped to 1e30 so that an axis-parallel ray gives huge finite values of
@@ -257,7 +271,7 @@ struct BvhAccel {
     // One visit of a 4-wide node: test the four child boxes (two children per packed fma), continue
     // with the nearest hit child and push the others so that the nearer ones are popped first.
     // Returns the next node.
-    __device__ __forceinline__ static int visit(const BvhNode *nodes, int node, const SlabRay &sr, float tbest, int *stack, int &sp)
+    __device__ __forceinline__ static int visit(const BvhNode *nodes, int node, const SlabRay &sr, float tbest, const TravStack &stack, int &sp)
     {
         const char *np = reinterpret_cast<const char *>(nodes + node);
         const f8 n0 = ldg256(np), n1 = ldg256(np + 32), n2 = ldg256(np + 64), n3 = ldg256(np + 96);
@@ -287,10 +301,10 @@ struct BvhAccel {
                                     tb = sw ? ta : tb; rb = sw ? ra : rb; ta = tt; ra = rr; }
         RVB_CSWAP(t0, r0, t1, r1) RVB_CSWAP(t2, r2, t3, r3) RVB_CSWAP(t0, r0, t2, r2) RVB_CSWAP(t1, r1, t3, r3) RVB_CSWAP(t1, r1, t2, r2)
 #undef RVB_CSWAP
-        if (t3 < INF) stack[sp++] = r3;
-        if (t2 < INF) stack[sp++] = r2;
-        if (t1 < INF) stack[sp++] = r1;
-        return t0 < INF ? r0 : stack[--sp];
+        if (t3 < INF) stack.push(sp, r3);
+        if (t2 < INF) stack.push(sp, r2);
+        if (t1 < INF) stack.push(sp, r1);
+        return t0 < INF ? r0 : stack.pop(sp);
     }
 
     // The (<= 4) triangles of one leaf record against the ray: the packed pair test of the
@@ -337,20 +351,19 @@ struct BvhAccel {
         // while-while traversal: every lane first walks inner nodes until it holds a leaf (or is
         // done), then the leaves are intersected together -- inner-node code and triangle code are
         // never interleaved inside a warp.
-        int stack[RVB_BVH_STACK];
         int sp = 0;
-        stack[sp++] = RVB_SENTINEL;
+        stk.push(sp, RVB_SENTINEL);
         int node = 0;
         uint32_t nbox = 0, ntri = 0;
         bool found = false;
         while (node != RVB_SENTINEL) {
             while (node >= 0) {
-                node = visit(nodes, node, sr, tbest, stack, sp);
+                node = visit(nodes, node, sr, tbest, stk, sp);
                 nbox += 4;
             }
             while (node < 0 && node != RVB_SENTINEL) {
                 leaf<ANY>(node, pos, dir, tlimit, tbest, ibest, found, ntri);
-                node = (ANY && found) ? RVB_SENTINEL : stack[--sp];
+                node = (ANY && found) ? RVB_SENTINEL : stk.pop(sp);
             }
         }
         c.queries++; c.tri += ntri; c.box += nbox;
@@ -362,17 +375,18 @@ struct BvhAccel {
     }
     // any-hit traversal for traces without a visibility map; out of line so that the hot kernels do
     // not carry a second traversal loop
-    __device__ __noinline__ static bool occluded_generic(const BvhNode *nodes, const float4 *leaf_quads, const uint4 *leaf_ids, f3 begin,
-                                                         f3 dir, float mag, Counters &c)
+    __device__ __noinline__ static bool occluded_generic(const BvhNode *nodes, const float4 *leaf_quads, const uint4 *leaf_ids, int *stack_col,
+                                                         f3 begin, f3 dir, float mag, Counters &c)
     {
-        const BvhAccel a{nodes, leaf_quads, leaf_ids, nullptr, MicMap{}};
+        const BvhAccel a{nodes, leaf_quads, leaf_ids, nullptr, MicMap{}, TravStack{stack_col}};
         float t; uint32_t i;
         return a.traverse<true>(begin, dir, mag, t, i, c);
     }
     // point_intersection(begin, mic) (kernel.cpp:274-296): dir = normalize(mic - begin), mag = |mic - begin|
     __device__ __forceinline__ bool occluded_to_mic(f3 begin, f3 dir, float mag, Counters &c) const
     {
-        if (mm.N == 0) return occluded_generic(nodes, leaf_quads, leaf_ids, begin, dir, mag, c);
+        // (the caller's own traversal is over when it asks for visibility, so its stack column is free)
+        if (mm.N == 0) return occluded_generic(nodes, leaf_quads, leaf_ids, stk.col, begin, dir, mag, c);
         bool blocked = false;
         const f3 w = mk3(begin.x - mm.mic[0], begin.y - mm.mic[1], begin.z - mm.mic[2]);
         const uint32_t cell = micmap_cell(w, mm.half_n, mm.N);
@@ -761,7 +775,8 @@ __global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceP
 template <bool IMAGES, int MINB>
 __global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams P)
 {
-    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap};
+    extern __shared__ int s_stack[];
+    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap, TravStack{s_stack + threadIdx.x}};
     Counters c;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrays; i += gridDim.x * blockDim.x) {
         if (IMAGES) image_phase_ray(acc, P, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, i, c);
@@ -908,10 +923,11 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const TraceParams P, unsigned int *fetch)
 {
     __shared__ WfShared S;
+    extern __shared__ int s_stack[];
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, tid = threadIdx.x;
-    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap};
-    int stack[RVB_BVH_STACK];
+    const TravStack stack{s_stack + tid};
+    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap, stack};
     int sp = 0, node = RVB_SENTINEL;
     bool has = false, exhausted = false;
     uint32_t ibest = RVB_NONE, nbox = 0, ntri = 0;
@@ -952,7 +968,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 S.index[tid] = index;
                 sr = BvhAccel::slab_ray(pos, dir);
                 tbest = RVB_INF; ibest = RVB_NONE;
-                sp = 0; stack[sp++] = RVB_SENTINEL; node = 0;
+                sp = 0; stack.push(sp, RVB_SENTINEL); node = 0;
             } else {
                 S.bounces[tid] += index - P.first;
                 if (P.count) P.count[ray] = (P.first ? P.count[ray] : 0u) + (index - P.first);
@@ -994,7 +1010,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                         S.ray[tid] = r; S.index[tid] = P.first;
                         sr = BvhAccel::slab_ray(pos, dir);
                         tbest = RVB_INF; ibest = RVB_NONE;
-                        sp = 0; stack[sp++] = RVB_SENTINEL; node = 0;
+                        sp = 0; stack.push(sp, RVB_SENTINEL); node = 0;
                         has = true; want = false;
                     }
                     // dead rays are skipped: keep asking
@@ -1018,7 +1034,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 if (lf) {
                     bool found = false;
                     acc.leaf<false>(node, pos, dir, RVB_INF, tbest, ibest, found, ntri);
-                    node = stack[--sp];
+                    node = stack.pop(sp);
                 }
             } else if (in) {
                 node = BvhAccel::visit(P.nodes, node, sr, tbest, stack, sp);
@@ -1033,7 +1049,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
     flush_counters(P, c);
 }
 
-static int launch_wavefront(const TraceParams &P_in, cudaStream_t st)
+static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStream_t st)
 {
     static const int minb_env = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 0;
     static const int service = getenv("RVB_WF_SERVICE") ? atoi(getenv("RVB_WF_SERVICE")) : 16;
@@ -1051,10 +1067,11 @@ static int launch_wavefront(const TraceParams &P_in, cudaStream_t st)
     RVB_CUDA(cudaMemsetAsync(d_fetch, 0, sizeof(unsigned int), st));
     auto go = [&](auto kernel) -> int {
         int per_sm = 0;
-        RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0));
+        RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_bytes));
+        RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, stack_bytes));
         const size_t want = ((size_t)P.nrays + 127) / 128;
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min(want, (size_t)std::max(per_sm, 1) * sm_count()));
-        note_launch(), kernel<<<grid, 128, 0, st>>>(P, d_fetch);
+        note_launch(), kernel<<<grid, 128, stack_bytes, st>>>(P, d_fetch);
         RVB_CUDA(cudaGetLastError());
         return RVB_OK;
     };
@@ -1106,7 +1123,8 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     static const bool wavefront = !(getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '0');
     if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
     P.state = d_state;
-    const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : 0;
+    // brute force: the whole scene; BVH: the traversal stacks (one column of Scene::bvh_stack entries per thread)
+    const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : (size_t)sc->bvh_stack * RVB_BVH_CTA * sizeof(int);
 
     // processing order of the image phase: rays sorted by direction cell
     uint32_t *d_perm_keys[2] = {nullptr, nullptr}, *d_perm_ids[2] = {nullptr, nullptr};
@@ -1142,21 +1160,21 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         if (split > 0) {
             P.first = 0; P.last = split;
             if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
-            else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, 0, st));
+            else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, smem, st));
             RVB_CUDA(cudaEventRecord(em, st));
             RVB_CUDA(cudaMemcpyAsync(hm, d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         }
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
             if (brute) RVB_TRY(launch_bruteforce<false>(P, smem, st));
-            else if (!wavefront) RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, 0, st));
-            else RVB_TRY(launch_wavefront(P, st));
+            else if (!wavefront) RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, smem, st));
+            else RVB_TRY(launch_wavefront(P, smem, st));
         }
     } else if (tr->nrays > 0 && images && tr->ray_offset == 0) {
         // zero reflections: the reference still computes the direct path for ray 0
         P.first = 0; P.last = 0;
         if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
-        else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, 0, st));
+        else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, smem, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
     unsigned long long *h = h_pin;
