@@ -7,14 +7,21 @@ A "step" is one pass of the whole hot path over one batch of synthetic rays:
   sort by sample index + segmented reduction) -> Linkwitz-Riley band filters -> mixdown / normalize /
   trim.
 
+Default workload at EVERY N: C3, the 100k-triangle hall with 1 Mi rays x 128 reflections, stereo --
+the configuration BASELINE.json's scaling target is quoted on (it fits one GPU), so the driver's
+1 -> 8 GPU curve is STRONG scaling of that one problem.
+
   value : whole-job rays*bounces/s with the directions already resident in HBM (CUDA events on
           the launching stream, max over ranks)
   e2e   : the same metric through the public C-ABI calls with HOST buffers: pinned-host
           directions -> device inside the timed region, final IR read back to the host
-  N > 1 : rays are sharded; per-GPU histograms are summed with one NCCL reduce, rank 0 filters.
-          The default workload (C2) scales weakly (every GPU traces the full per-GPU ray count of
-          its own contiguous slice of the direction set); C3/C4 keep the total ray count fixed
-          (strong); C5 shards independent source/receiver pairs with no collective.
+  N > 1 : rays are sharded; one small all-gather (time extrema + image sources), one NCCL reduce of
+          the per-GPU histograms, rank 0 filters.  After the timed region rank 0 renders the whole
+          ray set alone and the line carries `sharded_parity` (per-band relative L2 of the sharded IR
+          against it).
+  N = 1 : the line also carries `sub_blocks`: C2 (12-triangle shoebox, the brute-force kernel the
+          FP32 roofline target is stated for) and the 4352-triangle brute-force room, each measured
+          the same way with its own `roofline`.
 
 `--impl reference` times the CPU restatement of the reference's own algorithm (oracle/) on the
 host cores -- the reference's OpenCL build cannot run in this image (no OpenCL ICD).
@@ -33,9 +40,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 FLOP_PER_TEST = 52           # Moller-Trumbore, rayverb/kernel.cpp:63-88
+FLOP_PER_BOX = 20            # slab test of one child box
 SM_COUNT = 148
 FP32_LANES = 128
 SR = 44100.0
+DEFAULT_WORKLOAD = "C3_hall_100ktri_1Mx128_stereo"
+SUB_BLOCKS = ["C2_shoebox_12tri_1Mx128_omni", "X_room_4ktri_303kx64_bruteforce"]
+PARITY_TOL = 2e-6            # sharded vs one-GPU IR, relative L2 per band (float summation order only)
 
 
 def load_peaks():
@@ -61,8 +72,10 @@ def _pairs_grid():
 WORKLOADS = {
     "C2_shoebox_12tri_1Mx128_omni": dict(scene="shoebox", jobs=[((7, 2, 4), (2, 1.5, 2))], rays=1 << 20, refl=128, scaling="weak",
                                          speakers=[((0, 0, 1), 0.0)], seed=2015),
-    "C1_vault_like_room_1024x64": dict(scene="room700", jobs=[((5.5, 1.2, 3.5), (2, 1.5, 2))], rays=1024, refl=64, scaling="weak",
-                                       speakers=[((0, 0, -1), 0.0)], seed=2015),
+    # C1: the shipped vault room (3754 triangles after triangulation, tests/golden/vault_scene.npz),
+    # vault.json's source / microphone, one omni speaker
+    "C1_vault_3754tri_1024x64": dict(scene="vault", jobs=[((0, 1.75, 6), (0, 1.75, 0))], rays=1024, refl=64, scaling="weak",
+                                     speakers=[((0, 0, -1), 0.0)], seed=2015, lo_cutoff=60.0),
     "C3_hall_100ktri_1Mx128_stereo": dict(scene="hall", jobs=[((24, 1.5, 18), (20, 2.0, 4))], rays=1 << 20, refl=128, scaling="strong",
                                           speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], seed=2015),
     "C4_cathedral_1Mtri_4Mx256_hrtf": dict(scene="cathedral", jobs=[((15, 1.7, 60), (15, 2.0, 10))], rays=1 << 22, refl=256, scaling="strong",
@@ -79,9 +92,9 @@ def build_scene(name):
     from rayverb_b200 import scenes
     if name == "shoebox":
         return scenes.shoebox()
-    if name == "room700":
-        tri, vtx = scenes.displaced_box(8.0, 3.0, 5.0, 700, amp=0.08, fan=0.2, nsurfaces=4)
-        return tri, vtx, scenes.hall_surfaces()
+    if name == "vault":
+        sc = np.load(os.path.join(ROOT, "tests", "golden", "vault_scene.npz"))
+        return sc["triangles"], sc["vertices"], sc["surfaces"]
     if name == "room4k":
         tri, vtx = scenes.displaced_box(20.0, 8.0, 14.0, 4400, amp=0.1, fan=0.25, nsurfaces=4)
         return tri, vtx, scenes.hall_surfaces()
@@ -94,7 +107,7 @@ def build_scene(name):
 
 def render_kwargs(wl):
     from rayverb_b200 import scenes
-    kw = dict(sr=SR, ft="linkwitz_riley", lo_cutoff=45.0)
+    kw = dict(sr=SR, ft="linkwitz_riley", lo_cutoff=wl.get("lo_cutoff", 45.0))
     if "hrtf" in wl:
         kw["hrtf"] = dict(table=scenes.synthetic_hrtf_table(), facing=wl["hrtf"]["facing"], up=wl["hrtf"]["up"])
     else:
@@ -139,7 +152,7 @@ class ClockSampler(threading.Thread):
 
 def cpu_sample_rays(wl):
     """Bounded ray sample of the workload for the CPU legs (brute force over T triangles)."""
-    T = {"shoebox": 12, "room700": 700, "room4k": 4400, "hall": 100_000, "cathedral": 1_000_000}[wl["scene"]]
+    T = {"shoebox": 12, "vault": 3754, "room4k": 4400, "hall": 100_000, "cathedral": 1_000_000}[wl["scene"]]
     budget = 2.0e9   # ray-triangle tests per step: a few seconds on ~16 cores
     return int(max(16, min(wl["rays"], budget / (2.3 * wl["refl"] * T))))
 
@@ -182,7 +195,8 @@ def run_reference(args, wl_name, wl):
     value, dt, cores, sample = cpu_leg(wl, tri, vtx, srf, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "rays_x_bounces_per_s", "value": value, "unit": "rays*bounces/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if wl["scaling"] == "strong" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name,
                        "note": "CPU oracle port of rayverb/kernel.cpp + host pipeline (OpenMP over rays); the reference's OpenCL build has no ICD here"},
             "cpu_baseline": {"value": value, "unit": "rays*bounces/s", "cores": cores, "kind": "port", "sample": sample},
@@ -191,44 +205,39 @@ def run_reference(args, wl_name, wl):
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2_shoebox_12tri_1Mx128_omni", choices=sorted(WORKLOADS))
-    ap.add_argument("--rays", type=int, default=None, help="override the workload's ray count (testing)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-balance", action="store_true", help="multi-GPU: keep equal ray shards (no measured re-cut)")
-    ap.add_argument("--accel", type=int, default=None, help="0 auto, 1 brute force, 2 BVH")
-    args = ap.parse_args()
-    wl_name = args.workload
-    wl = dict(WORKLOADS[wl_name])
-    if args.rays:
-        wl["rays"] = args.rays
-    if args.impl == "reference":
-        return run_reference(args, wl_name, wl)
+def opencl_extra(wl, tri, vtx, srf, all_dirs, nrays, nrefl):
+    """Same-hardware context: the reference's verbatim OpenCL `raytrace` kernel on this B200 through
+    NVIDIA's OpenCL ICD (kernel only: no host pipeline, no flatten / filter).  Its brute-force loop
+    limits this to small scenes."""
+    try:
+        from oracle import cl_reference as clr
+        if not clr.available() or len(tri) > 5000:
+            return None
+        n = int(min(nrays, (1 << 30) // (64 * nrefl), 1 << 17))
+        mic0, src0 = wl["jobs"][0]
+        clr.raytrace(tri, vtx, srf, mic0, src0, all_dirs[:4096], nrefl, read_back=False)        # JIT + warm-up
+        secs = min(clr.raytrace(tri, vtx, srf, mic0, src0, all_dirs[:n], nrefl, read_back=False)["kernel_seconds"] for _ in range(3))
+        return {"value": n * nrefl / secs, "unit": "rays*bounces/s (raytrace kernel only)",
+                "sample": f"{n} rays x {nrefl} reflections, best of 3, {secs * 1e3:.1f} ms",
+                "note": "verbatim KERNEL_STRING of rayverb/kernel.cpp compiled by the driver's OpenCL 3.0 ICD"}
+    except Exception as e:   # never let the optional extra break the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
+
+def _mean(k, ss):
+    return float(np.mean([s[k] for s in ss])) if ss else 0.0
+
+
+def measure(wl_name, wl, args, env, steps, warmup, parity=False):
+    """Warm up, then time `steps` passes of workload `wl` on this rank's share (directions resident,
+    then from host buffers).  Returns the rank-0 result block (None on other ranks)."""
     import torch
     import torch.distributed as dist
     from rayverb_b200 import api, scenes, sharding
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the rayverb_b200 hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    api.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
-    api.set_stream(stream.cuda_stream)
-
+    world, rank, local, stream = env["world"], env["rank"], env["local"], env["stream"]
     tri, vtx, srf = build_scene(wl["scene"])
     nrefl, scaling = wl["refl"], wl["scaling"]
-    # ray set and the slice this rank owns
     if scaling == "weak":
         total_rays = world * wl["rays"]
         lo, hi = rank * wl["rays"], (rank + 1) * wl["rays"]
@@ -252,7 +261,6 @@ def main():
         shard["d"] = shard["h"].to("cuda", non_blocking=False)
 
     set_shard(lo, hi)
-    nrays = hi - lo
     accel = args.accel if args.accel is not None else wl.get("accel", 0)
     rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
     render_kw = render_kwargs(wl)
@@ -263,7 +271,7 @@ def main():
     # C5: independent pairs are small problems (16 k rays); several host threads, each with its own
     # CUDA stream and Raytracer, keep the GPU full.  The library's stream / error / stats state is
     # per thread, device blocks come from a mutex-protected cache.
-    workers = []
+    workers, pool = [], None
     if scaling == "jobs" and len(jobs) > 1:
         from concurrent.futures import ThreadPoolExecutor
         nworkers = min(int(os.environ.get("RVB_BENCH_WORKERS", "4")), len(jobs))
@@ -286,7 +294,7 @@ def main():
         w["stream"].synchronize()
         return out
 
-    def step(resident):
+    def step(resident, keep_bands=False):
         """One pass of the hot path over this rank's work.  Returns the IR(s) this rank produced."""
         irs = []
         if workers:
@@ -306,20 +314,20 @@ def main():
             state["trace"].append(tr.stats())
             timing = {"local_ms": 1e3 * (time.perf_counter() - t_host)}
             if not sharded:
-                irs.append(tr.render_ir(**render_kw))
+                irs.append(tr.render_ir(keep_bands=keep_bands, **render_kw))
                 state["render"].append(api.render_stats())
                 continue
-            # sharded: global predelay/lengths, cross-shard image merge, ONE NCCL reduce of the histogram
+            # sharded: ONE all-gather (extrema + image sources), ONE NCCL reduce of the histogram, rank 0 filters
             hist, lengths, _ = sharding.sharded_histogram(tr, cfg, rank, world, "cuda", SR, False, timing)
             state["render"].append(api.render_stats())
             if rank == 0:
                 t_host = time.perf_counter()
-                irs.append(api.render_finish(cfg, hist.data_ptr(), lengths))
+                irs.append(api.render_finish(cfg, hist.data_ptr(), lengths, keep_bands=keep_bands))
                 timing["exclusive_ms"] = timing.get("exclusive_ms", 0.0) + 1e3 * (time.perf_counter() - t_host)
             state["timing"] = timing
         return irs
 
-    def timed(resident, steps):
+    def timed(resident, nsteps):
         state["trace"].clear()
         state["render"].clear()
         if world > 1:
@@ -328,29 +336,29 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0, d2h = api.launch_count(), 0
         e0.record(stream)
-        for _ in range(steps):
+        for _ in range(nsteps):
             irs = step(resident)
             d2h = sum(c.nbytes for ir in irs for c in ir.channels)
         e1.record(stream)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        ms = e0.elapsed_time(e1) / nsteps
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, api.launch_count() - launches0, d2h
 
-    # Warm-up; on a sharded run the first warm-up step also MEASURES the ranks: rank 0 merges the image
-    # sources and filters the summed histogram on top of its share of the rays, so the contiguous ray
-    # slices are re-cut once so that every rank finishes at the same time (sharding.balance_weights).
+    # Warm-up; on a sharded run with several waves of rays per GPU the second warm-up step also MEASURES
+    # the ranks: rank 0 merges the image sources and filters the summed histogram on top of its share of
+    # the rays, so the contiguous ray slices are re-cut once so that every rank finishes at the same time
+    # (sharding.balance_weights).  With ~one wave per GPU the bounce kernels' time is a step function of
+    # the ray count and the linear model behind the re-cut does not hold (C3 at 8 GPUs: 20.5 ms re-cut vs
+    # 19.2 ms equal shards), so small shards stay equal.
     balance = None
-    for w_it in range(max(args.warmup, 3)):
+    for w_it in range(max(warmup, 3)):
         step(True)
-        # (only with several waves of rays per GPU: with ~1 wave the bounce kernels' time is a step
-        # function of the ray count and the linear model behind the re-cut does not hold -- measured
-        # on C3 at 8 GPUs, 131 k rays per GPU: 20.5 ms re-cut vs 19.2 ms equal shards)
         if sharded and w_it == 1 and not args.no_balance and shard["n"] >= (1 << 19):
             tm = state.get("timing", {})
             mine = torch.tensor([tm.get("local_ms", 0.0), tm.get("exclusive_ms", 0.0), float(shard["n"])], device="cuda", dtype=torch.float64)
@@ -363,47 +371,77 @@ def main():
             set_shard(cuts[rank], cuts[rank + 1])
             balance = {"rank0_share": (cuts[1] - cuts[0]) / total_rays, "equal_share": 1.0 / world,
                        "measured_exclusive_ms_rank0": float(allm[0, 1]), "measured_ms_per_kiloray": 1e3 * ms_per_ray}
-    sampler = ClockSampler(local)
-    sampler.start()
-    ms, launches, _ = timed(True, args.steps)
+    ms, launches, _ = timed(True, steps)
     tstats = [dict(s) for s in state["trace"]]
     rstats = [dict(s) for s in state["render"]]
     step(False)  # warm the host-buffer path (pinned H2D)
-    e2e_ms, _, d2h_bytes = timed(False, args.steps)
-    clocks = sampler.stop()
+    e2e_ms, _, d2h_bytes = timed(False, steps)
     nrays = shard["n"]   # after the shard re-cut
     h2d_bytes = shard["h"].numel() * 4 * len(jobs)
 
+    # sharded parity: the same total ray set on ONE GPU (rank 0) against the sharded result, per band
+    sharded_parity = None
+    if parity and sharded:
+        irs = step(True, keep_bands=True)
+        if rank == 0:
+            mic, src = jobs[0]
+            full = torch.from_numpy(all_dirs).to("cuda")
+            tr1 = rt.raytrace(mic, src, None, ray_offset=0, device_ptr=full.data_ptr(), nrays=total_rays)
+            one = tr1.render_ir(keep_bands=True, **render_kw)
+            worst, where = 0.0, None
+            same_len = all(len(a) == len(b) for a, b in zip(irs[0].channels, one.channels))
+            for c in range(len(one.bands)):
+                for b in range(one.bands[c].shape[0]):
+                    ref = one.bands[c][b].astype(np.float64)
+                    got = irs[0].bands[c][b].astype(np.float64)
+                    if ref.shape != got.shape:
+                        worst, where = float("inf"), (c, b)
+                        continue
+                    d = np.linalg.norm(ref)
+                    e = float(np.linalg.norm(got - ref) / d) if d > 0 else float(np.linalg.norm(got))
+                    if e > worst:
+                        worst, where = e, (c, b)
+            chan = max(float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+                       for a, b in zip(irs[0].channels, one.channels)) if same_len else float("inf")
+            sharded_parity = {"against": "the same %d rays rendered on one GPU (rank 0)" % total_rays,
+                              "max_rel_l2_per_band": worst, "worst_channel_band": where, "max_rel_l2_per_channel": chan,
+                              "tolerance": PARITY_TOL, "ok": bool(worst <= PARITY_TOL and chan <= PARITY_TOL)}
+            del full
+        if world > 1:
+            dist.barrier()
+
+    block = None
     if rank == 0:
         hbm_gbs, sm_max_mhz, peak_src = load_peaks()
         njobs_total = len(wl["jobs"])
         total_rb = total_rays * nrefl * (njobs_total if scaling == "jobs" else 1)
         fp32_peak_tf = SM_COUNT * FP32_LANES * 2 * sm_max_mhz * 1e6 / 1e12
-
-        def mean(k, ss):
-            return float(np.mean([s[k] for s in ss])) if ss else 0.0
-
-        steady_ms, image_ms = mean("steady_phase_ms", tstats), mean("image_phase_ms", tstats)
-        steady_tests = mean("steady_tri_tests", tstats)
-        all_tests = mean("tri_tests", tstats)
+        steady_ms, image_ms = _mean("steady_phase_ms", tstats), _mean("image_phase_ms", tstats)
+        steady_tests, steady_boxes = _mean("steady_tri_tests", tstats), _mean("steady_box_tests", tstats)
+        all_tests, all_boxes = _mean("tri_tests", tstats), _mean("box_tests", tstats)
         brute = rt.accel == api.ACCEL_BRUTE_FORCE
-        achieved_tf = steady_tests * FLOP_PER_TEST / (steady_ms * 1e-3) / 1e12 if steady_ms > 0 else 0.0
+        steady_flop = steady_tests * FLOP_PER_TEST + steady_boxes * FLOP_PER_BOX
+        achieved_tf = steady_flop / (steady_ms * 1e-3) / 1e12 if steady_ms > 0 else 0.0
         split = min(9, nrefl)
         emit_gbs = nrays * (nrefl - split) * 52 / (steady_ms * 1e-3) / 1e9 if steady_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if brute and os.path.exists(tp):   # DRAM bytes per ray*bounce of the steady kernel, from the committed ncu --set full capture
+        if brute and world == 1 and os.path.exists(tp):
+            # NOT measured in this run: DRAM bytes per ray*bounce of the steady kernel from the committed
+            # ncu --set full capture (profiles/ncu_traffic.json), scaled to this run's ray*bounce count
             traffic = json.load(open(tp))["steady_phase_dram_bytes_per_ray_bounce"] * nrays * (nrefl - split)
+            traffic_note = "profile-derived constant (profiles/ncu_traffic.json) x this run's rays*bounces, not measured live"
         both_ms = steady_ms + image_ms
-        line = {
+        bounces, emitted = _mean("bounces", tstats), _mean("emitted", tstats)
+        block = {
             "metric": "rays_x_bounces_per_s", "value": total_rb / (ms * 1e-3), "unit": "rays*bounces/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if scaling == "strong" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "triangles": int(len(tri)), "rays_total": int(total_rays), "rays_this_gpu": int(nrays),
                        "reflections": nrefl, "source_receiver_pairs": njobs_total, "channels": nch, "sample_rate": int(SR),
                        "attenuation": "hrtf" if "hrtf" in wl else "speakers", "filter": "linkwitz_riley",
-                       "accel": "brute_force_smem" if brute else "bvh",
+                       "accel": "brute_force_smem" if brute else "bvh+micmap",
                        "sharding": ("pairs/%d" % world if scaling == "jobs" else "rays/%d" % world) if world > 1 else "none",
                        "shard_balance": balance,
                        "l2": "inputs_larger_than_L2 (per-step working set %.2f GB per GPU)" % (nrays * nrefl * 52 / 1e9)},
@@ -411,46 +449,115 @@ def main():
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
             "ir_wall_ms": e2e_ms / max(1, len(jobs)),
             "gpu_launches": int(launches),
-            "clocks": clocks,
+            # executed reflections on rank 0's shard (a ray that leaves the mesh stops, kernel.cpp:372-375) and
+            # the share of them whose impulse the attenuators skip (zero volume, kernel.cpp:524,607)
+            "bounces": {"executed": int(bounces), "of": int(nrays * nrefl * max(1, len(jobs) if scaling == "jobs" else 1)),
+                        "emitted": int(emitted), "skipped_fraction": (1.0 - emitted / bounces) if bounces > 0 else None},
             "roofline": {"kernel": ("trace_bruteforce_kernel<false>" if brute else "trace_bvh_kernel<false>")
                          + " (steady phase, reflections %d..%d)" % (split, nrefl - 1),
                          "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp32_peak_tf, "traffic": traffic,
+                         "frac": achieved_tf / fp32_peak_tf, "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": f"148 SM x 128 lanes x 2 x {sm_max_mhz:.0f} MHz ({peak_src} clock)",
                          "kernel_ms": steady_ms, "tests_per_launch": int(steady_tests), "flop_per_test": FLOP_PER_TEST,
-                         "all_bounce_kernels": {"ms": both_ms, "tests": int(all_tests),
-                                                "achieved": all_tests * FLOP_PER_TEST / (both_ms * 1e-3) / 1e12 if both_ms > 0 else 0.0},
+                         "all_bounce_kernels": {"ms": both_ms, "tests": int(all_tests), "box_tests": int(all_boxes),
+                                                "achieved": (all_tests * FLOP_PER_TEST + all_boxes * FLOP_PER_BOX) / (both_ms * 1e-3) / 1e12 if both_ms > 0 else 0.0},
                          "hbm_view": {"achieved": emit_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": emit_gbs / hbm_gbs,
                                       "bytes_per_impulse": 52}},
-            "stages_ms": {"image_phase": image_ms, "steady_phase": steady_ms, "trace_total": mean("total_ms", tstats),
-                          "keys": mean("keys_ms", rstats), "sort": mean("sort_ms", rstats), "reduce": mean("reduce_ms", rstats),
-                          "filter": mean("filter_ms", rstats), "finish": mean("finish_ms", rstats)},
+            "stages_ms": {"image_phase": image_ms, "steady_phase": steady_ms, "trace_total": _mean("total_ms", tstats),
+                          "keys": _mean("keys_ms", rstats), "sort": _mean("sort_ms", rstats), "reduce": _mean("reduce_ms", rstats),
+                          "filter": _mean("filter_ms", rstats), "finish": _mean("finish_ms", rstats)},
         }
         if not brute:
-            line["roofline"]["box_tests_per_launch"] = int(mean("steady_box_tests", tstats))
+            block["roofline"]["box_tests_per_launch"] = int(steady_boxes)
+            block["roofline"]["flop_per_box_test"] = FLOP_PER_BOX
+            block["roofline"]["flop_model"] = "tri_tests x 52 + box_tests x 20 (SURVEY 8d); visibility queries go through the microphone map"
+            block["roofline"]["binding_resource"] = ("L1 data pipe: ncu l1tex__data_pipe_lsu_wavefronts 80-90 % of peak on this kernel "
+                                                     "(profiles/r2_bvh_kernels.md) -- divergent node fetches, not FP32 or HBM")
+            block["roofline"]["micmap"] = {"cells_per_face_edge": int(_mean("micmap_cells", tstats)), "entries": int(_mean("micmap_entries", tstats))}
+        if sharded_parity is not None:
+            block["sharded_parity"] = sharded_parity
+    for w in workers:
+        w["rt"].close()
+    if pool is not None:
+        pool.shutdown()
+    rt.close()
+    del shard["d"], shard["h"]
+    return block, (wl, tri, vtx, srf, all_dirs, nrays, nrefl)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--rays", type=int, default=None, help="override the workload's ray count (testing)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-blocks", action="store_true", help="N = 1: skip the C2 / brute-force-room sub-blocks")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-one-GPU IR comparison")
+    ap.add_argument("--no-balance", action="store_true", help="multi-GPU: keep equal ray shards (no measured re-cut)")
+    ap.add_argument("--accel", type=int, default=None, help="0 auto, 1 brute force, 2 BVH")
+    args = ap.parse_args()
+    wl_name = args.workload
+    wl = dict(WORKLOADS[wl_name])
+    if args.rays:
+        wl["rays"] = args.rays
+    if args.impl == "reference":
+        return run_reference(args, wl_name, wl)
+
+    import torch
+    import torch.distributed as dist
+    from rayverb_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rayverb_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    api.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    api.set_stream(stream.cuda_stream)
+    env = dict(world=world, rank=rank, local=local, stream=stream)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    line, (wl, tri, vtx, srf, all_dirs, nrays, nrefl) = measure(wl_name, wl, args, env, args.steps, args.warmup, parity=not args.no_parity)
+    clocks = sampler.stop()
+
+    subs, sub_ctx = {}, {}
+    if world == 1 and not args.no_sub_blocks and wl_name == DEFAULT_WORKLOAD and not args.rays:
+        for name in SUB_BLOCKS:
+            sub_args = argparse.Namespace(**vars(args))
+            sub_args.accel = None
+            s = ClockSampler(local)
+            s.start()
+            blk, ctx = measure(name, dict(WORKLOADS[name]), sub_args, env, args.steps, args.warmup)
+            sub_ctx[name] = (blk, ctx)
+            blk["clocks"] = s.stop()
+            for k in ("metric", "unit", "n_gpus", "higher_is_better", "vs_baseline", "dtype", "data"):
+                blk.pop(k, None)
+            subs[name] = blk
+
+    if rank == 0:
+        line["clocks"] = clocks
+        if subs:
+            line["sub_blocks"] = subs
+            c2 = subs.get("C2_shoebox_12tri_1Mx128_omni")
+            if c2:   # the FP32 intersection roofline the north star states its 50 % target for
+                line["intersection_roofline"] = {"workload": "C2_shoebox_12tri_1Mx128_omni (sub_blocks)", **{k: c2["roofline"][k] for k in
+                                                 ("kernel", "bound", "achieved", "peak", "unit", "frac", "kernel_ms", "tests_per_launch")}}
         if not args.no_cpu_baseline:
             v, dt, cores, sample = cpu_leg(wl, tri, vtx, srf, 1, 0)
             line["cpu_baseline"] = {"value": v, "unit": "rays*bounces/s", "cores": cores, "kind": "port", "sample": sample}
-            # Extra, same-hardware context: the reference's verbatim OpenCL `raytrace` kernel on this
-            # B200 through NVIDIA's OpenCL ICD (kernel only: no host pipeline, no flatten/filter).
-            try:
-                from oracle import cl_reference as clr
-                if clr.available() and len(tri) <= 5000:
-                    n = int(min(nrays, (1 << 30) // (64 * nrefl), 1 << 17))
-                    mic0, src0 = wl["jobs"][0]
-                    clr.raytrace(tri, vtx, srf, mic0, src0, all_dirs[:4096], nrefl, read_back=False)        # JIT + warm-up
-                    secs = min(clr.raytrace(tri, vtx, srf, mic0, src0, all_dirs[:n], nrefl, read_back=False)["kernel_seconds"] for _ in range(3))
-                    line["reference_opencl_kernel_on_b200"] = {
-                        "value": n * nrefl / secs, "unit": "rays*bounces/s (raytrace kernel only)",
-                        "sample": f"{n} rays x {nrefl} reflections, best of 3, {secs * 1e3:.1f} ms",
-                        "ours_same_stage": nrays * nrefl / (both_ms * 1e-3),
-                        "note": "verbatim KERNEL_STRING of rayverb/kernel.cpp compiled by the driver's OpenCL 3.0 ICD"}
-            except Exception as e:   # never let the optional extra break the bench line
-                line["reference_opencl_kernel_on_b200"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            for name, (blk, ctx) in sub_ctx.items():   # extra context on the small scenes (see opencl_extra)
+                extra = opencl_extra(*ctx)
+                if extra is not None:
+                    line["sub_blocks"][name]["reference_opencl_kernel_on_b200"] = extra
         print(json.dumps(line))
-    for w in workers:
-        w["rt"].close()
-    rt.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -67,12 +67,15 @@ __device__ __forceinline__ bool face_rect(const float (&p)[3][3], int face, cons
 
 // FILL = false: count entries per cell (counts[cell]) and near triangles (near_count)
 // FILL = true : write them (cursor[cell] starts at 0; offsets from the scan)
+// One WARP per triangle, lanes over the cells of its rectangles: the fill's atomics return a value,
+// and a single thread walking its ~30 cells one round trip after the other took 2 ms on the 100k-
+// triangle hall (18x the count pass).
 template <bool FILL>
-__global__ void micmap_bin_kernel(const MicMapParams M, uint32_t *counts_or_cursor, const uint32_t *cell_off, uint32_t *cell_ent,
-                                  uint32_t *near_count, uint32_t *near_ent)
+__global__ void __launch_bounds__(128) micmap_bin_kernel(const MicMapParams M, uint32_t *counts_or_cursor, const uint32_t *cell_off,
+                                                         uint32_t *cell_ent, uint32_t *near_count, uint32_t *near_ent)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M.T) return;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (i >= M.T) return;   // warp-uniform
     float p[3][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -88,19 +91,21 @@ __global__ void micmap_bin_kernel(const MicMapParams M, uint32_t *counts_or_curs
         d2 += d * d;
     }
     if (!(d2 >= M.r_near * M.r_near)) {   // near (or NaN): tested by every query
-        const uint32_t k = atomicAdd(near_count, 1u);
-        if (FILL && k < M.near_cap) near_ent[k] = i;
+        if (lane == 0) {
+            const uint32_t k = atomicAdd(near_count, 1u);
+            if (FILL && k < M.near_cap) near_ent[k] = i;
+        }
         return;
     }
     for (int f = 0; f < 6; ++f) {
         FaceRect r;
-        if (!face_rect(p, f, M, r)) continue;
-        for (uint32_t j = r.j0; j <= r.j1; ++j)
-            for (uint32_t ii = r.i0; ii <= r.i1; ++ii) {
-                const uint32_t cell = ((uint32_t)f * M.N + j) * M.N + ii;
-                const uint32_t k = atomicAdd(counts_or_cursor + cell, 1u);
-                if (FILL) cell_ent[cell_off[cell] + k] = i;
-            }
+        if (!face_rect(p, f, M, r)) continue;   // warp-uniform: every lane computes the same rectangle
+        const uint32_t w = r.i1 - r.i0 + 1, n = w * (r.j1 - r.j0 + 1);
+        for (uint32_t c = lane; c < n; c += 32u) {
+            const uint32_t cell = ((uint32_t)f * M.N + r.j0 + c / w) * M.N + r.i0 + c % w;
+            const uint32_t k = atomicAdd(counts_or_cursor + cell, 1u);
+            if (FILL) cell_ent[cell_off[cell] + k] = i;
+        }
     }
 }
 
@@ -136,7 +141,7 @@ int micmap_build(const Scene *sc, const float mic[3], MicMapStorage *out)
     RVB_CUDA(cudaMemsetAsync(out->d_cell_off, 0, (ncell + 1) * sizeof(uint32_t), st));
     RVB_CUDA(cudaMemsetAsync(d_cursor, 0, ncell * sizeof(uint32_t), st));
     RVB_CUDA(cudaMemsetAsync(d_near_count, 0, 2 * sizeof(uint32_t), st));
-    const unsigned grd = (M.T + 127) / 128;
+    const unsigned grd = (M.T + 3) / 4;   // one warp per triangle, four per CTA
     note_launch(), micmap_bin_kernel<false><<<grd, 128, 0, st>>>(M, out->d_cell_off, nullptr, nullptr, d_near_count, nullptr);
     if ((rc = exclusive_scan_u32(out->d_cell_off, out->d_cell_off, ncell, d_block, out->d_cell_off + ncell, st))) return done(rc);
     uint32_t h[2] = {0, 0};   // total entries, near triangles

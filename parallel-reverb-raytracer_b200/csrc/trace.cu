@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
 static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStream_t st)
 {
     static const int minb_env = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 0;
-    static const int service = getenv("RVB_WF_SERVICE") ? atoi(getenv("RVB_WF_SERVICE")) : 16;
+    static const int service = getenv("RVB_WF_SERVICE") ? atoi(getenv("RVB_WF_SERVICE")) : 24;
     static const int leaf_min = getenv("RVB_WF_LEAF_MIN") ? atoi(getenv("RVB_WF_LEAF_MIN")) : 8;
     TraceParams P = P_in;
     P.wf_service = (uint32_t)std::max(1, std::min(32, service));
@@ -1060,8 +1060,8 @@ static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStr
     // Few rays (a ray shard of a strong-scaling run): a lane keeps a ray for all its reflections, so the
     // kernel is as long as the slowest lane's chain of rays -- make sure every ray finds a free lane
     // at the start (7 CTAs of 128 threads per SM hold 132 k rays on 148 SMs).
-    int minb = minb_env ? minb_env : 6;
-    if (!minb_env && (size_t)P.nrays > (size_t)6 * 128 * sm_count() && (size_t)P.nrays <= (size_t)7 * 128 * sm_count()) minb = 7;
+    int minb = minb_env ? minb_env : 5;
+    if (!minb_env && (size_t)P.nrays > (size_t)5 * 128 * sm_count() && (size_t)P.nrays <= (size_t)7 * 128 * sm_count()) minb = 7;
     unsigned int *d_fetch = nullptr;
     RVB_TRY(dev_alloc(&d_fetch, 1));
     RVB_CUDA(cudaMemsetAsync(d_fetch, 0, sizeof(unsigned int), st));
@@ -1118,9 +1118,12 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
     float4 *d_state = nullptr;
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
-    // BVH scenes: the steady phase runs as the persistent wavefront kernel (launch_wavefront);
-    // RVB_WAVEFRONT=0 selects the one-thread-per-ray kernel for comparison.
-    static const bool wavefront = !(getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '0');
+    // BVH scenes, steady phase: one thread per ray (default) or the persistent wavefront kernel
+    // (RVB_WAVEFRONT=1).  Measured on the C3 hall (profiles/r2_bvh_kernels.md): both forms end up bound
+    // by the L1 data pipe (80-90 % of its peak), which serves the lanes' node fetches one line at a time;
+    // the wavefront form packs 15 instead of 11 lanes per instruction but is 0-10 % slower with many rays
+    // and 30 % slower with a single wave of rays per GPU, where its lane refill has nothing to refill.
+    static const bool wavefront = getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '1';
     if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
     P.state = d_state;
     // brute force: the whole scene; BVH: the traversal stacks (one column of Scene::bvh_stack entries per thread)

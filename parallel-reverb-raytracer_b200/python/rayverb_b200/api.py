@@ -280,8 +280,9 @@ class Trace:
 
     # ---- staged form for ray shards on several GPUs ------------------------------------------
     def render_times(self, cfg):
-        mn = np.zeros(64, dtype=np.float32)
-        mx = np.zeros(64, dtype=np.float32)
+        nch = 2 if cfg.model == MODEL_HRTF else max(1, int(cfg.nspeakers))   # one entry per channel is written
+        mn = np.zeros(nch, dtype=np.float32)
+        mx = np.zeros(nch, dtype=np.float32)
         n = C.c_size_t(0)
         _check(lib().rvb_render_times(self._h, C.byref(cfg), _p(mn), _p(mx), C.byref(n)))
         return mn[:n.value].copy(), mx[:n.value].copy()
@@ -291,10 +292,10 @@ class Trace:
         _check(lib().rvb_render_histogram(self._h, C.byref(cfg), C.c_float(predelay), _p(ln), C.c_void_p(d_hist_ptr)))
 
 
-def render_finish(cfg, d_hist_ptr, lengths):
+def render_finish(cfg, d_hist_ptr, lengths, keep_bands=False):
     ln = np.asarray(lengths, dtype=np.uint64)
     h = C.c_void_p()
-    lib().rvb_render_keep_bands(0)
+    lib().rvb_render_keep_bands(int(keep_bands))
     _check(lib().rvb_render_finish(C.byref(cfg), C.c_void_p(d_hist_ptr), _p(ln), len(ln), C.byref(h)))
     return Ir(h)
 

@@ -28,12 +28,14 @@ class OracleShard:
         self.diffuse = r["diffuse"]
         self.images, self.keys, self.klen = orc.image_dedupe(r["image"], r["image_idx"])
 
-    def _attenuated(self):
-        imp = np.concatenate([self.diffuse, self.images])
+    def _attenuated(self, images=None):
+        imp = np.concatenate([self.diffuse, self.images if images is None else images])
         return [self.orc.attenuate_speaker(imp, MIC, d, c) for d, c in SPEAKERS]
 
     def render_times(self, cfg):
-        att = self._attenuated()
+        # like rvb_render_times: cfg.remove_direct hides the shard's own direct path (key {0})
+        images = self.images[self.klen != 1] if cfg.get("remove_direct") and len(self.images) == len(self.klen) else None
+        att = self._attenuated(images)
         mn = [float(a["time"][a["time"] != 0].min()) if np.any(a["time"] != 0) else 0.0 for a in att]
         mx = [float(a["time"].max()) for a in att]
         return mn, mx
@@ -60,7 +62,7 @@ class OracleShard:
             o += 8 * l
 
 
-def _worker(rank, world, port, trim_predelay, q):
+def _worker(rank, world, port, trim_predelay, q, remove_direct=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as orc
@@ -68,8 +70,8 @@ def _worker(rank, world, port, trim_predelay, q):
     dirs = scenes.sphere_directions(NRAYS, seed=77)
     b, e = sharding.shard_slice(NRAYS, rank, world)
     shard = OracleShard(orc, tri, vtx, srf, dirs[b:e])
-    hist, lengths, predelay = sharding.sharded_histogram(shard, {"trim_predelay": trim_predelay}, rank, world, "cpu", SR,
-                                                         trim_predelay)
+    hist, lengths, predelay = sharding.sharded_histogram(shard, {"trim_predelay": trim_predelay, "remove_direct": remove_direct},
+                                                         rank, world, "cpu", SR, trim_predelay)
     if rank == 0:
         q.put((hist.numpy().copy(), lengths, predelay, len(shard.images)))
     dist.barrier()
@@ -84,11 +86,11 @@ def _free_port():
     return p
 
 
-def _run(trim_predelay, orc):
+def _run(trim_predelay, orc, remove_direct=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, trim_predelay, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, trim_predelay, q, remove_direct)) for r in range(2)]
     for p in procs:
         p.start()
     hist, lengths, predelay, nimg = q.get(timeout=120)
@@ -99,8 +101,8 @@ def _run(trim_predelay, orc):
     tri, vtx, srf = scenes.shoebox()
     dirs = scenes.sphere_directions(NRAYS, seed=77)
     r = orc.raytrace(tri, vtx, srf, MIC, SRC, dirs, NREFL, debug=False)
-    images, _, _ = orc.image_dedupe(r["image"], r["image_idx"])
-    assert nimg == len(images)                                   # merge == global dedupe
+    images, _, _ = orc.image_dedupe(r["image"], r["image_idx"], remove_direct)
+    assert nimg == len(images)                                   # merge == global dedupe (minus the direct path if asked)
     imp = np.concatenate([r["diffuse"], images])
     att = [orc.attenuate_speaker(imp, MIC, d, c) for d, c in SPEAKERS]
     if trim_predelay:
@@ -121,6 +123,13 @@ def test_two_shards_equal_unsharded(orc):
 
 def test_two_shards_with_predelay(orc):
     _run(True, orc)
+
+
+@pytest.mark.parametrize("trim_predelay", [False, True])
+def test_two_shards_remove_direct(orc, trim_predelay):
+    """remove_direct on the sharded path (rayverb.cpp:695-696): only rank 0's list carries key {0}, and it
+    must not reach the histogram; the predelay then comes from the remaining impulses."""
+    _run(trim_predelay, orc, remove_direct=True)
 
 
 def test_shard_slices_cover_all_rays():
