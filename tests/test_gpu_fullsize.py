@@ -13,6 +13,8 @@ comparison on a ray subsample of the very same run.
   * the flatten length is tight: round(max time * sr) + 1 means the last sample bin is occupied;
   * the extrema reduced inside the bounce kernels equal a scan of the emitted times.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -139,3 +141,105 @@ def test_full_size_run_contains_the_oracle_subsample(orc):
     assert np.array_equal(bits(d["time"][:k]), bits(rd["time"]))
     np.testing.assert_allclose(d["volume"][:k], rd["volume"], rtol=2e-6, atol=1e-30)
     rt.close()
+
+
+def _oracle_ir_in_chunks(orc, tri, vtx, srf, mic, src, dirs, nrefl, chunk, kw):
+    """orc.render_ir for ray sets whose 64-byte impulses do not fit the host comfortably (8.6 GB at C2's
+    full size, three copies alive in render_ir): rays are traced, attenuated and flattened chunk by
+    chunk -- flattenImpulses is a sum over impulses (rayverb.cpp:67-74), so the chunks' histograms add up
+    (in float64 here; the reference's single float32 pass differs from that by ~1e-7 relative) -- image
+    sources are merged across chunks with the first (lowest) ray winning (rayverb.cpp:669-673), then
+    process() runs once on the sum."""
+    speakers, sr = kw["speakers"], kw["sr"]
+    sums = [np.zeros((NBANDS, 0), np.float64) for _ in speakers]
+    images = {}
+
+    def add(att):
+        for c, a in enumerate(att):
+            f = orc.flatten(a, sr)
+            if f.shape[1] > sums[c].shape[1]:
+                sums[c] = np.pad(sums[c], ((0, 0), (0, f.shape[1] - sums[c].shape[1])))
+            sums[c][:, :f.shape[1]] += f
+
+    for c0 in range(0, len(dirs), chunk):
+        r = orc.raytrace(tri, vtx, srf, mic, src, dirs[c0:c0 + chunk], nrefl, debug=False)
+        img, keys, klen = orc.image_dedupe(r["image"], r["image_idx"])
+        for i in range(len(img)):
+            images.setdefault(tuple(int(k) for k in keys[i][:klen[i]]), img[i].copy())
+        add([orc.attenuate_speaker(r["diffuse"], mic, d, c) for d, c in speakers])
+        del r
+    if images:
+        imgs = np.array([images[k] for k in sorted(images)], dtype=orc.IMPULSE)
+        add([orc.attenuate_speaker(imgs, mic, d, c) for d, c in speakers])
+    flat = [s_.astype(np.float32) for s_ in sums]
+    out = orc.process(kw["ft"], flat, sr, lo_cutoff=kw["lo_cutoff"])
+    bands = [orc.filter_channel(kw["ft"], f, sr, kw["lo_cutoff"]) for f in flat]
+    return out, bands
+
+
+def test_c2_full_size_ir_against_the_oracle(orc):
+    """BASELINE configs[1] at its FULL size -- 1 Mi rays x 128 reflections in the 12-triangle shoebox -- as
+    an impulse response against the CPU oracle: every band within relative L2 <= 1e-4 (north_star bar).
+    The oracle traces 134 M ray*bounces over 12 triangles in ~15-30 s on the box's host cores."""
+    tri, vtx, srf = scenes.shoebox()
+    mic, src, nrays, nrefl = (7, 2, 4), (2, 1.5, 2), 1 << 20, 128
+    dirs = scenes.sphere_directions(nrays, seed=2015)
+    kw = dict(speakers=[((0, 0, 1), 0.0)], sr=44100.0, ft="linkwitz_riley", lo_cutoff=45.0)
+    rt = api.Raytracer(nrefl, tri, vtx, srf)
+    tr = rt.raytrace(mic, src, dirs)
+    ir = tr.render_ir(keep_bands=True, **kw)
+    rt.close()
+    try:
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    want, bands = _oracle_ir_in_chunks(orc, tri, vtx, srf, mic, src, dirs, nrefl, 1 << 16, kw)
+    assert len(ir.channels) == len(want) == 1 and len(ir.channels[0]) == len(want[0])
+    assert ir.bands[0].shape == bands[0].shape
+    for b in range(NBANDS):
+        assert rel_l2(ir.bands[0][b], bands[0][b]) <= 1e-4, (b, rel_l2(ir.bands[0][b], bands[0][b]))
+    assert rel_l2(ir.channels[0], want[0]) <= 1e-4
+
+
+def test_c5_worker_threads_equal_sequential():
+    """The C5 path bench.py times: several host threads, each with its own CUDA stream and Raytracer,
+    tracing and rendering source / receiver pairs concurrently (per-thread pools, event-ordered block
+    re-use in scene.cu).  Eight pairs through four threads must give, bit for bit, the IRs of the same
+    pairs rendered one after the other on one thread."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    tri, vtx, srf = scenes.concert_hall(20_000)
+    nrefl, nrays = 32, 8192
+    dirs = scenes.sphere_directions(nrays, seed=2015)
+    pairs = [((8.0 + 3.0 * i, 1.5, 16.0 + 0.8 * i), (14.0 + 1.5 * i, 2.0, 3.0 + 0.6 * i)) for i in range(8)]
+    kw = dict(speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], sr=44100.0, ft="linkwitz_riley", lo_cutoff=45.0)
+    d_dirs = torch.from_numpy(dirs).to("cuda")
+
+    def run(rt, my_pairs, stream):
+        api.set_device(0)
+        api.set_stream(stream.cuda_stream if stream is not None else None)
+        out = []
+        for mic, src in my_pairs:
+            tr = rt.raytrace(mic, src, None, device_ptr=d_dirs.data_ptr(), nrays=nrays)
+            out.append([c.copy() for c in tr.render_ir(**kw).channels])
+        if stream is not None:
+            stream.synchronize()
+        return out
+
+    rt0 = api.Raytracer(nrefl, tri, vtx, srf)
+    seq = run(rt0, pairs, None)
+    rt0.close()
+    for _ in range(3):   # three rounds: block re-use across rounds is part of what is being checked
+        workers = [(api.Raytracer(nrefl, tri, vtx, srf), torch.cuda.Stream()) for _ in range(4)]
+        with ThreadPoolExecutor(max_workers=4) as pool:
+            futs = [pool.submit(run, rt, pairs[i::4], st) for i, (rt, st) in enumerate(workers)]
+            res = [f.result() for f in futs]
+        for i in range(4):
+            for k, chans in enumerate(res[i]):
+                want = seq[i + 4 * k]
+                assert len(chans) == len(want) == 2
+                for a, b in zip(chans, want):
+                    assert a.shape == b.shape and a.tobytes() == b.tobytes(), ("pair", i + 4 * k)
+        for rt, _ in workers:
+            rt.close()
+    api.set_stream(None)

@@ -87,6 +87,50 @@ def test_cli_end_to_end_vs_oracle(orc, tmp_path, ext, bits, model):
     assert np.abs(pcm - ir).max() <= 1.0 / ((1 << (bits - 1)) - 1)
 
 
+def test_cli_loads_hrtf_table_file(orc, tmp_path):
+    """RAYVERB_HRTF_TABLE / HrtfAttenuator::loadTable (host/rayverb.cpp: readTable): the CLI renders with a
+    table produced by the HRTF pipeline (rayverb_b200/hrtf_table.py) instead of the synthetic built-in,
+    and a file of the wrong size is an error (exit code 1, like every std::runtime_error in
+    cmd/main.cpp:299-316)."""
+    from rayverb_b200 import hrtf_table as ht
+    rng = np.random.default_rng(9)
+    grid = [({"r": 1, "a": a, "e": e}, (0.2 + rng.random((2, 8))).tolist()) for a in range(0, 361, 30) for e in range(0, 181, 30)]
+    table = ht.interpolate(grid)
+    ht.write_table(str(tmp_path / "table.f32"), table)
+    cfg = {"rays": 2000, "reflections": 16, "sample_rate": 44100, "bit_depth": 16, "source_position": [1.5, 1.5, 1.0],
+           "mic_position": [4.5, 1.2, 1.2], "filter": "linkwitz_riley", "hipass": 60, "trim_predelay": False,
+           "output_mode": "all", "normalize": True, "trim_tail": True,
+           "attenuation_model": {"hrtf": {"facing": [0.3, 0, -1], "up": [0, 1, 0]}}}
+    (tmp_path / "cfg.json").write_text(json.dumps(cfg))
+    args = [os.path.join(BIN, "parallel_raytrace"), str(tmp_path / "cfg.json"), os.path.join(GOLD, "l_room.obj"),
+            os.path.join(GOLD, "materials.json"), str(tmp_path / "ir.wav")]
+    env = dict(os.environ, RAYVERB_SEED="77", RAYVERB_DUMP_DIRECTIONS=str(tmp_path / "dirs.bin"), RAYVERB_DUMP_IR=str(tmp_path / "ir.bin"),
+               RAYVERB_HRTF_TABLE=str(tmp_path / "table.f32"))
+    r = subprocess.run(args, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    dirs = np.fromfile(tmp_path / "dirs.bin", dtype=np.float32).reshape(-1, 4)
+    raw = open(tmp_path / "ir.bin", "rb").read()
+    nch, n = struct.unpack_from("<QQ", raw, 0)
+    ir = np.frombuffer(raw, dtype=np.float32, offset=16).reshape(nch, n)
+    tri, vtx, srf = scenes.load_obj(os.path.join(GOLD, "l_room.obj"), os.path.join(GOLD, "materials.json"))
+    f = np.array([0.3, 0, -1]); f = f / np.linalg.norm(f)
+    want = orc.render_ir(tri, vtx, srf, cfg["mic_position"], cfg["source_position"], dirs, cfg["reflections"], sr=44100.0,
+                         ft="linkwitz_riley", lo_cutoff=60.0, hrtf=dict(table=table, facing=tuple(f), up=(0, 1, 0)))
+    assert nch == 2
+    for c in range(2):
+        assert n == len(want[c])
+        assert np.linalg.norm(ir[c] - want[c]) <= 1e-4 * np.linalg.norm(want[c])
+    # the built-in table gives a different response: the file really was used
+    r2 = subprocess.run(args, capture_output=True, text=True, env={k: v for k, v in env.items() if k != "RAYVERB_HRTF_TABLE"})
+    assert r2.returncode == 0
+    raw2 = open(tmp_path / "ir.bin", "rb").read()
+    ir2 = np.frombuffer(raw2, dtype=np.float32, offset=16).reshape(struct.unpack_from("<QQ", raw2, 0))
+    assert ir2.shape != ir.shape or np.linalg.norm(ir2 - ir) > 1e-2 * np.linalg.norm(ir)
+    (tmp_path / "short.f32").write_bytes(b"\0" * 1000)
+    r3 = subprocess.run(args, capture_output=True, text=True, env=dict(env, RAYVERB_HRTF_TABLE=str(tmp_path / "short.f32")))
+    assert r3.returncode == 1 and "HRTF table" in (r3.stderr + r3.stdout)
+
+
 def test_c1_golden_vectors():
     """C1: the shipped vault room (3754 triangles, fixture tests/golden/vault_scene.npz),
     1024 rays x 64 reflections, one speaker, against golden oracle vectors committed with the

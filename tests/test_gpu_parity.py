@@ -137,9 +137,17 @@ def test_attenuators_random_vs_oracle(orc):
         ref = orc.attenuate_hrtf(imp, mic, table[ch], facing, up, ch)
         assert np.array_equal(bits(o["time"]), bits(ref["time"]))
         # atan2 is a library function on both sides: a 1-ulp difference can flip the degree
-        # truncation at an integer boundary (documented near-tie class); allow a handful
-        mism = np.any(bits(o["volume"]) != bits(ref["volume"]), axis=1)
-        assert mism.mean() < 1e-3
+        # truncation at an integer boundary (documented near-tie class); allow a handful -- and every one
+        # of them must be the NEIGHBOURING table cell (azimuth or elevation index off by one), not noise
+        mism = np.flatnonzero(np.any(bits(o["volume"]) != bits(ref["volume"]), axis=1))
+        assert len(mism) < 1e-3 * n
+        tab = table[ch].reshape(360, 180, 8)
+        for i in mism:
+            gain = o["volume"][i] / imp["volume"][i]
+            gref = ref["volume"][i] / imp["volume"][i]
+            a, e = np.unravel_index(np.argmin(np.abs(tab - gref[None, None, :]).sum(-1)), (360, 180))
+            neigh = [tab[(a + da) % 360, min(179, max(0, e + de))] for da in (-1, 0, 1) for de in (-1, 0, 1)]
+            assert min(np.abs(nb - gain).max() for nb in neigh) <= 1e-5 * np.abs(gain).max(), (i, a, e)
 
 
 def test_trace_shoebox_vs_oracle(orc):
