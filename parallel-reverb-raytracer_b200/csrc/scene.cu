@@ -59,12 +59,18 @@ static const size_t kCacheLimit = (size_t)48 << 30;   // beyond this, idle block
 // Small blocks: a stream-ordered memory pool PER HOST THREAD (and device).  With the device's default
 // pool, a block freed on one thread's stream and re-used on another's makes the driver chain the two
 // streams together, and the worker threads of a parameter sweep end up running one after the other.
+// A pool outlives the host thread that used it: traces made on a worker thread hold small blocks that
+// another thread frees later, and destroying a pool at thread exit with such blocks outstanding crashed
+// inside the runtime (found by tests/test_gpu_fullsize.py: worker threads == sequential).  A thread that
+// ends hands its pools to an idle list; the next new thread adopts one from there.
+static std::vector<cudaMemPool_t> g_idle_pools[64];
 struct ThreadPools {
     cudaMemPool_t pool[64] = {};
     bool own[64] = {};
-    ~ThreadPools()   // the thread is gone: give its cached blocks back (outstanding blocks stay valid until freed)
+    ~ThreadPools()
     {
-        for (int d = 0; d < 64; ++d) if (pool[d] && own[d]) cudaMemPoolDestroy(pool[d]);
+        std::lock_guard<std::mutex> lk(g_mutex);
+        for (int d = 0; d < 64; ++d) if (pool[d] && own[d]) g_idle_pools[d].push_back(pool[d]);
     }
 };
 static thread_local ThreadPools g_tp;
@@ -72,6 +78,15 @@ static cudaMemPool_t thread_pool(int dev)
 {
     cudaMemPool_t *g_thread_pool = g_tp.pool;
     if (!g_thread_pool[dev]) {
+        {
+            std::lock_guard<std::mutex> lk(g_mutex);
+            if (!g_idle_pools[dev].empty()) {
+                g_thread_pool[dev] = g_idle_pools[dev].back();
+                g_idle_pools[dev].pop_back();
+                g_tp.own[dev] = true;
+                return g_thread_pool[dev];
+            }
+        }
         cudaMemPoolProps props{};
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
@@ -230,8 +245,33 @@ StageTimer::~StageTimer()
     if (on) { cudaStreamSynchronize(lib_stream()); fprintf(stderr, "[rvb] %-28s %8.3f ms\n", name, now_ms() - t0); }
 }
 
+// RVB_DEBUG_SIGNALS=1: print a native backtrace on SIGFPE / SIGSEGV (debug aid; resolve the offsets
+// with addr2line -e librayverb_b200.so)
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void debug_signal_handler(int sig)
+{
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "[rvb] fatal signal, native backtrace:\n";
+    if (write(2, msg, sizeof msg - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+static void maybe_install_debug_signals()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char *e = getenv("RVB_DEBUG_SIGNALS");
+    if (e && *e == '1') { signal(SIGFPE, debug_signal_handler); signal(SIGSEGV, debug_signal_handler); }
+}
+
 int ensure_device()
 {
+    maybe_install_debug_signals();
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
