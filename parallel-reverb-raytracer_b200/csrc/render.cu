@@ -191,10 +191,15 @@ __global__ void bounds_kernel(const KeyT *keys, uint32_t n, uint32_t nseg, uint3
 // One warp per segment: lane l takes entries begin+l, begin+l+32, ... in order (four gathers in
 // flight per lane), then a fixed xor-shuffle tree combines the 32 partial sums of every
 // (sub-bin, channel, band).  hist layout: [channel][band][L].
+// The partial sums are kept in DOUBLE and rounded to float once per bin: the reference adds a bin's
+// impulses one by one in float (rayverb.cpp:67-74); with the sign of the volume flipping at every
+// reflection (kernel.cpp:461) the high bands cancel heavily, and a float tree sum in a different
+// order -- one GPU vs. eight partial histograms -- differed from it by up to 2e-6 relative L2.  The
+// kernels are bound by the gathers, the double adds are free.
 // NSUB sub-bins x MAXC channels <= RVB_MAX_GROUP accumulator sets.
 template <int MODEL, bool NEED_POS, int NSUB, int MAXC>
 __device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &C, uint32_t i, uint32_t sub, float4 va, float4 vb,
-                                               float (&acc)[NSUB][MAXC][RVB_NBANDS])
+                                               double (&acc)[NSUB][MAXC][RVB_NBANDS])
 {
     const float v[RVB_NBANDS] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
     float term[MAXC][RVB_NBANDS];
@@ -226,12 +231,12 @@ __device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = __fadd_rn(acc[s][c][b], term[c][b]);
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = __dadd_rn(acc[s][c][b], (double)term[c][b]);
         }
 }
 
 template <int MODEL, bool NEED_POS, int NSUB, int MAXC>
-__global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *keys, const uint32_t *vals,
+__global__ void __launch_bounds__(256, 2) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *keys, const uint32_t *vals,
                                                      const uint32_t *seg_begin, const uint32_t *seg_end, uint32_t nseg, uint32_t L,
                                                      float *hist, size_t chan_stride)
 {
@@ -243,13 +248,13 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
         const uint32_t seg = nseg - 1 - w;
         const uint32_t b0 = seg_begin[seg], b1 = seg_end[seg];
         if (b0 == b1) continue;   // warp-uniform
-        float acc[NSUB][MAXC][RVB_NBANDS];
+        double acc[NSUB][MAXC][RVB_NBANDS];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0f;
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0;
         for (uint32_t j = b0 + lane; j < b1; j += 128) {
             uint32_t idx[4], sub[4];
             float4 va[4], vb[4];
@@ -282,9 +287,9 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
             for (int c = 0; c < MAXC; ++c) {
 #pragma unroll
                 for (int b = 0; b < RVB_NBANDS; ++b) {
-                    float x = acc[s][c][b];
-                    for (int o = 16; o; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
-                    if (lane == 0 && c < C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = x;
+                    double x = acc[s][c][b];
+                    for (int o = 16; o; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+                    if (lane == 0 && c < C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = (float)x;
                 }
             }
         }
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
                                                                           float *hist, size_t chan_stride)
 {
     static_assert(NSUB * MAXC * RVB_NBANDS == 32, "one lane per (sub-bin, channel, band) in the final combine");
-    __shared__ float part[RVB_REDUCE_WARPS][32];
+    __shared__ double part[RVB_REDUCE_WARPS][32];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (uint32_t w = blockIdx.x; w < nseg; w += gridDim.x) {
         const uint32_t seg = nseg - 1 - w;   // from the end of the response (ascending order measured the same)
@@ -314,13 +319,13 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
         if (b0 == b1) continue;   // block-uniform
         const uint32_t chunk = (b1 - b0 + RVB_REDUCE_WARPS - 1) / RVB_REDUCE_WARPS;
         const uint32_t m0 = min(b1, b0 + wid * chunk), m1 = min(b1, m0 + chunk);
-        float acc[NSUB][MAXC][RVB_NBANDS];
+        double acc[NSUB][MAXC][RVB_NBANDS];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0f;
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0;
         for (uint32_t j = m0 + lane; j < m1; j += 128) {
             uint32_t idx[4], sub[4];
             float4 va[4], vb[4];
@@ -352,18 +357,18 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
                 for (int b = 0; b < RVB_NBANDS; ++b) {
-                    float x = acc[s][c][b];
-                    for (int o = 16; o; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+                    double x = acc[s][c][b];
+                    for (int o = 16; o; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
                     if (lane == 0) part[wid][(s * MAXC + c) * RVB_NBANDS + b] = x;
                 }
         __syncthreads();
         if (wid == 0) {
-            float x = part[0][lane];
+            double x = part[0][lane];
 #pragma unroll
-            for (int q = 1; q < RVB_REDUCE_WARPS; ++q) x = __fadd_rn(x, part[q][lane]);
+            for (int q = 1; q < RVB_REDUCE_WARPS; ++q) x = __dadd_rn(x, part[q][lane]);
             const uint32_t b = lane % RVB_NBANDS, c = (lane / RVB_NBANDS) % MAXC, sb = lane / (RVB_NBANDS * MAXC);
             const uint32_t bin = seg * NSUB + sb;
-            if (c < (uint32_t)C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = x;
+            if (c < (uint32_t)C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = (float)x;
         }
         __syncthreads();
     }

@@ -79,7 +79,11 @@ struct Counters {
 // LDS.128 is a broadcast, and each packed instruction (FFMA2 ...) tests the ray against TWO
 // triangles.  Triangles are visited in index order and the strict '<' keeps the lowest index on
 // exact ties, as the reference loop does.
+// result of the nearest-hit query that rides along with a visibility query (BruteSmem::visible_and_next)
+struct NextHit { bool want; float t; uint32_t prim; };
+
 struct BruteSmem {
+    static constexpr bool kFused = true;
     const float4 *s;
     uint32_t T, nquads;
 
@@ -130,6 +134,33 @@ struct BruteSmem {
         c.queries++; c.tri += T;
         return blocked;
     }
+    // The visibility query of a reflection (kernel.cpp:463) and the nearest-hit query of the NEXT one
+    // (:363) start at the same point X -- the reflected direction (:492-499) does not depend on the
+    // visibility -- so ONE sweep over the records answers both: two queries, 2 T tests, but the
+    // direction-independent third of every test and all shared-memory loads are done once.
+    __device__ __forceinline__ bool visible_and_next(f3 pos, f3 dir_mic, float mag, f3 dir_next, NextHit &next, Counters &c) const
+    {
+        bool blocked = false;
+        float tbest = RVB_INF;
+        uint32_t ibest = RVB_NONE;
+#pragma unroll 2
+        for (uint32_t q = 0; q < nquads; ++q) {
+            f3x2 v0a, e0a, e1a, v0b, e0b, e1b;
+            load(q, v0a, e0a, e1a, v0b, e0b, e1b);
+            PairHit ma, na, mb, nb;
+            mt_intersect_pair_2rays(v0a, e0a, e1a, pos, dir_mic, dir_next, ma, na);
+            mt_intersect_pair_2rays(v0b, e0b, e1b, pos, dir_mic, dir_next, mb, nb);
+            blocked |= (ma.ok_a && ma.t.x > RVB_EPSILON && ma.t.x <= mag) | (ma.ok_b && ma.t.y > RVB_EPSILON && ma.t.y <= mag)
+                     | (mb.ok_a && mb.t.x > RVB_EPSILON && mb.t.x <= mag) | (mb.ok_b && mb.t.y > RVB_EPSILON && mb.t.y <= mag);
+            if (na.ok_a && na.t.x > RVB_EPSILON && na.t.x < tbest) { tbest = na.t.x; ibest = 4 * q; }
+            if (na.ok_b && na.t.y > RVB_EPSILON && na.t.y < tbest) { tbest = na.t.y; ibest = 4 * q + 1; }
+            if (nb.ok_a && nb.t.x > RVB_EPSILON && nb.t.x < tbest) { tbest = nb.t.x; ibest = 4 * q + 2; }
+            if (nb.ok_b && nb.t.y > RVB_EPSILON && nb.t.y < tbest) { tbest = nb.t.y; ibest = 4 * q + 3; }
+        }
+        next.t = tbest; next.prim = ibest;
+        c.queries += 2; c.tri += 2ull * T;
+        return blocked;
+    }
 };
 
 // ---- brute force, one WARP per ray (few rays, many triangles) ----------------------------------
@@ -139,6 +170,7 @@ struct BruteSmem {
 // the triangle records: lane l tests records l, l + 32, ...  The (t, index) minimum over the lanes,
 // lexicographic, is exactly what the in-order strict '<' loop keeps (kernel.cpp:180-188).
 struct BruteSmemWarp {
+    static constexpr bool kFused = false;
     const float4 *s;
     uint32_t T, nquads;
 
@@ -235,6 +267,7 @@ struct TravStack {
 };
 
 struct BvhAccel {
+    static constexpr bool kFused = false;
     const BvhNode *nodes;
     const float4 *leaf_quads;   // [RVB_LEAF_STRIDE * n_leaves]: 36 floats of triangle data + the four triangle indices
     const uint4 *leaf_ids;      // unused (the indices ride in the record)
@@ -509,9 +542,11 @@ struct RayState {
 };
 
 // kernel.cpp:459-501: everything a reflection does after the nearest hit is known
+// `next`: with a fused accelerator (Accel::kFused) and next->want, the visibility sweep also answers
+// the nearest-hit query of the reflected ray (see BruteSmem::visible_and_next).
 template <class Accel>
 __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceParams &P, f3 mic, uint32_t ray, uint32_t index,
-                                                  float tclosest, uint32_t prim, RayState &R, Counters &c)
+                                                  float tclosest, uint32_t prim, RayState &R, Counters &c, NextHit *next = nullptr)
 {
     const f3 X = madd(R.pos, R.dir, tclosest);                               // :459
     const float newDist = __fadd_rn(R.distance, tclosest);
@@ -525,7 +560,15 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
 #pragma unroll
     for (int b = 0; b < RVB_NBANDS / 2; ++b) newVol[b] = __fmul2_rn(neg2(R.volume[b]), spec[b]);   // :461
 
-    const bool vis = point_visible(acc, X, mic, c);                          // :463
+    const f3 newDir = reflect(normal, R.dir);                                // :492-499 (independent of the visibility)
+    bool vis;
+    if constexpr (Accel::kFused) {
+        if (next && next->want) {
+            const f3 btp = mic - X;                                          // point_intersection, :274-296
+            const float mag = length(btp);
+            vis = !acc.visible_and_next(X, normalize(btp), mag, newDir, *next, c);
+        } else vis = point_visible(acc, X, mic, c);
+    } else vis = point_visible(acc, X, mic, c);                              // :463
     const float DIST = vis ? __fadd_rn(newDist, length(mic - X)) : 0.0f;     // :471
     const float DIFF = fabsf(dot(normal, R.dir));                            // :478
     float2 out[RVB_NBANDS / 2];
@@ -557,7 +600,7 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
     }
     if (P.hit) P.hit[slot] = prim;
 
-    R.dir = reflect(normal, R.dir);                                          // :492-499
+    R.dir = newDir;
     R.pos = X;
     R.distance = newDist;
 #pragma unroll
@@ -677,11 +720,26 @@ __device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TracePa
         R.volume[2] = make_float2(vb.x, vb.y); R.volume[3] = make_float2(vb.z, vb.w);
     }
     uint32_t index = P.first;
-    for (; index != P.last; ++index) {
+    if constexpr (Accel::kFused) {
+        // every reflection but the last asks for its successor's nearest hit together with its visibility
         float tclosest;
         uint32_t prim;
-        if (!acc.nearest(R.pos, R.dir, tclosest, prim, c)) break;                // :363-375
-        shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c);
+        bool hit = acc.nearest(R.pos, R.dir, tclosest, prim, c);                 // :363-375
+        while (hit) {
+            NextHit next{index + 1 != P.last, 0.0f, RVB_NONE};
+            shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c, &next);
+            ++index;
+            if (index == P.last) break;
+            tclosest = next.t; prim = next.prim;
+            hit = prim != RVB_NONE;
+        }
+    } else {
+        for (; index != P.last; ++index) {
+            float tclosest;
+            uint32_t prim;
+            if (!acc.nearest(R.pos, R.dir, tclosest, prim, c)) break;            // :363-375
+            shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c);
+        }
     }
     c.bounces += index - P.first;
     if (P.count) P.count[ray] = (P.first ? P.count[ray] : 0u) + (index - P.first);
