@@ -225,25 +225,43 @@ __global__ void emit_nodes_kernel(int n, const int2 *children, const int2 *range
             slots[ns++] = make_slot(g.y, ranges, tri_boxes, ids, node_boxes, rec_of);
         } else slots[ns++] = s;
     }
-    float lo[3][4], hi[3][4];
-    int ref[4];
-    for (int k = 0; k < 4; ++k) {
-        if (k < ns) {
-            const Aabb &b = slots[k].box;
-            lo[0][k] = b.lo.x - pad; lo[1][k] = b.lo.y - pad; lo[2][k] = b.lo.z - pad;
-            hi[0][k] = b.hi.x + pad; hi[1][k] = b.hi.y + pad; hi[2][k] = b.hi.z + pad;
-            ref[k] = slots[k].ref;
-        } else {
-            for (int a = 0; a < 3; ++a) { lo[a][k] = 3e38f; hi[a][k] = -3e38f; }
-            ref[k] = RVB_BVH_EMPTY;
-        }
+    // the node's own box = union of its (padded) child boxes: the quantisation grid
+    float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
+    float clo[4][3], chi[4][3];
+    for (int k = 0; k < ns; ++k) {
+        const Aabb &b = slots[k].box;
+        clo[k][0] = b.lo.x - pad; clo[k][1] = b.lo.y - pad; clo[k][2] = b.lo.z - pad;
+        chi[k][0] = b.hi.x + pad; chi[k][1] = b.hi.y + pad; chi[k][2] = b.hi.z + pad;
+        for (int a = 0; a < 3; ++a) { blo[a] = fminf(blo[a], clo[k][a]); bhi[a] = fmaxf(bhi[a], chi[k][a]); }
     }
     BvhNode nd;
-    nd.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); nd.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
-    nd.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); nd.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
-    nd.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]); nd.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
-    nd.ref = make_int4(ref[0], ref[1], ref[2], ref[3]);
-    nd.pad = make_float4(0.f, 0.f, 0.f, 0.f);
+    nd.exps = 0;
+    nd.pad[0] = nd.pad[1] = 0;
+    for (int a = 0; a < 3; ++a) {
+        nd.origin[a] = blo[a];
+        // cell size: the smallest power of two with 255 cells covering the extent (with a little room
+        // for the rounding of the decode); biased exponent kept in [1, 230] so that 2^15 * cell is a float
+        int e;
+        frexpf(fmaxf((bhi[a] - blo[a]) * 1.0001f / 255.0f, 1e-30f), &e);   // v < 2^e
+        e = min(max(e + 127, 1), 230);
+        nd.exps |= (uint32_t)e << (8 * a);
+        const float cell = __uint_as_float((uint32_t)e << 23);
+        uint32_t wlo = 0, whi = 0;
+        for (int k = 0; k < 4; ++k) {
+            int ql = 255, qh = 0;   // unused slot: inverted
+            if (k < ns) {
+                ql = (int)fminf(fmaxf(floorf((clo[k][a] - blo[a]) / cell), 0.0f), 255.0f);
+                qh = (int)fminf(fmaxf(ceilf((chi[k][a] - blo[a]) / cell), 0.0f), 255.0f);
+                // outward under the decode's own arithmetic
+                while (ql > 0 && fmaf((float)ql, cell, blo[a]) > clo[k][a]) --ql;
+                while (qh < 255 && fmaf((float)qh, cell, blo[a]) < chi[k][a]) ++qh;
+            }
+            wlo |= (uint32_t)ql << (8 * k);
+            whi |= (uint32_t)qh << (8 * k);
+        }
+        nd.qlo[a] = wlo; nd.qhi[a] = whi;
+    }
+    for (int k = 0; k < 4; ++k) nd.ref[k] = k < ns ? slots[k].ref : RVB_BVH_EMPTY;
     out[i] = nd;
 }
 

@@ -197,6 +197,18 @@ __global__ void bounds_kernel(const KeyT *keys, uint32_t n, uint32_t nseg, uint3
 // order -- one GPU vs. eight partial histograms -- differed from it by up to 2e-6 relative L2.  The
 // kernels are bound by the gathers, the double adds are free.
 // NSUB sub-bins x MAXC channels <= RVB_MAX_GROUP accumulator sets.
+// float -> double with integer instructions (the F2F conversion unit is slow enough to show in the
+// reduction: +0.46 ms on C2).  Exact for normal numbers and zero; denormals (< 1.2e-38) count as zero;
+// inf / nan take the real conversion.
+__device__ __forceinline__ double f2d_fast(float x)
+{
+    const uint32_t u = __float_as_uint(x);
+    const uint32_t ex = u & 0x7f800000u;
+    if (ex == 0x7f800000u) return (double)x;
+    const uint32_t hi = (((u & 0x7fffffffu) >> 3) + 0x38000000u) | (u & 0x80000000u);
+    return ex ? __hiloint2double((int)hi, (int)(u << 29)) : 0.0;
+}
+
 template <int MODEL, bool NEED_POS, int NSUB, int MAXC>
 __device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &C, uint32_t i, uint32_t sub, float4 va, float4 vb,
                                                double (&acc)[NSUB][MAXC][RVB_NBANDS])
@@ -231,7 +243,7 @@ __device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = __dadd_rn(acc[s][c][b], (double)term[c][b]);
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = __dadd_rn(acc[s][c][b], f2d_fast(term[c][b]));
         }
 }
 

@@ -74,19 +74,27 @@ int pinned_scratch(void **p, size_t bytes);                       // grown on de
 int read_back(void *dst, const void *d_src, size_t bytes);        // copy + synchronise the library stream of this thread
 
 // ---- BVH node (see bvh.cu) ------------------------------------------------------------------
-// 4-wide node, one 128-byte line: the boxes of up to four children in SoA form (slot k of every
-// float4), so one visit decides four descents and the dependent-load chain is half as long as with
-// a binary tree.  Child ref: >= 0 -> inner node index; < 0 (and != RVB_BVH_EMPTY) -> leaf:
-// ~ref = first position in the sorted triangle order | (count - 1) << 28.  Unused slots carry
-// RVB_BVH_EMPTY and an inverted box.
+// 4-wide node in HALF a cache line (64 bytes, two 32-byte loads).  The bounce kernels are bound by the
+// L1 data pipe, which moves a divergent warp's node fetches 16-32 bytes per lane and cycle (ncu:
+// l1tex data-pipe wavefronts at 85-90 % of peak with 128-byte nodes), so the child boxes are stored
+// quantised: 8 bits per plane on a grid spanned by the node's own box -- origin (3 floats) and one
+// power-of-two cell size per axis -- rounded OUTWARDS, so a quantised box contains the exact one.
+//   plane = origin + q * 2^(e - 127)
+// q bytes are grouped by plane (qlo[axis] / qhi[axis] hold the four children's bytes) so that one PRMT
+// per value drops a byte into a float's mantissa (trace.cu: BvhAccel::visit).
+// Child ref: >= 0 -> inner node index; < 0 (and != RVB_BVH_EMPTY) -> leaf:
+// ~ref = leaf record | (count - 1) << 28.  Unused slots carry RVB_BVH_EMPTY.
 #define RVB_BVH_EMPTY ((int)0x80000001)
 #define RVB_LEAF_STRIDE 10           // float4 per leaf record: 9 of triangle data + 1 of triangle indices (160 bytes)
 #define RVB_BVH_STACK 96             // traversal stack entries per thread (bvh.cu refuses deeper hierarchies)
-struct __align__(16) BvhNode {
-    float4 lox, loy, loz, hix, hiy, hiz;
-    int4 ref;
-    float4 pad;
+struct __align__(32) BvhNode {
+    float origin[3];
+    uint32_t exps;            // biased exponents of the cell sizes: x | y << 8 | z << 16
+    uint32_t qlo[3], qhi[3];  // byte k of qlo[a] / qhi[a]: child k's lower / upper plane on axis a
+    int ref[4];
+    uint32_t pad[2];
 };
+static_assert(sizeof(BvhNode) == 64, "BvhNode is half a cache line");
 
 // ---- scene ----------------------------------------------------------------------------------
 struct Scene {

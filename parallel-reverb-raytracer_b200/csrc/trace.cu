@@ -301,32 +301,46 @@ struct BvhAccel {
         return tn <= tf * 1.00001f + 1e-6f ? tn : RVB_INF;
     }
 
-    // One visit of a 4-wide node: test the four child boxes (two children per packed fma), continue
-    // with the nearest hit child and push the others so that the nearer ones are popped first.
-    // Returns the next node.
+    // One visit of a 4-wide node: decode and test the four child boxes, continue with the nearest hit
+    // child and push the others so that the nearer ones are popped first.  Returns the next node.
+    //
+    // The node is 64 bytes (rvb_internal.cuh): plane = origin + q * cell, q a byte.  With
+    // m = 1 + q * 2^-15 (the byte dropped into a float's mantissa by ONE PRMT) the plane distance is
+    //   t = plane * inv + oinv = m * A + B,   A = 2^15 * cell * inv,   B = (origin * inv + oinv) - A
+    // i.e. still one fma per plane (two children per packed fma); A and B cost nine operations per
+    // node.  Rounding: B is rounded at magnitude ~2^15 cell |inv|, i.e. the planes move by ~2^-9 of a
+    // cell -- far inside the padding every box carries (the q are rounded outwards on top of it).
     __device__ __forceinline__ static int visit(const BvhNode *nodes, int node, const SlabRay &sr, float tbest, const TravStack &stack, int &sp)
     {
         const char *np = reinterpret_cast<const char *>(nodes + node);
-        const f8 n0 = ldg256(np), n1 = ldg256(np + 32), n2 = ldg256(np + 64), n3 = ldg256(np + 96);
-        const float4 lox = n0.a, loy = n0.b, loz = n1.a, hix = n1.b, hiy = n2.a, hiz = n2.b;
-        const int4 ref = make_int4(__float_as_int(n3.a.x), __float_as_int(n3.a.y), __float_as_int(n3.a.z), __float_as_int(n3.a.w));
+        const f8 n0 = ldg256(np), n1 = ldg256(np + 32);
+        const uint32_t exps = __float_as_uint(n0.a.w);
+        const uint32_t qlx = __float_as_uint(n0.b.x), qly = __float_as_uint(n0.b.y), qlz = __float_as_uint(n0.b.z);
+        const uint32_t qhx = __float_as_uint(n0.b.w), qhy = __float_as_uint(n1.a.x), qhz = __float_as_uint(n1.a.y);
+        int r0 = __float_as_int(n1.a.z), r1 = __float_as_int(n1.a.w), r2 = __float_as_int(n1.b.x), r3 = __float_as_int(n1.b.y);
+        const float Ax = __uint_as_float(((exps & 0xffu) + 15u) << 23) * sr.inv.x;
+        const float Ay = __uint_as_float((((exps >> 8) & 0xffu) + 15u) << 23) * sr.inv.y;
+        const float Az = __uint_as_float((((exps >> 16) & 0xffu) + 15u) << 23) * sr.inv.z;
+        const float Bx = __fmaf_rn(n0.a.x, sr.inv.x, sr.oinv.x) - Ax;
+        const float By = __fmaf_rn(n0.a.y, sr.inv.y, sr.oinv.y) - Ay;
+        const float Bz = __fmaf_rn(n0.a.z, sr.inv.z, sr.oinv.z) - Az;
         // candidates farther than the best are useless; equal t must still be visited (tie-break)
         const float lim = tbest * 1.00001f + 1e-6f;
         const float INF = RVB_INF;
-        const float2 ix = bcast2(sr.inv.x), iy = bcast2(sr.inv.y), iz = bcast2(sr.inv.z);
-        const float2 ox = bcast2(sr.oinv.x), oy = bcast2(sr.oinv.y), oz = bcast2(sr.oinv.z);
-        const float2 ax0 = __ffma2_rn(make_float2(lox.x, lox.y), ix, ox), bx0 = __ffma2_rn(make_float2(lox.z, lox.w), ix, ox);
-        const float2 ax1 = __ffma2_rn(make_float2(hix.x, hix.y), ix, ox), bx1 = __ffma2_rn(make_float2(hix.z, hix.w), ix, ox);
-        const float2 ay0 = __ffma2_rn(make_float2(loy.x, loy.y), iy, oy), by0 = __ffma2_rn(make_float2(loy.z, loy.w), iy, oy);
-        const float2 ay1 = __ffma2_rn(make_float2(hiy.x, hiy.y), iy, oy), by1 = __ffma2_rn(make_float2(hiy.z, hiy.w), iy, oy);
-        const float2 az0 = __ffma2_rn(make_float2(loz.x, loz.y), iz, oz), bz0 = __ffma2_rn(make_float2(loz.z, loz.w), iz, oz);
-        const float2 az1 = __ffma2_rn(make_float2(hiz.x, hiz.y), iz, oz), bz1 = __ffma2_rn(make_float2(hiz.z, hiz.w), iz, oz);
+#define RVB_M(w, k) __uint_as_float(__byte_perm((w), 0x3f800000u, 0x7604u | ((k) << 4)))   /* 1 + byte k * 2^-15 */
+#define RVB_PLANES(w, A, B, ta, tb)                                                                              \
+        const float2 ta = __ffma2_rn(make_float2(RVB_M(w, 0u), RVB_M(w, 1u)), bcast2(A), bcast2(B)),              \
+                     tb = __ffma2_rn(make_float2(RVB_M(w, 2u), RVB_M(w, 3u)), bcast2(A), bcast2(B));
+        RVB_PLANES(qlx, Ax, Bx, ax0, bx0) RVB_PLANES(qhx, Ax, Bx, ax1, bx1)
+        RVB_PLANES(qly, Ay, By, ay0, by0) RVB_PLANES(qhy, Ay, By, ay1, by1)
+        RVB_PLANES(qlz, Az, Bz, az0, bz0) RVB_PLANES(qhz, Az, Bz, az1, bz1)
+#undef RVB_PLANES
+#undef RVB_M
         float t0 = slab_hit(ax0.x, ax1.x, ay0.x, ay1.x, az0.x, az1.x, lim);
         float t1 = slab_hit(ax0.y, ax1.y, ay0.y, ay1.y, az0.y, az1.y, lim);
         float t2 = slab_hit(bx0.x, bx1.x, by0.x, by1.x, bz0.x, bz1.x, lim);
         float t3 = slab_hit(bx0.y, bx1.y, by0.y, by1.y, bz0.y, bz1.y, lim);
-        int r0 = ref.x, r1 = ref.y, r2 = ref.z, r3 = ref.w;
-        // slots 0 and 1 always exist; the min/max slab form would accept an unused slot's box
+        // slots 0 and 1 always exist; unused slots are marked in the ref
         if (r2 == RVB_BVH_EMPTY) t2 = INF;
         if (r3 == RVB_BVH_EMPTY) t3 = INF;
         // sorting network on (t, ref), ascending; misses carry +inf
@@ -922,7 +936,10 @@ static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
     }
     static const int forced = getenv("RVB_BLOCK") ? atoi(getenv("RVB_BLOCK")) : 0;
     const int sizes[5] = {256, 384, 512, 768, 1024};
-    const float eff[5] = {1.0f, 1.0f, 1.0f, 0.9f, 0.7f};
+    // steady phase (fused two-ray sweep, ~128 registers): 512 threads measured best on C2 and on the
+    // 4352-triangle room (profiles/r2_sweep_bruteforce_block.log); image phase: as in round 1
+    const float eff_images[5] = {1.0f, 1.0f, 1.0f, 0.9f, 0.7f}, eff_steady[5] = {0.9f, 0.7f, 1.0f, 0.6f, 0.49f};
+    const float *eff = IMAGES ? eff_images : eff_steady;
     int per_sm[5] = {0, 0, 0, 0, 0};
     RVB_TRY((try_block<IMAGES, 256>(P, smem, per_sm[0])));
     RVB_TRY((try_block<IMAGES, 384>(P, smem, per_sm[1])));
@@ -1228,7 +1245,13 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
             if (brute) RVB_TRY(launch_bruteforce<false>(P, smem, st));
-            else if (!wavefront) RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, smem, st));
+            else if (!wavefront) {
+                // resident CTAs of 128 threads per SM (register cap 65536 / (128 n)); RVB_BVH_MINB overrides
+                static const int minb = getenv("RVB_BVH_MINB") ? atoi(getenv("RVB_BVH_MINB")) : 7;
+                if (minb <= 5) RVB_TRY(launch_phase(trace_bvh_kernel<false, 5>, P, 128, smem, st));
+                else if (minb == 6) RVB_TRY(launch_phase(trace_bvh_kernel<false, 6>, P, 128, smem, st));
+                else RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, smem, st));
+            }
             else RVB_TRY(launch_wavefront(P, smem, st));
         }
     } else if (tr->nrays > 0 && images && tr->ray_offset == 0) {
