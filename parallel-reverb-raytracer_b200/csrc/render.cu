@@ -191,27 +191,16 @@ __global__ void bounds_kernel(const KeyT *keys, uint32_t n, uint32_t nseg, uint3
 // One warp per segment: lane l takes entries begin+l, begin+l+32, ... in order (four gathers in
 // flight per lane), then a fixed xor-shuffle tree combines the 32 partial sums of every
 // (sub-bin, channel, band).  hist layout: [channel][band][L].
-// The partial sums are kept in DOUBLE and rounded to float once per bin: the reference adds a bin's
-// impulses one by one in float (rayverb.cpp:67-74); with the sign of the volume flipping at every
-// reflection (kernel.cpp:461) the high bands cancel heavily, and a float tree sum in a different
-// order -- one GPU vs. eight partial histograms -- differed from it by up to 2e-6 relative L2.  The
-// kernels are bound by the gathers, the double adds are free.
+// Every lane adds its (few) impulses in float, as the reference does (rayverb.cpp:67-74); the lanes'
+// and warps' partial sums are then combined in DOUBLE and rounded to float once per bin.  With the
+// sign of the volume flipping at every reflection (kernel.cpp:461) the high bands cancel heavily, and
+// an all-float tree in a different grouping -- one GPU vs. eight partial histograms -- differed by up to
+// 2e-6 relative L2.  (Accumulating every impulse in double was measured too: the conversions cost
+// +0.5 ms on C2 and far more on the two-channel C3 reduction.)
 // NSUB sub-bins x MAXC channels <= RVB_MAX_GROUP accumulator sets.
-// float -> double with integer instructions (the F2F conversion unit is slow enough to show in the
-// reduction: +0.46 ms on C2).  Exact for normal numbers and zero; denormals (< 1.2e-38) count as zero;
-// inf / nan take the real conversion.
-__device__ __forceinline__ double f2d_fast(float x)
-{
-    const uint32_t u = __float_as_uint(x);
-    const uint32_t ex = u & 0x7f800000u;
-    if (ex == 0x7f800000u) return (double)x;
-    const uint32_t hi = (((u & 0x7fffffffu) >> 3) + 0x38000000u) | (u & 0x80000000u);
-    return ex ? __hiloint2double((int)hi, (int)(u << 29)) : 0.0;
-}
-
 template <int MODEL, bool NEED_POS, int NSUB, int MAXC>
 __device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &C, uint32_t i, uint32_t sub, float4 va, float4 vb,
-                                               double (&acc)[NSUB][MAXC][RVB_NBANDS])
+                                               float (&acc)[NSUB][MAXC][RVB_NBANDS])
 {
     const float v[RVB_NBANDS] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
     float term[MAXC][RVB_NBANDS];
@@ -243,12 +232,36 @@ __device__ __forceinline__ void accumulate_one(const Source &S, const ChanSpec &
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = __dadd_rn(acc[s][c][b], f2d_fast(term[c][b]));
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = __fadd_rn(acc[s][c][b], term[c][b]);
         }
 }
 
+// Sum of 32 values per lane over the 32 lanes of a warp: lane l ends up with the total of value l.
+// A butterfly that halves the values a lane holds at every step (16 + 8 + 4 + 2 + 1 = 31 exchanges
+// instead of 32 five-step trees), in a fixed order => deterministic.  In double (see above).
+__device__ __forceinline__ double warp_reduce_32x32(const float (&acc)[32], uint32_t lane)
+{
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {   // step 16: lanes 16..31 keep values 16..31
+        const bool up = lane & 16u;
+        const double keep = (double)(up ? acc[16 + i] : acc[i]), send = (double)(up ? acc[i] : acc[16 + i]);
+        v[i] = __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        const bool up = lane & (uint32_t)o;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const double keep = up ? v[o + i] : v[i], send = up ? v[i] : v[o + i];
+            v[i] = __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
+        }
+    }
+    return v[0];
+}
+
 template <int MODEL, bool NEED_POS, int NSUB, int MAXC>
-__global__ void __launch_bounds__(256, 2) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *keys, const uint32_t *vals,
+__global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanSpec C, const uint32_t *keys, const uint32_t *vals,
                                                      const uint32_t *seg_begin, const uint32_t *seg_end, uint32_t nseg, uint32_t L,
                                                      float *hist, size_t chan_stride)
 {
@@ -260,13 +273,13 @@ __global__ void __launch_bounds__(256, 2) reduce_kernel(const Source S, const Ch
         const uint32_t seg = nseg - 1 - w;
         const uint32_t b0 = seg_begin[seg], b1 = seg_end[seg];
         if (b0 == b1) continue;   // warp-uniform
-        double acc[NSUB][MAXC][RVB_NBANDS];
+        float acc[NSUB][MAXC][RVB_NBANDS];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0;
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0f;
         for (uint32_t j = b0 + lane; j < b1; j += 128) {
             uint32_t idx[4], sub[4];
             float4 va[4], vb[4];
@@ -292,18 +305,12 @@ __global__ void __launch_bounds__(256, 2) reduce_kernel(const Source S, const Ch
             for (int u = 0; u < 4; ++u)
                 if (idx[u] != RVB_NO_IMPULSE) accumulate_one<MODEL, NEED_POS, NSUB, MAXC>(S, C, idx[u], sub[u], va[u], vb[u], acc);
         }
-#pragma unroll
-        for (int s = 0; s < NSUB; ++s) {
-            const uint32_t bin = seg * NSUB + s;
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c) {
-#pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) {
-                    double x = acc[s][c][b];
-                    for (int o = 16; o; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
-                    if (lane == 0 && c < C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = (float)x;
-                }
-            }
+        {
+            static_assert(NSUB * MAXC * RVB_NBANDS == 32, "one lane per (sub-bin, channel, band) after the butterfly");
+            const double x = warp_reduce_32x32(reinterpret_cast<const float (&)[32]>(acc), lane);
+            const uint32_t b = lane % RVB_NBANDS, c = (lane / RVB_NBANDS) % MAXC, sb = lane / (RVB_NBANDS * MAXC);
+            const uint32_t bin = seg * NSUB + sb;
+            if (c < (uint32_t)C.nch && bin < L) hist[(size_t)c * chan_stride + (size_t)b * L + bin] = (float)x;
         }
     }
 }
@@ -331,13 +338,13 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
         if (b0 == b1) continue;   // block-uniform
         const uint32_t chunk = (b1 - b0 + RVB_REDUCE_WARPS - 1) / RVB_REDUCE_WARPS;
         const uint32_t m0 = min(b1, b0 + wid * chunk), m1 = min(b1, m0 + chunk);
-        double acc[NSUB][MAXC][RVB_NBANDS];
+        float acc[NSUB][MAXC][RVB_NBANDS];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0;
+                for (int b = 0; b < RVB_NBANDS; ++b) acc[s][c][b] = 0.0f;
         for (uint32_t j = m0 + lane; j < m1; j += 128) {
             uint32_t idx[4], sub[4];
             float4 va[4], vb[4];
@@ -363,16 +370,7 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
             for (int u = 0; u < 4; ++u)
                 if (idx[u] != RVB_NO_IMPULSE) accumulate_one<MODEL, NEED_POS, NSUB, MAXC>(S, C, idx[u], sub[u], va[u], vb[u], acc);
         }
-#pragma unroll
-        for (int s = 0; s < NSUB; ++s)
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c)
-#pragma unroll
-                for (int b = 0; b < RVB_NBANDS; ++b) {
-                    double x = acc[s][c][b];
-                    for (int o = 16; o; o >>= 1) x = __dadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
-                    if (lane == 0) part[wid][(s * MAXC + c) * RVB_NBANDS + b] = x;
-                }
+        part[wid][lane] = warp_reduce_32x32(reinterpret_cast<const float (&)[32]>(acc), lane);   // value index = (s * MAXC + c) * 8 + b
         __syncthreads();
         if (wid == 0) {
             double x = part[0][lane];

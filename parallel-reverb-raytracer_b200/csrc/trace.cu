@@ -1193,12 +1193,13 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
     float4 *d_state = nullptr;
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
-    // BVH scenes, steady phase: one thread per ray (default) or the persistent wavefront kernel
-    // (RVB_WAVEFRONT=1).  Measured on the C3 hall (profiles/r2_bvh_kernels.md): both forms end up bound
-    // by the L1 data pipe (80-90 % of its peak), which serves the lanes' node fetches one line at a time;
-    // the wavefront form packs 15 instead of 11 lanes per instruction but is 0-10 % slower with many rays
-    // and 30 % slower with a single wave of rays per GPU, where its lane refill has nothing to refill.
-    static const bool wavefront = getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '1';
+    // BVH scenes, steady phase: the persistent wavefront kernel when there are several waves of rays
+    // (its lanes pick up new rays as they finish: C3, 1 Mi rays: 52.5 ms against 61.5 ms), one thread per
+    // ray when every ray finds a lane at once (a 131 k-ray shard: 8.2 ms against 9.1 ms -- nothing to
+    // refill, and the per-ray form's lanes start every query together).  RVB_WAVEFRONT=0 / 1 forces one.
+    // Both are bound by the L1 data pipe (profiles/r2_bvh_kernels.md).
+    static const int wf_env = getenv("RVB_WAVEFRONT") ? atoi(getenv("RVB_WAVEFRONT")) : -1;
+    const bool wavefront = wf_env >= 0 ? wf_env != 0 : (size_t)tr->nrays >= (size_t)3 * 7 * 128 * sm_count();
     if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
     P.state = d_state;
     // brute force: the whole scene; BVH: the traversal stacks (one column of Scene::bvh_stack entries per thread)

@@ -41,9 +41,34 @@ static float mt(const Tri &t, V3 pos, V3 dir, bool &ok)
 }
 
 // ---- the map, as the CUDA build computes it -----------------------------------------------------------
-struct Rect { int i0, i1, j0, j1; };
+struct Rect { int i0, i1, j0, j1; int np; float pu[4], pv[4], margin; };
+static bool g_exact = true;
+// is cell (i, j) certainly outside the projected polygon grown by r.margin?
+static bool cell_outside(const Rect &r, int i, int j, int N)
+{
+    if (!g_exact || r.np < 3) return false;
+    const float h = 2.0f / N;
+    const float cu0 = -1.0f + i * h, cu1 = cu0 + h, cv0 = -1.0f + j * h, cv1 = cv0 + h;
+    // orientation
+    float area = 0;
+    for (int k = 0; k < r.np; ++k) { const int k1 = (k + 1) % r.np; area += r.pu[k] * r.pv[k1] - r.pu[k1] * r.pv[k]; }
+    if (fabsf(area) < 1e-12f) return false;
+    const float sgn = area > 0 ? 1.0f : -1.0f;
+    for (int k = 0; k < r.np; ++k) {
+        const int k1 = (k + 1) % r.np;
+        // outward normal of edge k -> k1 (for a counter-clockwise polygon: (dv, -du))
+        const float du = r.pu[k1] - r.pu[k], dv = r.pv[k1] - r.pv[k];
+        const float nu = sgn * dv, nv = -sgn * du;
+        const float len = sqrtf(nu * nu + nv * nv);
+        if (len == 0) continue;
+        const float cu = nu > 0 ? cu0 : cu1, cv = nv > 0 ? cv0 : cv1;   // the cell corner deepest inside
+        if (nu * (cu - r.pu[k]) + nv * (cv - r.pv[k]) > (r.margin + 1e-5f) * len * 1.0001f + 1e-7f) return true;
+    }
+    return false;
+}
 static bool face_rect(const V3 p[3], int face, float wc, float delta, int N, Rect &r)
 {
+    r.np = 0; r.margin = 0;
     const int a = face >> 1;
     const float s = (face & 1) ? -1.0f : 1.0f;
     float w[3], ub[3], vc[3];
@@ -56,8 +81,13 @@ static bool face_rect(const V3 p[3], int face, float wc, float delta, int N, Rec
     auto add = [&](float W, float U, float Vv) {
         const float wn = W - delta, wf = W + delta;   // wn > 0 because wc > delta
         const float u0 = U - delta, u1 = U + delta, v0 = Vv - delta, v1 = Vv + delta;
-        ulo = std::min(ulo, std::min(u0 / wn, u0 / wf)); uhi = std::max(uhi, std::max(u1 / wn, u1 / wf));
-        vlo = std::min(vlo, std::min(v0 / wn, v0 / wf)); vhi = std::max(vhi, std::max(v1 / wn, v1 / wf));
+        const float a0 = std::min(u0 / wn, u0 / wf), a1 = std::max(u1 / wn, u1 / wf), b0 = std::min(v0 / wn, v0 / wf), b1 = std::max(v1 / wn, v1 / wf);
+        ulo = std::min(ulo, a0); uhi = std::max(uhi, a1); vlo = std::min(vlo, b0); vhi = std::max(vhi, b1);
+        const float pu = U / W, pv = Vv / W;
+        if (r.np < 4) { r.pu[r.np] = pu; r.pv[r.np] = pv; ++r.np; }
+        // the grown vertex projects inside [a0, a1] x [b0, b1]: its distance from (pu, pv) is at most the box's half diagonal
+        const float mu = std::max(a1 - pu, pu - a0), mv = std::max(b1 - pv, pv - b0);
+        r.margin = std::max(r.margin, sqrtf(mu * mu + mv * mv));
     };
     for (int k = 0; k < 3; ++k) {
         const int k1 = (k + 1) % 3;
@@ -105,6 +135,7 @@ int main(int argc, char **argv)
     if (argc > 4) mic = {(float)atof(argv[2]), (float)atof(argv[3]), (float)atof(argv[4])};
     const float delta_rel = argc > 5 ? (float)atof(argv[5]) : 1e-4f;
     const float cpt = argc > 6 ? (float)atof(argv[6]) : 4.0f;
+    g_exact = !(argc > 8 && atoi(argv[8]) == 0);
     const int T = (int)tris.size();
     V3 lo = {3e38f, 3e38f, 3e38f}, hi = {-3e38f, -3e38f, -3e38f};
     for (auto &t : tris) for (V3 p : {t.a, t.b, t.c}) {
@@ -133,7 +164,10 @@ int main(int argc, char **argv)
         for (int f = 0; f < 6; ++f) {
             Rect r;
             if (!face_rect(p, f, wc, delta, N, r)) continue;
-            for (int j = r.j0; j <= r.j1; ++j) for (int ii = r.i0; ii <= r.i1; ++ii) { cells[(f * N + j) * N + ii].push_back(i); ++entries; }
+            for (int j = r.j0; j <= r.j1; ++j) for (int ii = r.i0; ii <= r.i1; ++ii) {
+                if (cell_outside(r, ii, j, N)) continue;
+                cells[(f * N + j) * N + ii].push_back(i); ++entries;
+            }
         }
     }
     size_t mx = 0; for (auto &c : cells) mx = std::max(mx, c.size());
@@ -155,6 +189,7 @@ int main(int argc, char **argv)
     std::mt19937 rng(12345);
     std::uniform_real_distribution<float> U(0, 1);
     const int nrand = argc > 7 ? atoi(argv[7]) : 20000;
+    
     for (int k = 0; k < nrand; ++k) {
         const Tri &t = tris[rng() % T];
         float a = U(rng), b = U(rng);

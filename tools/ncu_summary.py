@@ -14,7 +14,12 @@ METRICS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__bl
            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "smsp__warps_eligible.avg.per_cycle_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-           "sm__icc_request_hit_rate.pct"]
+           "sm__icc_request_hit_rate.pct",
+           # the L1 data pipe: what bounds the BVH bounce kernels (divergent node / leaf fetches)
+           "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+           "l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_st.sum",
+           "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 STALLS = "smsp__pcsamp_warps_issue_stalled_"
 
 
