@@ -935,6 +935,7 @@ static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
         }
     }
     static const int forced = getenv("RVB_BLOCK") ? atoi(getenv("RVB_BLOCK")) : 0;
+    if (forced == 640) return launch_phase(trace_bruteforce_kernel<IMAGES, 640>, P, 640, smem, st);   // experiment: 20 warps at <= 102 registers
     const int sizes[5] = {256, 384, 512, 768, 1024};
     // steady phase (fused two-ray sweep, ~128 registers): 512 threads measured best on C2 and on the
     // 4352-triangle room (profiles/r2_sweep_bruteforce_block.log); image phase: as in round 1

@@ -1,0 +1,23 @@
+#!/bin/bash
+# strong scaling of the default workload (C3) + where the sharded step's time goes
+O=gpurun_out/r2n; mkdir -p $O
+cd "$(dirname "$0")/.."
+NMAX=${1:-8}
+for N in 1 2 4 8; do
+  [ $N -gt $NMAX ] && continue
+  if [ $N -eq 1 ]; then
+    timeout 900 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --no-sub-blocks > $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err
+  else
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err
+  fi
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$O/bench_${N}gpu.json").read().strip().splitlines()[-1])
+    print("N=%d ms/step %.2f value %.4g e2e %.4g" % (d["n_gpus"], d["ms_per_step"], d["value"], d["e2e"]["value"]), {k: round(v,2) for k,v in d["stages_ms"].items()}, d.get("sharded_parity"))
+except Exception as e:
+    print("N=$N FAILED", e)
+PY
+done
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NMAX --master-addr 127.0.0.1 --master-port 29512 tools/shard_timeline.py > $O/timeline_${NMAX}gpu.log 2>&1
+grep "it 5" $O/timeline_${NMAX}gpu.log | sort | head -8

@@ -13,7 +13,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 api.set_stream(torch.cuda.current_stream().cuda_stream)
 sys.path.insert(0, ROOT)
 import bench
-wl_name = sys.argv[1] if len(sys.argv) > 1 else "C2_shoebox_12tri_1Mx128_omni"
+wl_name = sys.argv[1] if len(sys.argv) > 1 else "C3_hall_100ktri_1Mx128_stereo"
 wl = bench.WORKLOADS[wl_name]
 tri, vtx, srf = bench.build_scene(wl["scene"])
 if wl["scaling"] == "weak":
@@ -35,17 +35,16 @@ for it in range(6):
     tr = rt.raytrace(MIC, SRC, None, ray_offset=lo, device_ptr=dirs.data_ptr(), nrays=nrays); mark()
     mn, mx = tr.render_times(cfg); mark()
     img, keys, klen = tr.raw_images(with_keys=True); mark()
-    predelay, gmx, counts = sharding.exchange_extrema(mn, mx, len(img), world, "cuda"); mark()
+    predelay, gmx, merged, mlen = sharding.exchange(mn, mx, img, keys, klen, rank, world, "cuda"); mark()
     lengths = [sharding.flatten_length(m, predelay, False, 44100.0) for m in gmx]
-    merged = sharding.merge_images(img, keys, klen, counts, rank, world, "cuda"); mark()
     tr.set_images(merged); mark()
-    hist = torch.zeros(sum(NBANDS * l for l in lengths), device="cuda", dtype=torch.float32); mark()
+    hist = torch.empty(sum(NBANDS * l for l in lengths), device="cuda", dtype=torch.float32); mark()
     tr.render_histogram(cfg, predelay, lengths, hist.data_ptr()); mark()
     dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM); mark()
     if rank == 0:
         ir = api.render_finish(cfg, hist.data_ptr(), lengths)
     mark()
-    names = ["raytrace", "render_times", "raw_images(D2H)", "exchange_extrema(allgather)", "merge_images(gather+host)", "set_images", "hist alloc", "render_histogram", "reduce(NCCL)", "finish(rank0)"]
+    names = ["raytrace", "render_times", "raw_images(D2H)", "exchange(allgather+merge)", "set_images", "hist alloc", "render_histogram", "reduce(NCCL)", "finish(rank0)"]
     d = [1e3 * (T[i + 1] - T[i]) for i in range(len(T) - 1)]
     print(f"rank {rank} it {it} total {1e3*(T[-1]-T[0]):.2f} ms: " + ", ".join(f"{n} {v:.2f}" for n, v in zip(names, d)) + f" | images {len(img)} L {lengths}", flush=True)
 dist.destroy_process_group()
