@@ -1,11 +1,12 @@
 // Build of the microphone visibility map (see micmap.cuh for what it is and why it is exact).
 //
-// One thread per triangle, two passes (count, fill) around a device-wide exclusive scan.  For each
+// One warp per triangle, two passes (count, fill) around a device-wide exclusive scan.  For each
 // cube face the triangle is clipped against w >= wc (w = depth along the face axis), its vertices
-// are grown by `delta` in world space, projected to (u, v) = (b / w, c / w) and the bounding
-// rectangle of the result -- plus an absolute slack for the rounding of the query's own cell
-// computation -- is registered in every cell it touches.  Entries inside a cell are in no
-// particular order: a visibility query is an OR over its cell's triangles.
+// are grown by `delta` in world space and projected to (u, v) = (b / w, c / w); the triangle is
+// registered in every cell of the bounding rectangle of the result -- plus an absolute slack for the
+// rounding of the query's own cell computation -- that a separating-edge test against the projected
+// polygon (grown by the same margins) cannot exclude.  Entries inside a cell are in no particular
+// order: a visibility query is an OR over its cell's triangles.
 //
 // tools/bvh_lab/micmap_lab.cpp runs this very construction on the CPU against the brute-force loop
 // (canonical float arithmetic) for traced and adversarial queries, including a microphone a few
@@ -28,14 +29,45 @@ struct MicMapParams {
     uint32_t near_cap;
 };
 
-struct FaceRect { uint32_t i0, i1, j0, j1; };
+// cell rectangle of a triangle on one cube face + the projected (clipped) polygon and the margin it was
+// grown by, for the per-cell test
+struct FaceRect { uint32_t i0, i1, j0, j1; int np; float pu[4], pv[4], margin; };
 
-__device__ __forceinline__ void grow_uv(float W, float U, float V, float delta, float &ulo, float &uhi, float &vlo, float &vhi)
+__device__ __forceinline__ void grow_uv(float W, float U, float V, float delta, float &ulo, float &uhi, float &vlo, float &vhi, FaceRect &r)
 {
     const float wn = W - delta, wf = W + delta;   // wn > 0: W >= wc = 20 delta
     const float u0 = U - delta, u1 = U + delta, v0 = V - delta, v1 = V + delta;
-    ulo = fminf(ulo, fminf(u0 / wn, u0 / wf)); uhi = fmaxf(uhi, fmaxf(u1 / wn, u1 / wf));
-    vlo = fminf(vlo, fminf(v0 / wn, v0 / wf)); vhi = fmaxf(vhi, fmaxf(v1 / wn, v1 / wf));
+    const float a0 = fminf(u0 / wn, u0 / wf), a1 = fmaxf(u1 / wn, u1 / wf), b0 = fminf(v0 / wn, v0 / wf), b1 = fmaxf(v1 / wn, v1 / wf);
+    ulo = fminf(ulo, a0); uhi = fmaxf(uhi, a1); vlo = fminf(vlo, b0); vhi = fmaxf(vhi, b1);
+    // the vertex itself and how far its grown image can project from it
+    const float pu = U / W, pv = V / W;
+    if (r.np < 4) { r.pu[r.np] = pu; r.pv[r.np] = pv; ++r.np; }
+    const float mu = fmaxf(a1 - pu, pu - a0), mv = fmaxf(b1 - pv, pv - b0);
+    r.margin = fmaxf(r.margin, sqrtf(mu * mu + mv * mv));
+}
+
+// Is cell (i, j) certainly outside the projected polygon grown by its margin?  (Separating-edge test
+// against the cell corner that lies deepest inside; a degenerate, edge-on polygon rejects nothing.)
+__device__ __forceinline__ bool cell_outside(const FaceRect &r, uint32_t i, uint32_t j, uint32_t N)
+{
+    if (r.np < 3) return false;
+    const float h = 2.0f / (float)N;
+    const float cu0 = -1.0f + (float)i * h, cu1 = cu0 + h, cv0 = -1.0f + (float)j * h, cv1 = cv0 + h;
+    float area = 0.0f;
+    for (int k = 0; k < r.np; ++k) { const int k1 = (k + 1) % r.np; area += r.pu[k] * r.pv[k1] - r.pu[k1] * r.pv[k]; }
+    if (fabsf(area) < 1e-12f) return false;
+    const float sgn = area > 0.0f ? 1.0f : -1.0f;
+    for (int k = 0; k < r.np; ++k) {
+        const int k1 = (k + 1) % r.np;
+        const float du = r.pu[k1] - r.pu[k], dv = r.pv[k1] - r.pv[k];
+        const float nu = sgn * dv, nv = -sgn * du;               // outward normal of edge k -> k1
+        const float len = sqrtf(nu * nu + nv * nv);
+        if (len == 0.0f) continue;
+        const float cu = nu > 0.0f ? cu0 : cu1, cv = nv > 0.0f ? cv0 : cv1;
+        // (the cell bounds above are recomputed from the index, hence the 2e-5 on top of the map's own 1e-5 slack)
+        if (nu * (cu - r.pu[k]) + nv * (cv - r.pv[k]) > (r.margin + 3e-5f) * len * 1.0001f + 1e-7f) return true;
+    }
+    return false;
 }
 
 // p: the triangle's vertices relative to the microphone
@@ -48,13 +80,14 @@ __device__ __forceinline__ bool face_rect(const float (&p)[3][3], int face, cons
     for (int k = 0; k < 3; ++k) { w[k] = s * p[k][a]; ub[k] = p[k][b]; vc[k] = p[k][c]; }
     if (w[0] < M.wc && w[1] < M.wc && w[2] < M.wc) return false;
     float ulo = 3e38f, uhi = -3e38f, vlo = 3e38f, vhi = -3e38f;
+    r.np = 0; r.margin = 0.0f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int k1 = (k + 1) % 3;
-        if (w[k] >= M.wc) grow_uv(w[k], ub[k], vc[k], M.delta, ulo, uhi, vlo, vhi);
+        if (w[k] >= M.wc) grow_uv(w[k], ub[k], vc[k], M.delta, ulo, uhi, vlo, vhi, r);
         if ((w[k] < M.wc) != (w[k1] < M.wc)) {   // the edge crosses the clip plane
             const float t = (M.wc - w[k]) / (w[k1] - w[k]);
-            grow_uv(M.wc, ub[k] + t * (ub[k1] - ub[k]), vc[k] + t * (vc[k1] - vc[k]), M.delta, ulo, uhi, vlo, vhi);
+            grow_uv(M.wc, ub[k] + t * (ub[k1] - ub[k]), vc[k] + t * (vc[k1] - vc[k]), M.delta, ulo, uhi, vlo, vhi, r);
         }
     }
     const float slack = 1e-5f;   // rounding of the query's (u, v)
@@ -102,7 +135,9 @@ __global__ void __launch_bounds__(128) micmap_bin_kernel(const MicMapParams M, u
         if (!face_rect(p, f, M, r)) continue;   // warp-uniform: every lane computes the same rectangle
         const uint32_t w = r.i1 - r.i0 + 1, n = w * (r.j1 - r.j0 + 1);
         for (uint32_t c = lane; c < n; c += 32u) {
-            const uint32_t cell = ((uint32_t)f * M.N + r.j0 + c / w) * M.N + r.i0 + c % w;
+            const uint32_t j = r.j0 + c / w, ii = r.i0 + c % w;
+            if (cell_outside(r, ii, j, M.N)) continue;
+            const uint32_t cell = ((uint32_t)f * M.N + j) * M.N + ii;
             const uint32_t k = atomicAdd(counts_or_cursor + cell, 1u);
             if (FILL) cell_ent[cell_off[cell] + k] = i;
         }
@@ -120,7 +155,7 @@ int micmap_build(const Scene *sc, const float mic[3], MicMapStorage *out)
     *out = MicMapStorage{};
     static const int enabled = getenv("RVB_MICMAP") ? atoi(getenv("RVB_MICMAP")) : 1;
     if (!enabled || sc->accel != RVB_ACCEL_BVH || !(sc->diag > 0.0f)) return RVB_OK;
-    static const double cells_per_tri = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 8.0;
+    static const double cells_per_tri = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 16.0;
     cudaStream_t st = lib_stream();
     MicMapParams M{};
     M.verts = sc->d_verts; M.T = sc->T;

@@ -439,27 +439,22 @@ struct BvhAccel {
         const uint32_t cell = micmap_cell(w, mm.half_n, mm.N);
         const uint32_t e0 = __ldg(mm.cell_off + cell), ne = __ldg(mm.cell_off + cell + 1) - e0;
         const uint32_t ntri = ne + mm.n_near;
-        // Four candidates at a time: their index loads, then their triangle loads, are issued together
-        // (two memory latencies per group instead of two per triangle).  Past the end the last
-        // candidate is simply tested again -- the answer is an OR -- so every load is unconditional.
-        for (uint32_t k0 = 0; k0 < ntri; k0 += 4) {
-            const uint32_t ka = k0, kb = min(k0 + 1, ntri - 1), kc = min(k0 + 2, ntri - 1), kd = min(k0 + 3, ntri - 1);
+        // Two candidates per iteration (their index loads, then their triangle loads, are issued together:
+        // two memory latencies per pair).  Finer than that starves the loads, coarser wastes lanes: the
+        // lanes of a warp hold 1..12 candidates each and wait for the longest list (ncu, groups of four:
+        // 7.8 of 24 lanes active in this loop).  Past the end the last candidate is simply tested again --
+        // the answer is an OR -- so every load is unconditional.
+        for (uint32_t k0 = 0; k0 < ntri; k0 += 2) {
+            const uint32_t ka = k0, kb = min(k0 + 1, ntri - 1);
             const uint32_t ia = ka < ne ? __ldg(mm.cell_ent + e0 + ka) : __ldg(mm.near_ent + (ka - ne));
             const uint32_t ib = kb < ne ? __ldg(mm.cell_ent + e0 + kb) : __ldg(mm.near_ent + (kb - ne));
-            const uint32_t ic = kc < ne ? __ldg(mm.cell_ent + e0 + kc) : __ldg(mm.near_ent + (kc - ne));
-            const uint32_t id = kd < ne ? __ldg(mm.cell_ent + e0 + kd) : __ldg(mm.near_ent + (kd - ne));
-            const float4 *pa = tri + 3 * (size_t)ia, *pb = tri + 3 * (size_t)ib, *pc = tri + 3 * (size_t)ic, *pd = tri + 3 * (size_t)id;
+            const float4 *pa = tri + 3 * (size_t)ia, *pb = tri + 3 * (size_t)ib;
             const float4 Aa = __ldg(pa), Ba = __ldg(pa + 1), Ab = __ldg(pb), Bb = __ldg(pb + 1);
-            const float4 Ac = __ldg(pc), Bc = __ldg(pc + 1), Ad = __ldg(pd), Bd = __ldg(pd + 1);
             const float Ca = __ldg(reinterpret_cast<const float *>(pa + 2)), Cb = __ldg(reinterpret_cast<const float *>(pb + 2));
-            const float Cc = __ldg(reinterpret_cast<const float *>(pc + 2)), Cd = __ldg(reinterpret_cast<const float *>(pd + 2));
-            bool oka, okb, okc, okd;
+            bool oka, okb;
             const float ta = mt_intersect_pred(mk3(Aa.x, Aa.y, Aa.z), mk3(Aa.w, Ba.x, Ba.y), mk3(Ba.z, Ba.w, Ca), begin, dir, oka);
             const float tb = mt_intersect_pred(mk3(Ab.x, Ab.y, Ab.z), mk3(Ab.w, Bb.x, Bb.y), mk3(Bb.z, Bb.w, Cb), begin, dir, okb);
-            const float tc = mt_intersect_pred(mk3(Ac.x, Ac.y, Ac.z), mk3(Ac.w, Bc.x, Bc.y), mk3(Bc.z, Bc.w, Cc), begin, dir, okc);
-            const float td = mt_intersect_pred(mk3(Ad.x, Ad.y, Ad.z), mk3(Ad.w, Bd.x, Bd.y), mk3(Bd.z, Bd.w, Cd), begin, dir, okd);
-            blocked |= (oka && ta > RVB_EPSILON && ta <= mag) | (okb && tb > RVB_EPSILON && tb <= mag)
-                     | (okc && tc > RVB_EPSILON && tc <= mag) | (okd && td > RVB_EPSILON && td <= mag);
+            blocked |= (oka && ta > RVB_EPSILON && ta <= mag) | (okb && tb > RVB_EPSILON && tb <= mag);
         }
         c.queries++; c.tri += ntri;
         return blocked;
@@ -1133,11 +1128,8 @@ static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStr
     TraceParams P = P_in;
     P.wf_service = (uint32_t)std::max(1, std::min(32, service));
     P.wf_leaf_min = (uint32_t)std::max(1, std::min(32, leaf_min));
-    // Few rays (a ray shard of a strong-scaling run): a lane keeps a ray for all its reflections, so the
-    // kernel is as long as the slowest lane's chain of rays -- make sure every ray finds a free lane
-    // at the start (7 CTAs of 128 threads per SM hold 132 k rays on 148 SMs).
-    int minb = minb_env ? minb_env : 5;
-    if (!minb_env && (size_t)P.nrays > (size_t)5 * 128 * sm_count() && (size_t)P.nrays <= (size_t)7 * 128 * sm_count()) minb = 7;
+    // 5 CTAs of 128 threads per SM (<= 96 registers): 4 and 6 are 3-5 % slower, 7 (72 registers, spills) 23 %
+    const int minb = minb_env ? minb_env : 5;
     unsigned int *d_fetch = nullptr;
     RVB_TRY(dev_alloc(&d_fetch, 1));
     RVB_CUDA(cudaMemsetAsync(d_fetch, 0, sizeof(unsigned int), st));
@@ -1194,13 +1186,11 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
     float4 *d_state = nullptr;
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
-    // BVH scenes, steady phase: the persistent wavefront kernel when there are several waves of rays
-    // (its lanes pick up new rays as they finish: C3, 1 Mi rays: 52.5 ms against 61.5 ms), one thread per
-    // ray when every ray finds a lane at once (a 131 k-ray shard: 8.2 ms against 9.1 ms -- nothing to
-    // refill, and the per-ray form's lanes start every query together).  RVB_WAVEFRONT=0 / 1 forces one.
-    // Both are bound by the L1 data pipe (profiles/r2_bvh_kernels.md).
-    static const int wf_env = getenv("RVB_WAVEFRONT") ? atoi(getenv("RVB_WAVEFRONT")) : -1;
-    const bool wavefront = wf_env >= 0 ? wf_env != 0 : (size_t)tr->nrays >= (size_t)3 * 7 * 128 * sm_count();
+    // BVH scenes, steady phase: the persistent wavefront kernel (launch_wavefront); RVB_WAVEFRONT=0 selects
+    // the one-thread-per-ray kernel for comparison.  Measured on the C3 hall with 64-byte nodes
+    // (profiles/r2_bvh_kernels.md): 52.5 ms against 61.5 ms at 1 Mi rays, 14.6 against 16.0 at 262 k,
+    // 8.1 against 8.2 at 131 k (the per-GPU share of an 8-GPU run).
+    static const bool wavefront = !(getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '0');
     if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
     P.state = d_state;
     // brute force: the whole scene; BVH: the traversal stacks (one column of Scene::bvh_stack entries per thread)
