@@ -325,8 +325,9 @@ int scene_build_bvh(Scene *sc)
     int depth = 0;
     RVB_TRY(read_back(&n_leaves, d_rec_of + T, sizeof n_leaves));
     RVB_TRY(read_back(&depth, d_depth, sizeof depth));
-    // a 4-wide visit descends two binary levels and pushes at most three entries
-    sc->bvh_stack = 3 * (depth / 2 + 2) + 2;
+    // a 4-wide visit descends two binary levels (one when it ends in a leaf) and pushes at most three
+    // entries; + the sentinel and one spare
+    sc->bvh_stack = 3 * ((depth + 1) / 2) + 2;
     if (sc->bvh_stack > RVB_BVH_STACK)
         return fail(RVB_ERR_UNSUPPORTED, "BVH of depth " + std::to_string(depth) + " exceeds the traversal stack (near-coincident triangles?)");
     sc->n_leaves = n_leaves;
