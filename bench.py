@@ -276,21 +276,20 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
         from concurrent.futures import ThreadPoolExecutor
         nworkers = min(int(os.environ.get("RVB_BENCH_WORKERS", "4")), len(jobs))
         pool = ThreadPoolExecutor(max_workers=nworkers)
-        workers = [dict(stream=torch.cuda.Stream(), rt=api.Raytracer(nrefl, tri, vtx, srf, accel=accel)) for _ in range(nworkers)]
+        workers = [dict(stream=torch.cuda.Stream()) for _ in range(nworkers)]
 
-    def run_jobs_on_worker(w, my_jobs, resident):
+    def render_on_worker(w, traces, ready):
+        """Render this worker's share of a batched trace on its own stream."""
         out = []
         torch.cuda.set_device(local)
         api.set_device(local)
         api.set_stream(w["stream"].cuda_stream)
-        for mic, src in my_jobs:
-            if resident:
-                tr = w["rt"].raytrace(mic, src, None, ray_offset=shard["lo"], device_ptr=shard["d"].data_ptr(), nrays=shard["n"])
-            else:
-                tr = w["rt"].raytrace(mic, src, shard["h"].numpy(), ray_offset=shard["lo"])
+        w["stream"].wait_event(ready)
+        for tr in traces:
             st_t = tr.stats()
             ir = tr.render_ir(**render_kw)
             out.append((st_t, api.render_stats(), ir))
+            tr.close()
         w["stream"].synchronize()
         return out
 
@@ -298,7 +297,17 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
         """One pass of the hot path over this rank's work.  Returns the IR(s) this rank produced."""
         irs = []
         if workers:
-            futs = [pool.submit(run_jobs_on_worker, w, jobs[i::len(workers)], resident) for i, w in enumerate(workers)]
+            # C5: ONE batched trace of all this rank's pairs (rvb_trace_run_batch), then the per-pair renders
+            # (small sorts / filters) on the worker threads' streams
+            if resident:
+                d_ptr = shard["d"].data_ptr()
+            else:   # host buffers: the directions go to the device inside the timed region
+                state["e2e_dirs"] = shard["h"].to("cuda", non_blocking=True)
+                d_ptr = state["e2e_dirs"].data_ptr()
+            traces = rt.raytrace_batch(jobs, device_ptr=d_ptr, nrays=shard["n"])
+            ready = torch.cuda.Event()
+            ready.record(stream)
+            futs = [pool.submit(render_on_worker, w, traces[i::len(workers)], ready) for i, w in enumerate(workers)]
             for f in futs:
                 for st_t, st_r, ir in f.result():
                     state["trace"].append(st_t)
@@ -417,13 +426,15 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
         total_rb = total_rays * nrefl * (njobs_total if scaling == "jobs" else 1)
         fp32_peak_tf = SM_COUNT * FP32_LANES * 2 * sm_max_mhz * 1e6 / 1e12
         steady_ms, image_ms = _mean("steady_phase_ms", tstats), _mean("image_phase_ms", tstats)
-        steady_tests, steady_boxes = _mean("steady_tri_tests", tstats), _mean("steady_box_tests", tstats)
-        all_tests, all_boxes = _mean("tri_tests", tstats), _mean("box_tests", tstats)
+        # counts per launch: a batched trace (C5) runs all of this rank's pairs in the same kernels
+        per_launch = (lambda k: _mean(k, tstats) * len(jobs)) if scaling == "jobs" else (lambda k: _mean(k, tstats))
+        steady_tests, steady_boxes = per_launch("steady_tri_tests"), per_launch("steady_box_tests")
+        all_tests, all_boxes = per_launch("tri_tests"), per_launch("box_tests")
         brute = rt.accel == api.ACCEL_BRUTE_FORCE
         steady_flop = steady_tests * FLOP_PER_TEST + steady_boxes * FLOP_PER_BOX
         achieved_tf = steady_flop / (steady_ms * 1e-3) / 1e12 if steady_ms > 0 else 0.0
         split = min(9, nrefl)
-        emit_gbs = nrays * (nrefl - split) * 52 / (steady_ms * 1e-3) / 1e9 if steady_ms > 0 else 0.0
+        emit_gbs = nrays * (len(jobs) if scaling == "jobs" else 1) * (nrefl - split) * 52 / (steady_ms * 1e-3) / 1e9 if steady_ms > 0 else 0.0
         traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if brute and world == 1 and os.path.exists(tp):
@@ -432,7 +443,7 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
             traffic = json.load(open(tp))["steady_phase_dram_bytes_per_ray_bounce"] * nrays * (nrefl - split)
             traffic_note = "profile-derived constant (profiles/ncu_traffic.json) x this run's rays*bounces, not measured live"
         both_ms = steady_ms + image_ms
-        bounces, emitted = _mean("bounces", tstats), _mean("emitted", tstats)
+        bounces, emitted = per_launch("bounces"), per_launch("emitted")
         block = {
             "metric": "rays_x_bounces_per_s", "value": total_rb / (ms * 1e-3), "unit": "rays*bounces/s",
             "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
@@ -476,8 +487,6 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
             block["roofline"]["micmap"] = {"cells_per_face_edge": int(_mean("micmap_cells", tstats)), "entries": int(_mean("micmap_entries", tstats))}
         if sharded_parity is not None:
             block["sharded_parity"] = sharded_parity
-    for w in workers:
-        w["rt"].close()
     if pool is not None:
         pool.shutdown()
     rt.close()

@@ -92,6 +92,14 @@ int rvb_trace_run(rvb_scene *scene, const float mic[3], const float source[3],
 int rvb_trace_run_device(rvb_scene *scene, const float mic[3], const float source[3],
                          const rvb_float3 *d_directions, size_t nrays, size_t nreflections,
                          uint64_t ray_offset, unsigned flags, rvb_trace **out);
+/* Parameter sweeps (cmd/main.cpp:241-297 executed once per source / microphone pair): `njobs` pairs
+ * over the same scene and the same device-resident directions, traced together in one launch pair --
+ * a few thousand rays per pair do not fill a B200 on their own.  mics / sources: njobs x 3 floats.
+ * out[njobs] receives one trace per pair, each identical (bit for bit) to what rvb_trace_run_device
+ * returns for that pair alone; their kernel-time statistics are those of the whole batch. */
+int rvb_trace_run_batch(rvb_scene *scene, size_t njobs, const float *mics, const float *sources,
+                        const rvb_float3 *d_directions, size_t nrays, size_t nreflections,
+                        unsigned flags, rvb_trace **out);
 int rvb_trace_destroy(rvb_trace *trace);
 
 /* getRawDiffuse (rayverb.cpp:687-690): nrays*nreflections impulses, ray-major, zeros where a ray

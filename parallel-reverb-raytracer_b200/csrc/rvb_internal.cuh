@@ -180,8 +180,10 @@ void micmap_free(MicMapStorage *s);
 
 // ---- stage entry points (defined in the .cu files) ----------------------------------------------
 int scene_build_bvh(Scene *sc);                                                       // bvh.cu
-int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB,
-                 float4 *d_cand_pt, uint32_t *d_cand_idx);                            // trace.cu
+// image-source candidate slots of one job (freed after de-duplication)
+struct CandBuffers { float4 *volA = nullptr, *volB = nullptr, *pt = nullptr; uint32_t *idx = nullptr; };
+// traces all jobs (same scene, directions, counts and flags; their own microphone / source) in one launch pair
+int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const CandBuffers *cands);   // trace.cu
 int images_dedupe(Trace *tr, const float4 *d_cand_volA, const float4 *d_cand_volB,
                   const float4 *d_cand_pt, const uint32_t *d_cand_idx);               // images.cu
 

@@ -43,24 +43,33 @@ struct TraceParams {
     const BvhNode *nodes;
     const float4 *leaf_quads;
     const uint4 *leaf_ids;
-    MicMap micmap;            // visibility map around the microphone (N == 0: none)
-    const float4 *dirs;
+    const float4 *dirs;       // [nrays] shared by all jobs of a batch
     const uint32_t *ray_perm;  // image phase: processing order (rays sorted by direction), or null
-    uint32_t nrays, nrefl;
+    uint32_t nrays, nrefl;    // rays PER JOB
     uint32_t first, last;     // reflections [first, last) handled by this launch
-    uint64_t ray_offset;
-    float mic[3], src[3];
     float air[RVB_NBANDS];
+    uint32_t wf_service, wf_leaf_min;          // wavefront kernel: lanes that must wait before `serve` / hold a leaf before the triangle step
+    const struct TraceJob *jobs;               // [njobs] device array
+    uint32_t njobs;
+    uint32_t flags;
+};
+
+// One (microphone, source) pair of a trace launch.  A plain trace is a batch of one; a batched trace
+// (rvb_trace_run_batch: parameter sweeps, cmd/main.cpp:241-297 run once per pair) traces every pair's
+// rays in the same launches -- a CTA (a warp of the wavefront kernel) works for one job at a time and
+// keeps that job's record in shared memory.
+struct TraceJob {
+    float mic[3], src[3];
+    uint64_t ray_offset;
+    MicMap micmap;            // visibility map around this job's microphone (N == 0: none)
     float4 *vol, *pt;         // vol: 2 x float4 per slot
     float *tkey;
     uint32_t *hit, *count;
     float4 *state;            // [4*nrays] (pos, distance) (dir, alive) volA volB
     float4 *cand_volA, *cand_volB, *cand_pt;   // [nrays*10] image-source candidates
     uint32_t *cand_idx;                        // [nrays*10] triangle+1, 0 = none (pre-zeroed)
-    uint32_t wf_service, wf_leaf_min;          // wavefront kernel: lanes that must wait before `serve` / hold a leaf before the triangle step
     unsigned long long *counters;              // [0] queries [1] tri tests [2] box tests [3] bounces [5] emitted impulses
     int *time_ext;                             // [0] ordered min non-zero, [1] ordered max time of the emitted diffuse impulses
-    uint32_t flags;
 };
 
 struct Counters {
@@ -527,7 +536,7 @@ __device__ __forceinline__ f3 mirror_point(f3 p, const MirrorTri &t)
 }
 
 // kernel.cpp:243-265
-__device__ __forceinline__ void add_image(const TraceParams &P, f3 mic, f3 mic_reflection, f3 source, size_t slot,
+__device__ __forceinline__ void add_image(const TraceParams &P, const TraceJob &J, f3 mic, f3 mic_reflection, f3 source, size_t slot,
                                           const float2 *volume, uint32_t object_index)
 {
     f3 diff = source - mic_reflection;
@@ -538,10 +547,10 @@ __device__ __forceinline__ void add_image(const TraceParams &P, f3 mic, f3 mic_r
 #pragma unroll
     for (int b = 0; b < RVB_NBANDS / 2; ++b) v[b] = __fmul2_rn(volume[b], att[b]);
     f3 p = mic + diff;
-    P.cand_volA[slot] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
-    P.cand_volB[slot] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
-    P.cand_pt[slot] = make_float4(p.x, p.y, p.z, __fmul_rn(RVB_SECONDS_PER_METER, dist));
-    P.cand_idx[slot] = object_index;
+    J.cand_volA[slot] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    J.cand_volB[slot] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+    J.cand_pt[slot] = make_float4(p.x, p.y, p.z, __fmul_rn(RVB_SECONDS_PER_METER, dist));
+    J.cand_idx[slot] = object_index;
 }
 
 struct RayState {
@@ -554,7 +563,7 @@ struct RayState {
 // `next`: with a fused accelerator (Accel::kFused) and next->want, the visibility sweep also answers
 // the nearest-hit query of the reflected ray (see BruteSmem::visible_and_next).
 template <class Accel>
-__device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceParams &P, f3 mic, uint32_t ray, uint32_t index,
+__device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceParams &P, const TraceJob &J, f3 mic, uint32_t ray, uint32_t index,
                                                   float tclosest, uint32_t prim, RayState &R, Counters &c, NextHit *next = nullptr)
 {
     const f3 X = madd(R.pos, R.dir, tclosest);                               // :459
@@ -598,16 +607,16 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
     const size_t slot = slot_of(ray, index, P.nrays);
     // streaming stores: the impulses are read back much later (flatten), they should not push the
     // scene out of L2
-    __stcs(P.vol + 2 * slot, make_float4(out[0].x, out[0].y, out[1].x, out[1].y));
-    __stcs(P.vol + 2 * slot + 1, make_float4(out[2].x, out[2].y, out[3].x, out[3].y));
-    __stcs(P.pt + slot, make_float4(X.x, X.y, X.z, time));
-    __stcs(P.tkey + slot, any ? time : -1.0f);
+    __stcs(J.vol + 2 * slot, make_float4(out[0].x, out[0].y, out[1].x, out[1].y));
+    __stcs(J.vol + 2 * slot + 1, make_float4(out[2].x, out[2].y, out[3].x, out[3].y));
+    __stcs(J.pt + slot, make_float4(X.x, X.y, X.z, time));
+    __stcs(J.tkey + slot, any ? time : -1.0f);
     if (any) {
         c.emitted++;
         if (time != 0.0f) c.tmin_nz = fminf(c.tmin_nz, time);
         c.tmax = fmaxf(c.tmax, time);
     }
-    if (P.hit) P.hit[slot] = prim;
+    if (J.hit) J.hit[slot] = prim;
 
     R.dir = newDir;
     R.pos = X;
@@ -617,19 +626,19 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
 }
 
 // a ray that left the mesh keeps zero impulses in its remaining slots (rayverb.cpp:601-603)
-__device__ __forceinline__ void zero_fill(const TraceParams &P, uint32_t ray, uint32_t index)
+__device__ __forceinline__ void zero_fill(const TraceParams &P, const TraceJob &J, uint32_t ray, uint32_t index)
 {
     for (; index != P.nrefl; ++index) {
         const size_t slot = slot_of(ray, index, P.nrays);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        P.vol[2 * slot] = z; P.vol[2 * slot + 1] = z; P.pt[slot] = z; P.tkey[slot] = -1.0f;
-        if (P.hit) P.hit[slot] = RVB_NONE;
+        J.vol[2 * slot] = z; J.vol[2 * slot + 1] = z; J.pt[slot] = z; J.tkey[slot] = -1.0f;
+        if (J.hit) J.hit[slot] = RVB_NONE;
     }
 }
 
-__device__ __forceinline__ void store_state(const TraceParams &P, uint32_t ray, const RayState &R, bool alive)
+__device__ __forceinline__ void store_state(const TraceJob &J, uint32_t ray, const RayState &R, bool alive)
 {
-    float4 *s = P.state + 4 * (size_t)ray;
+    float4 *s = J.state + 4 * (size_t)ray;
     s[0] = make_float4(R.pos.x, R.pos.y, R.pos.z, R.distance);
     s[1] = make_float4(R.dir.x, R.dir.y, R.dir.z, alive ? 1.0f : 0.0f);
     s[2] = make_float4(R.volume[0].x, R.volume[0].y, R.volume[1].x, R.volume[1].y);
@@ -638,10 +647,10 @@ __device__ __forceinline__ void store_state(const TraceParams &P, uint32_t ray, 
 
 // Reflections [0, P.last) WITH the image-source branch (kernel.cpp:379-457); P.last <= 9.
 template <class Accel>
-__device__ void image_phase_ray(const Accel &acc, const TraceParams &P, uint32_t ray, Counters &c)
+__device__ void image_phase_ray(const Accel &acc, const TraceParams &P, const TraceJob &J, uint32_t ray, Counters &c)
 {
-    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
-    const f3 source = mk3(P.src[0], P.src[1], P.src[2]);
+    const f3 mic = mk3(J.mic[0], J.mic[1], J.mic[2]);
+    const f3 source = mk3(J.src[0], J.src[1], J.src[2]);
     RayState R;
     R.pos = source;
     R.dir = mk3(__ldg(P.dirs + ray));
@@ -654,9 +663,9 @@ __device__ void image_phase_ray(const Accel &acc, const TraceParams &P, uint32_t
     // Direct path (kernel.cpp:335-357).  Every work-item of the reference computes the same
     // source->mic query and the host keeps the first ray's copy (rayverb.cpp:667-673); only
     // global ray 0 needs to do it.
-    if (P.ray_offset + ray == 0) {
+    if (J.ray_offset + ray == 0) {
         if (point_visible(acc, source, mic_reflection, c))
-            add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE, R.volume, 0u);
+            add_image(P, J, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE, R.volume, 0u);
     }
 
     uint32_t index = 0;
@@ -698,30 +707,30 @@ __device__ void image_phase_ray(const Accel &acc, const TraceParams &P, uint32_t
             }
             if (intersects) intersects = point_visible(acc, prevI, mic, c);      // :431
             if (intersects)   // pre-bounce volume
-                add_image(P, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE + index + 1, R.volume, prim + 1u);
+                add_image(P, J, mic, mic_reflection, source, (size_t)ray * RVB_NUM_IMAGE_SOURCE + index + 1, R.volume, prim + 1u);
         }
-        shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c);
+        shade_and_reflect(acc, P, J, mic, ray, index, tclosest, prim, R, c);
     }
     c.bounces += index;
-    if (P.count) P.count[ray] = index;
-    if (!alive) zero_fill(P, ray, index);
-    if (P.last < P.nrefl) store_state(P, ray, R, alive);
+    if (J.count) J.count[ray] = index;
+    if (!alive) zero_fill(P, J, ray, index);
+    if (P.last < P.nrefl) store_state(J, ray, R, alive);
 }
 
 // Reflections [P.first, P.last) without image sources: the steady state of the reference loop.
 template <class Accel>
-__device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TraceParams &P, uint32_t ray, Counters &c)
+__device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TraceParams &P, const TraceJob &J, uint32_t ray, Counters &c)
 {
-    const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+    const f3 mic = mk3(J.mic[0], J.mic[1], J.mic[2]);
     RayState R;
     if (P.first == 0) {
-        R.pos = mk3(P.src[0], P.src[1], P.src[2]);
+        R.pos = mk3(J.src[0], J.src[1], J.src[2]);
         R.dir = mk3(__ldg(P.dirs + ray));
         R.distance = 0.0f;
 #pragma unroll
         for (int b = 0; b < RVB_NBANDS / 2; ++b) R.volume[b] = make_float2(1.0f, 1.0f);
     } else {
-        const float4 *s = P.state + 4 * (size_t)ray;
+        const float4 *s = J.state + 4 * (size_t)ray;
         const float4 a = s[0], d = s[1], va = s[2], vb = s[3];
         if (d.w == 0.0f) return;   // left the mesh during the image phase (slots already zero-filled)
         R.pos = mk3(a); R.distance = a.w; R.dir = mk3(d);
@@ -736,7 +745,7 @@ __device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TracePa
         bool hit = acc.nearest(R.pos, R.dir, tclosest, prim, c);                 // :363-375
         while (hit) {
             NextHit next{index + 1 != P.last, 0.0f, RVB_NONE};
-            shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c, &next);
+            shade_and_reflect(acc, P, J, mic, ray, index, tclosest, prim, R, c, &next);
             ++index;
             if (index == P.last) break;
             tclosest = next.t; prim = next.prim;
@@ -747,15 +756,15 @@ __device__ __forceinline__ void steady_phase_ray(const Accel &acc, const TracePa
             float tclosest;
             uint32_t prim;
             if (!acc.nearest(R.pos, R.dir, tclosest, prim, c)) break;            // :363-375
-            shade_and_reflect(acc, P, mic, ray, index, tclosest, prim, R, c);
+            shade_and_reflect(acc, P, J, mic, ray, index, tclosest, prim, R, c);
         }
     }
     c.bounces += index - P.first;
-    if (P.count) P.count[ray] = (P.first ? P.count[ray] : 0u) + (index - P.first);
-    if (index != P.last) zero_fill(P, ray, index);
+    if (J.count) J.count[ray] = (P.first ? J.count[ray] : 0u) + (index - P.first);
+    if (index != P.last) zero_fill(P, J, ray, index);
 }
 
-__device__ __forceinline__ void flush_counters(const TraceParams &P, const Counters &c)
+__device__ __forceinline__ void flush_counters(const TraceJob &J, const Counters &c)
 {
     // warp-aggregate, then one atomic per warp (integer adds: order-independent)
     unsigned long long q = c.queries, t = c.tri, b = c.box, n = c.bounces, em = c.emitted;
@@ -767,10 +776,10 @@ __device__ __forceinline__ void flush_counters(const TraceParams &P, const Count
         mn = fminf(mn, __shfl_down_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(P.counters + 0, q); atomicAdd(P.counters + 1, t);
-        atomicAdd(P.counters + 2, b); atomicAdd(P.counters + 3, n); atomicAdd(P.counters + 5, em);
+        atomicAdd(J.counters + 0, q); atomicAdd(J.counters + 1, t);
+        atomicAdd(J.counters + 2, b); atomicAdd(J.counters + 3, n); atomicAdd(J.counters + 5, em);
         // order-preserving integer keys: min / max are order-independent, so this is deterministic
-        atomicMin(P.time_ext, ordered_key(mn)); atomicMax(P.time_ext + 1, ordered_key(mx));
+        atomicMin(J.time_ext, ordered_key(mn)); atomicMax(J.time_ext + 1, ordered_key(mx));
     }
 }
 
@@ -805,6 +814,16 @@ __device__ __forceinline__ void stage_scene(float4 *s_tri, const TraceParams &P)
     }
 }
 
+// The job a CTA works for (blockIdx.y) in shared memory: word-wise copy by the first threads.
+__device__ __forceinline__ void load_job(TraceJob *dst, const TraceJob *src)
+{
+    static_assert(sizeof(TraceJob) % 4 == 0, "word copy");
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(src);
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t k = threadIdx.x; k < sizeof(TraceJob) / 4; k += blockDim.x) d[k] = s[k];
+    __syncthreads();
+}
+
 // BLOCK = 256 for small scenes (several CTAs per SM); when the shared-memory scene leaves room for
 // only one CTA per SM the launcher switches to 1024 (steady phase) / 512 (image phase) threads so
 // that the schedulers still have 8 / 4 warps each.
@@ -812,13 +831,15 @@ template <bool IMAGES, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TraceParams P)
 {
     extern __shared__ float4 s_tri[];
+    __shared__ TraceJob J;
+    load_job(&J, P.jobs + blockIdx.y);
     stage_scene(s_tri, P);
     BruteSmem acc{s_tri, P.T, P.nquads};
     Counters c;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrays; i += gridDim.x * blockDim.x) {
-        if (IMAGES) image_phase_ray(acc, P, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, i, c);
+        if (IMAGES) image_phase_ray(acc, P, J, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, J, i, c);
     }
-    flush_counters(P, c);
+    flush_counters(J, c);
 }
 
 // One warp per ray (BruteSmemWarp): all lanes run the per-ray code on the same ray; identical values
@@ -827,28 +848,32 @@ template <bool IMAGES>
 __global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceParams P)
 {
     extern __shared__ float4 s_tri[];
+    __shared__ TraceJob J;
+    load_job(&J, P.jobs + blockIdx.y);
     stage_scene(s_tri, P);
     BruteSmemWarp acc{s_tri, P.T, P.nquads};
     Counters c;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < P.nrays; ray += nwarps) {
         const uint32_t before = c.bounces, emitted_before = c.emitted;
-        if (IMAGES) image_phase_ray(acc, P, ray, c); else steady_phase_ray(acc, P, ray, c);
+        if (IMAGES) image_phase_ray(acc, P, J, ray, c); else steady_phase_ray(acc, P, J, ray, c);
         if (threadIdx.x & 31u) { c.bounces = before; c.emitted = emitted_before; }
     }
-    flush_counters(P, c);
+    flush_counters(J, c);
 }
 
 template <bool IMAGES, int MINB>
 __global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams P)
 {
     extern __shared__ int s_stack[];
-    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap, TravStack{s_stack + threadIdx.x}};
+    __shared__ TraceJob J;
+    load_job(&J, P.jobs + blockIdx.y);
+    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, J.micmap, TravStack{s_stack + threadIdx.x}};
     Counters c;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrays; i += gridDim.x * blockDim.x) {
-        if (IMAGES) image_phase_ray(acc, P, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, i, c);
+        if (IMAGES) image_phase_ray(acc, P, J, P.ray_perm ? P.ray_perm[i] : i, c); else steady_phase_ray(acc, P, J, i, c);
     }
-    flush_counters(P, c);
+    flush_counters(J, c);
 }
 
 // Direction cell of a ray (256 x 256 cells over z and the azimuth), used only to
@@ -884,9 +909,11 @@ static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, 
     int per_sm = 0;
     RVB_TRY(occupancy_of(kernel, block, smem, per_sm));
     if (per_sm < 1) return fail(RVB_ERR_INVALID, "scene does not fit in shared memory for the brute-force kernel");
+    // grid.y = job; the resident CTAs are shared out among the jobs
     const size_t want = ((size_t)P.nrays + block - 1) / block;
-    const size_t grid = std::min(want, (size_t)per_sm * sm_count());
-    note_launch(), kernel<<<(unsigned)grid, block, smem, st>>>(P);
+    const size_t share = std::max<size_t>(1, ((size_t)per_sm * sm_count() + P.njobs - 1) / P.njobs);
+    const size_t grid = std::max<size_t>(1, std::min(want, share));
+    note_launch(), kernel<<<dim3((unsigned)grid, P.njobs), block, smem, st>>>(P);
     RVB_CUDA(cudaGetLastError());
     return RVB_OK;
 }
@@ -923,8 +950,9 @@ static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
         RVB_TRY(occupancy_of(trace_bruteforce_warp_kernel<IMAGES>, 256, smem, per_sm));
         if (per_sm >= 1) {
             const size_t want = ((size_t)P.nrays * 32 + 255) / 256;
-            const size_t grid = std::max<size_t>(1, std::min(want, (size_t)per_sm * sm_count()));
-            note_launch(), trace_bruteforce_warp_kernel<IMAGES><<<(unsigned)grid, 256, smem, st>>>(P);
+            const size_t share = std::max<size_t>(1, ((size_t)per_sm * sm_count() + P.njobs - 1) / P.njobs);
+            const size_t grid = std::max<size_t>(1, std::min(want, share));
+            note_launch(), trace_bruteforce_warp_kernel<IMAGES><<<dim3((unsigned)grid, P.njobs), 256, smem, st>>>(P);
             RVB_CUDA(cudaGetLastError());
             return RVB_OK;
         }
@@ -991,14 +1019,29 @@ struct WfShared {
 };
 
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const TraceParams P, unsigned int *fetch)
+__global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const TraceParams P, unsigned int *fetch_all /* [njobs] */)
 {
     __shared__ WfShared S;
+    __shared__ TraceJob sJ[4];                       // the job each warp currently works for
     extern __shared__ int s_stack[];
     const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u, tid = threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, tid = threadIdx.x, warp = threadIdx.x >> 5;
     const TravStack stack{s_stack + tid};
-    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, P.micmap, stack};
+    const TraceJob &J = sJ[warp];
+    // A warp works for ONE job at a time (a plain trace has one job).  With at least as many warps as
+    // jobs the warps are dealt round-robin to the jobs, otherwise the jobs to the warps.
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
+    const bool many_warps = nw >= P.njobs;
+  for (uint32_t job = many_warps ? gw % P.njobs : gw; job < P.njobs; job += many_warps ? P.njobs : nw) {
+    __syncwarp();
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(P.jobs + job);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&sJ[warp]);
+        for (uint32_t k = lane; k < sizeof(TraceJob) / 4; k += 32) dst[k] = src[k];
+    }
+    __syncwarp();
+    unsigned int *fetch = fetch_all + job;
+    const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, J.micmap, stack};
     int sp = 0, node = RVB_SENTINEL;
     bool has = false, exhausted = false;
     uint32_t ibest = RVB_NONE, nbox = 0, ntri = 0;
@@ -1016,14 +1059,14 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
             uint32_t index = S.index[tid];
             bool more = false;
             if (ibest != RVB_NONE) {
-                const f3 mic = mk3(P.mic[0], P.mic[1], P.mic[2]);
+                const f3 mic = mk3(J.mic[0], J.mic[1], J.mic[2]);
                 RayState R;
                 R.pos = pos; R.dir = dir; R.distance = S.distance[tid];
 #pragma unroll
                 for (int b = 0; b < RVB_NBANDS / 2; ++b) R.volume[b] = make_float2(S.volume[2 * b][tid], S.volume[2 * b + 1][tid]);
                 Counters c;
                 c.tmin_nz = S.tmin_nz[tid]; c.tmax = S.tmax[tid];
-                shade_and_reflect(acc, P, mic, ray, index, tbest, ibest, R, c);
+                shade_and_reflect(acc, P, J, mic, ray, index, tbest, ibest, R, c);
                 pos = R.pos; dir = R.dir; S.distance[tid] = R.distance;
 #pragma unroll
                 for (int b = 0; b < RVB_NBANDS / 2; ++b) { S.volume[2 * b][tid] = R.volume[b].x; S.volume[2 * b + 1][tid] = R.volume[b].y; }
@@ -1033,7 +1076,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 more = index != P.last;
             } else {
                 S.queries[tid] += 1u;
-                zero_fill(P, ray, index);                                    // left the mesh, kernel.cpp:372-375
+                zero_fill(P, J, ray, index);                                    // left the mesh, kernel.cpp:372-375
             }
             if (more) {
                 S.index[tid] = index;
@@ -1042,7 +1085,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 sp = 0; stack.push(sp, RVB_SENTINEL); node = 0;
             } else {
                 S.bounces[tid] += index - P.first;
-                if (P.count) P.count[ray] = (P.first ? P.count[ray] : 0u) + (index - P.first);
+                if (J.count) J.count[ray] = (P.first ? J.count[ray] : 0u) + (index - P.first);
                 has = false;
             }
         }
@@ -1061,13 +1104,13 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 else {
                     bool live = true;
                     if (P.first == 0) {
-                        pos = mk3(P.src[0], P.src[1], P.src[2]);
+                        pos = mk3(J.src[0], J.src[1], J.src[2]);
                         dir = mk3(__ldg(P.dirs + r));
                         S.distance[tid] = 0.0f;
 #pragma unroll
                         for (int b = 0; b < RVB_NBANDS; ++b) S.volume[b][tid] = 1.0f;
                     } else {
-                        const float4 *s = P.state + 4 * (size_t)r;
+                        const float4 *s = J.state + 4 * (size_t)r;
                         const float4 a = s[0], d = s[1];
                         live = d.w != 0.0f;   // dead: left the mesh during the image phase (slots already zero-filled)
                         if (live) {
@@ -1117,7 +1160,8 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
     c.queries = S.queries[tid]; c.bounces = S.bounces[tid]; c.emitted = S.emitted[tid];
     c.tri = (unsigned long long)S.tri[tid] + ntri; c.box = nbox;
     c.tmin_nz = S.tmin_nz[tid]; c.tmax = S.tmax[tid];
-    flush_counters(P, c);
+    flush_counters(J, c);
+  }
 }
 
 static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStream_t st)
@@ -1130,14 +1174,14 @@ static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStr
     P.wf_leaf_min = (uint32_t)std::max(1, std::min(32, leaf_min));
     // 5 CTAs of 128 threads per SM (<= 96 registers): 4 and 6 are 3-5 % slower, 7 (72 registers, spills) 23 %
     const int minb = minb_env ? minb_env : 5;
-    unsigned int *d_fetch = nullptr;
-    RVB_TRY(dev_alloc(&d_fetch, 1));
-    RVB_CUDA(cudaMemsetAsync(d_fetch, 0, sizeof(unsigned int), st));
+    unsigned int *d_fetch = nullptr;   // one ray counter per job
+    RVB_TRY(dev_alloc(&d_fetch, (size_t)P.njobs));
+    RVB_CUDA(cudaMemsetAsync(d_fetch, 0, P.njobs * sizeof(unsigned int), st));
     auto go = [&](auto kernel) -> int {
         int per_sm = 0;
         RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_bytes));
         RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, stack_bytes));
-        const size_t want = ((size_t)P.nrays + 127) / 128;
+        const size_t want = ((size_t)P.nrays * P.njobs + 127) / 128;
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min(want, (size_t)std::max(per_sm, 1) * sm_count()));
         note_launch(), kernel<<<grid, 128, stack_bytes, st>>>(P, d_fetch);
         RVB_CUDA(cudaGetLastError());
@@ -1155,32 +1199,29 @@ static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStr
     return rc;
 }
 
-int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d_cand_volB, float4 *d_cand_pt,
-                 uint32_t *d_cand_idx)
+int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const CandBuffers *cands)
 {
+    Trace *tr = trs[0];                  // scene, ray / reflection counts and flags are common to the batch
     Scene *sc = tr->scene;
     cudaStream_t st = lib_stream();
     TraceParams P{};
     P.verts = sc->d_verts; P.tri = sc->d_tri; P.quad = sc->d_quad; P.nquads = sc->nquads; P.nrm = sc->d_nrm; P.surfaces = sc->d_surfaces; P.T = sc->T;
     P.nodes = sc->d_nodes; P.leaf_quads = sc->d_leaf_quads; P.leaf_ids = sc->d_leaf_ids;
-    P.dirs = d_dirs; P.nrays = (uint32_t)tr->nrays; P.nrefl = (uint32_t)tr->nrefl; P.ray_offset = tr->ray_offset;
-    for (int i = 0; i < 3; ++i) { P.mic[i] = tr->mic[i]; P.src[i] = tr->src[i]; }
+    P.dirs = d_dirs; P.nrays = (uint32_t)tr->nrays; P.nrefl = (uint32_t)tr->nrefl;
+    P.njobs = (uint32_t)njobs;
     // AIR_COEFFICIENT: doubles narrowed to float (rayverb.cpp:632-641)
     const double air[RVB_NBANDS] = {0.001 * -0.1, 0.001 * -0.2, 0.001 * -0.5, 0.001 * -1.1,
                                     0.001 * -2.7, 0.001 * -9.4, 0.001 * -29.0, 0.001 * -60.0};
     for (int b = 0; b < RVB_NBANDS; ++b) P.air[b] = (float)air[b];
-    P.vol = tr->d_vol; P.pt = tr->d_pt; P.tkey = tr->d_tkey;
-    P.hit = tr->d_hit; P.count = tr->d_count;
-    P.cand_volA = d_cand_volA; P.cand_volB = d_cand_volB; P.cand_pt = d_cand_pt; P.cand_idx = d_cand_idx;
     P.flags = tr->flags;
-    unsigned long long *d_counters = nullptr;
-    RVB_TRY(dev_alloc(&d_counters, 6));
-    {   // [4] holds the two ordered time keys: ordered(+inf), ordered(0)
-        const unsigned long long init[6] = {0, 0, 0, 0, 0x000000007f800000ull, 0};
-        RVB_CUDA(cudaMemcpyAsync(d_counters, init, sizeof init, cudaMemcpyHostToDevice, st));
+    unsigned long long *d_counters = nullptr;   // six per job; [4] holds the two ordered time keys
+    RVB_TRY(dev_alloc(&d_counters, 6 * njobs));
+    {
+        std::vector<unsigned long long> init(6 * njobs, 0ull);
+        for (size_t j = 0; j < njobs; ++j) init[6 * j + 4] = 0x000000007f800000ull;   // ordered(+inf), ordered(0)
+        RVB_CUDA(cudaMemcpyAsync(d_counters, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        RVB_CUDA(cudaStreamSynchronize(st));   // `init` is pageable and goes out of scope
     }
-    P.counters = d_counters;
-    P.time_ext = reinterpret_cast<int *>(d_counters + 4);
 
     const bool images = !(tr->flags & RVB_TRACE_NO_IMAGES);
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
@@ -1191,12 +1232,11 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     // (profiles/r2_bvh_kernels.md): 52.5 ms against 61.5 ms at 1 Mi rays, 14.6 against 16.0 at 262 k,
     // 8.1 against 8.2 at 131 k (the per-GPU share of an 8-GPU run).
     static const bool wavefront = !(getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '0');
-    if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays));
-    P.state = d_state;
+    if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays * njobs));
     // brute force: the whole scene; BVH: the traversal stacks (one column of Scene::bvh_stack entries per thread)
     const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : (size_t)sc->bvh_stack * RVB_BVH_CTA * sizeof(int);
 
-    // processing order of the image phase: rays sorted by direction cell
+    // processing order of the image phase: rays sorted by direction cell (the jobs share the directions)
     uint32_t *d_perm_keys[2] = {nullptr, nullptr}, *d_perm_ids[2] = {nullptr, nullptr};
     uint8_t *d_perm_tmp = nullptr;
     if (split > 0 && tr->nrays >= 4096) {
@@ -1214,17 +1254,31 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
     RVB_CUDA(cudaEventCreate(&em));
-    unsigned long long *h_pin = nullptr;   // [0..6) final counters, [6..10) counters after the image phase
-    RVB_TRY(pinned_scratch(reinterpret_cast<void **>(&h_pin), 10 * sizeof(unsigned long long)));
-    for (int i = 0; i < 10; ++i) h_pin[i] = 0;
-    unsigned long long *hm = h_pin + 6;
+    std::vector<unsigned long long> h_end(6 * njobs, 0ull), h_mid(6 * njobs, 0ull);
     RVB_CUDA(cudaEventRecord(e0, st));
-    // BVH scenes: the visibility map around this trace's microphone (rebuilt for every trace: it is
-    // part of the measured work, not a cache)
-    MicMapStorage mm;
-    if (!brute && tr->nrays > 0) RVB_TRY(micmap_build(sc, tr->mic, &mm));
-    P.micmap = mm.map;
-    tr->stats.micmap_cells = mm.map.N; tr->stats.micmap_entries = mm.entries;
+    // The job records.  BVH scenes: the visibility map around every job's microphone (rebuilt for every
+    // trace: it is part of the measured work, not a cache).
+    std::vector<MicMapStorage> mms(njobs);
+    std::vector<TraceJob> jobs(njobs);
+    for (size_t j = 0; j < njobs; ++j) {
+        Trace *t = trs[j];
+        if (!brute && t->nrays > 0) RVB_TRY(micmap_build(sc, t->mic, &mms[j]));
+        TraceJob &J = jobs[j];
+        for (int i = 0; i < 3; ++i) { J.mic[i] = t->mic[i]; J.src[i] = t->src[i]; }
+        J.ray_offset = t->ray_offset;
+        J.micmap = mms[j].map;
+        J.vol = t->d_vol; J.pt = t->d_pt; J.tkey = t->d_tkey; J.hit = t->d_hit; J.count = t->d_count;
+        J.state = d_state ? d_state + 4 * t->nrays * j : nullptr;
+        J.cand_volA = cands[j].volA; J.cand_volB = cands[j].volB; J.cand_pt = cands[j].pt; J.cand_idx = cands[j].idx;
+        J.counters = d_counters + 6 * j;
+        J.time_ext = reinterpret_cast<int *>(d_counters + 6 * j + 4);
+        t->stats.micmap_cells = mms[j].map.N; t->stats.micmap_entries = mms[j].entries;
+    }
+    TraceJob *d_jobs = nullptr;
+    RVB_TRY(dev_alloc(&d_jobs, njobs));
+    RVB_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), njobs * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
+    RVB_CUDA(cudaStreamSynchronize(st));
+    P.jobs = d_jobs;
     RVB_CUDA(cudaEventRecord(em, st));
     if (tr->nrays > 0 && tr->nrefl > 0) {
         if (split > 0) {
@@ -1232,7 +1286,7 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
             if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
             else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, smem, st));
             RVB_CUDA(cudaEventRecord(em, st));
-            RVB_CUDA(cudaMemcpyAsync(hm, d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            RVB_CUDA(cudaMemcpyAsync(h_mid.data(), d_counters, 6 * njobs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         }
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
@@ -1246,38 +1300,40 @@ int trace_launch(Trace *tr, const float4 *d_dirs, float4 *d_cand_volA, float4 *d
             }
             else RVB_TRY(launch_wavefront(P, smem, st));
         }
-    } else if (tr->nrays > 0 && images && tr->ray_offset == 0) {
+    } else if (tr->nrays > 0 && images) {
         // zero reflections: the reference still computes the direct path for ray 0
         P.first = 0; P.last = 0;
         if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
         else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, smem, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
-    unsigned long long *h = h_pin;
-    RVB_CUDA(cudaMemcpyAsync(h, d_counters, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RVB_CUDA(cudaMemcpyAsync(h_end.data(), d_counters, 6 * njobs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f, ms_image = 0.f, ms_steady = 0.f;
     RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     RVB_CUDA(cudaEventElapsedTime(&ms_image, e0, em));
     RVB_CUDA(cudaEventElapsedTime(&ms_steady, em, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(em);
-    tr->stats.image_phase_ms = ms_image; tr->stats.steady_phase_ms = ms_steady;
-    tr->stats.steady_tri_tests = h[1] - hm[1]; tr->stats.steady_box_tests = h[2] - hm[2];
     dev_free(d_counters);
     dev_free(d_state);
-    micmap_free(&mm);
+    dev_free(d_jobs);
+    for (size_t j = 0; j < njobs; ++j) micmap_free(&mms[j]);
     for (int i = 0; i < 2; ++i) { dev_free(d_perm_keys[i]); dev_free(d_perm_ids[i]); }
     dev_free(d_perm_tmp);
-    {
+    for (size_t j = 0; j < njobs; ++j) {
+        Trace *t = trs[j];
+        const unsigned long long *h = h_end.data() + 6 * j, *hm = h_mid.data() + 6 * j;
+        // kernel times are those of the whole launch (all jobs of the batch run in the same kernels)
+        t->stats.image_phase_ms = ms_image; t->stats.steady_phase_ms = ms_steady; t->stats.trace_kernel_ms = ms;
+        t->stats.steady_tri_tests = h[1] - hm[1]; t->stats.steady_box_tests = h[2] - hm[2];
         int ext[2];
         memcpy(ext, &h[4], sizeof ext);
-        tr->diffuse_tmin_nz = unordered_key(ext[0]);   // +inf: no non-zero time
-        tr->diffuse_tmax = unordered_key(ext[1]);
-        tr->has_time_ext = true;
+        t->diffuse_tmin_nz = unordered_key(ext[0]);   // +inf: no non-zero time
+        t->diffuse_tmax = unordered_key(ext[1]);
+        t->has_time_ext = true;
+        t->stats.queries = h[0]; t->stats.tri_tests = h[1]; t->stats.box_tests = h[2]; t->stats.bounces = h[3];
+        t->stats.emitted = h[5];
     }
-    tr->stats.queries = h[0]; tr->stats.tri_tests = h[1]; tr->stats.box_tests = h[2]; tr->stats.bounces = h[3];
-    tr->stats.emitted = h[5];
-    tr->stats.trace_kernel_ms = ms;
     return RVB_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <unordered_map>
 #include <map>
+#include <vector>
 
 #include "rvb_internal.cuh"
 
@@ -61,51 +62,65 @@ __global__ void export_hits_kernel(const uint32_t *hit, uint32_t nrays, uint32_t
     out[i] = hit[slot_of(r, b, nrays)];
 }
 
-static int trace_run_impl(rvb_scene *scene, const float mic[3], const float source[3], const float4 *d_dirs, size_t nrays,
-                          size_t nrefl, uint64_t ray_offset, unsigned flags, rvb_trace **out)
+// Traces `njobs` (microphone, source) pairs over the same scene and directions in one launch pair.
+static int trace_run_impl(rvb_scene *scene, size_t njobs, const float *mics /* [njobs][3] */, const float *sources /* [njobs][3] */,
+                          const float4 *d_dirs, size_t nrays, size_t nrefl, uint64_t ray_offset, unsigned flags, rvb_trace **out)
 {
     cudaStream_t st = lib_stream();
-    rvb_trace *tr = new rvb_trace();
-    tr->scene = scene; tr->nrays = nrays; tr->nrefl = nrefl; tr->ray_offset = ray_offset; tr->flags = flags;
-    for (int i = 0; i < 3; ++i) { tr->mic[i] = mic[i]; tr->src[i] = source[i]; }
-    tr->stats.nrays = nrays; tr->stats.nreflections = nrefl;
     const size_t nslots = slot_count(nrays, nrefl);
-    int rc = RVB_OK;
-    float4 *cvA = nullptr, *cvB = nullptr, *cpt = nullptr;
-    uint32_t *cidx = nullptr;
     const bool images = !(flags & RVB_TRACE_NO_IMAGES);
     const size_t ncand = images ? nrays * RVB_NUM_IMAGE_SOURCE : 0;
+    std::vector<rvb_trace *> trs(njobs, nullptr);
+    std::vector<CandBuffers> cands(njobs);
+    int rc = RVB_OK;
     StageTimer t_all("trace.total");
-    auto bail = [&](int code) { dev_free(cvA); dev_free(cvB); dev_free(cpt); dev_free(cidx); rvb_trace_destroy(tr); return code; };
+    auto bail = [&](int code) {
+        for (size_t j = 0; j < njobs; ++j) {
+            dev_free(cands[j].volA); dev_free(cands[j].volB); dev_free(cands[j].pt); dev_free(cands[j].idx);
+            if (trs[j]) rvb_trace_destroy(trs[j]);
+            out[j] = nullptr;
+        }
+        return code;
+    };
     {
     StageTimer t_alloc("trace.alloc");
-    if ((rc = dev_alloc(&tr->d_vol, 2 * nslots)) || (rc = dev_alloc(&tr->d_pt, nslots)) ||
-        (rc = dev_alloc(&tr->d_tkey, nslots)))
-        return bail(rc);
-    if ((nrefl % RVB_SLOT_GROUP) && nrays) note_launch(), mark_unused_slots_kernel<<<(unsigned)((nrays + 255) / 256), 256, 0, st>>>(tr->d_tkey, (uint32_t)nrays, (uint32_t)nrefl);
-    if (flags & RVB_TRACE_DEBUG) {
-        if ((rc = dev_alloc(&tr->d_hit, nslots)) || (rc = dev_alloc(&tr->d_count, nrays))) return bail(rc);
-    }
-    if (images && ncand) {
-        if ((rc = dev_alloc(&cvA, ncand)) || (rc = dev_alloc(&cvB, ncand)) || (rc = dev_alloc(&cpt, ncand)) ||
-            (rc = dev_alloc(&cidx, ncand)))
+    for (size_t j = 0; j < njobs; ++j) {
+        rvb_trace *tr = new rvb_trace();
+        trs[j] = tr;
+        tr->scene = scene; tr->nrays = nrays; tr->nrefl = nrefl; tr->ray_offset = ray_offset; tr->flags = flags;
+        for (int i = 0; i < 3; ++i) { tr->mic[i] = mics[3 * j + i]; tr->src[i] = sources[3 * j + i]; }
+        tr->stats.nrays = nrays; tr->stats.nreflections = nrefl;
+        if ((rc = dev_alloc(&tr->d_vol, 2 * nslots)) || (rc = dev_alloc(&tr->d_pt, nslots)) || (rc = dev_alloc(&tr->d_tkey, nslots)))
             return bail(rc);
-        cudaMemsetAsync(cidx, 0, ncand * sizeof(uint32_t), st);
-        // slot 0 of ray 0 is read even if the direct path is occluded (key {0} is unconditional)
-        cudaMemsetAsync(cvA, 0, sizeof(float4), st); cudaMemsetAsync(cvB, 0, sizeof(float4), st); cudaMemsetAsync(cpt, 0, sizeof(float4), st);
+        if ((nrefl % RVB_SLOT_GROUP) && nrays) note_launch(), mark_unused_slots_kernel<<<(unsigned)((nrays + 255) / 256), 256, 0, st>>>(tr->d_tkey, (uint32_t)nrays, (uint32_t)nrefl);
+        if (flags & RVB_TRACE_DEBUG) {
+            if ((rc = dev_alloc(&tr->d_hit, nslots)) || (rc = dev_alloc(&tr->d_count, nrays))) return bail(rc);
+        }
+        if (images && ncand) {
+            CandBuffers &cb = cands[j];
+            if ((rc = dev_alloc(&cb.volA, ncand)) || (rc = dev_alloc(&cb.volB, ncand)) || (rc = dev_alloc(&cb.pt, ncand)) || (rc = dev_alloc(&cb.idx, ncand)))
+                return bail(rc);
+            cudaMemsetAsync(cb.idx, 0, ncand * sizeof(uint32_t), st);
+            // slot 0 of ray 0 is read even if the direct path is occluded (key {0} is unconditional)
+            cudaMemsetAsync(cb.volA, 0, sizeof(float4), st); cudaMemsetAsync(cb.volB, 0, sizeof(float4), st); cudaMemsetAsync(cb.pt, 0, sizeof(float4), st);
+        }
     }
     }
     {
         StageTimer t_k("trace.kernel");
-        if ((rc = trace_launch(tr, d_dirs, cvA, cvB, cpt, cidx))) return bail(rc);
+        std::vector<Trace *> base(trs.begin(), trs.end());
+        if ((rc = trace_launch(base.data(), njobs, d_dirs, cands.data()))) return bail(rc);
     }
     if (images && ncand) {
         StageTimer t_d("trace.dedupe");
-        if ((rc = images_dedupe(tr, cvA, cvB, cpt, cidx))) return bail(rc);
+        for (size_t j = 0; j < njobs; ++j)
+            if ((rc = images_dedupe(trs[j], cands[j].volA, cands[j].volB, cands[j].pt, cands[j].idx))) return bail(rc);
     }
     StageTimer t_f("trace.free");
-    dev_free(cvA); dev_free(cvB); dev_free(cpt); dev_free(cidx);
-    *out = tr;
+    for (size_t j = 0; j < njobs; ++j) {
+        dev_free(cands[j].volA); dev_free(cands[j].volB); dev_free(cands[j].pt); dev_free(cands[j].idx);
+        out[j] = trs[j];
+    }
     return RVB_OK;
 }
 
@@ -128,10 +143,36 @@ int rvb_trace_run_device(rvb_scene *scene, const float mic[3], const float sourc
     cudaEvent_t e0, e1;
     RVB_CUDA(cudaEventCreate(&e0)); RVB_CUDA(cudaEventCreate(&e1));
     RVB_CUDA(cudaEventRecord(e0, st));
-    int rc = trace_run_impl(scene, mic, source, reinterpret_cast<const float4 *>(d_directions), nrays, nreflections, ray_offset, flags, out);
+    int rc = trace_run_impl(scene, 1, mic, source, reinterpret_cast<const float4 *>(d_directions), nrays, nreflections, ray_offset, flags, out);
     if (rc == RVB_OK) {
         cudaEventRecord(e1, st); cudaEventSynchronize(e1);
         cudaEventElapsedTime(&(*out)->stats.total_ms, e0, e1);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+int rvb_trace_run_batch(rvb_scene *scene, size_t njobs, const float *mics, const float *sources, const rvb_float3 *d_directions,
+                        size_t nrays, size_t nreflections, unsigned flags, rvb_trace **out)
+{
+    if (!out) return fail(RVB_ERR_INVALID, "out is null");
+    for (size_t j = 0; j < njobs; ++j) out[j] = nullptr;
+    if (njobs == 0) return RVB_OK;
+    if (!scene || !mics || !sources || (!d_directions && nrays)) return fail(RVB_ERR_INVALID, "null argument");
+    if (nrays >= (1ull << 32) || nreflections >= (1ull << 32)) return fail(RVB_ERR_UNSUPPORTED, "ray or reflection count too large");
+    if (njobs > 65535) return fail(RVB_ERR_UNSUPPORTED, "more than 65535 jobs in one batch");
+    RVB_CUDA(cudaSetDevice(scene->device));
+    RVB_TRY(ensure_device());
+    cudaStream_t st = lib_stream();
+    cudaEvent_t e0, e1;
+    RVB_CUDA(cudaEventCreate(&e0)); RVB_CUDA(cudaEventCreate(&e1));
+    RVB_CUDA(cudaEventRecord(e0, st));
+    int rc = trace_run_impl(scene, njobs, mics, sources, reinterpret_cast<const float4 *>(d_directions), nrays, nreflections, 0, flags, out);
+    if (rc == RVB_OK) {
+        float ms = 0.f;
+        cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        for (size_t j = 0; j < njobs; ++j) out[j]->stats.total_ms = ms;   // of the whole batch
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;

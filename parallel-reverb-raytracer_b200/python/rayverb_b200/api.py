@@ -53,7 +53,7 @@ class RenderConfig(C.Structure):
 EXPORTS = [
     "rvb_last_error", "rvb_device_count", "rvb_set_device", "rvb_version", "rvb_set_stream", "rvb_launch_count",
     "rvb_scene_create", "rvb_scene_destroy", "rvb_scene_accel",
-    "rvb_trace_run", "rvb_trace_run_device", "rvb_trace_destroy", "rvb_trace_diffuse_count", "rvb_trace_copy_diffuse",
+    "rvb_trace_run", "rvb_trace_run_device", "rvb_trace_run_batch", "rvb_trace_destroy", "rvb_trace_diffuse_count", "rvb_trace_copy_diffuse",
     "rvb_trace_image_count", "rvb_trace_copy_images", "rvb_trace_set_images", "rvb_images_merge",
     "rvb_trace_copy_debug", "rvb_trace_get_stats",
     "rvb_attenuate_speaker", "rvb_attenuate_hrtf",
@@ -90,6 +90,7 @@ def lib():
         L.rvb_scene_accel.argtypes = [vp, vp]
         L.rvb_trace_run.argtypes = [vp, vp, vp, vp, sz, sz, u64, u32, vp]
         L.rvb_trace_run_device.argtypes = [vp, vp, vp, vp, sz, sz, u64, u32, vp]
+        L.rvb_trace_run_batch.argtypes = [vp, sz, vp, vp, vp, sz, sz, u32, vp]
         L.rvb_trace_destroy.argtypes = [vp]
         L.rvb_trace_diffuse_count.argtypes = [vp, vp]
         L.rvb_trace_copy_diffuse.argtypes = [vp, vp]
@@ -367,6 +368,16 @@ class Raytracer:
                                        int(flags), C.byref(h)))
         self.trace = Trace(h, mic)
         return self.trace
+
+    def raytrace_batch(self, pairs, *, device_ptr, nrays, flags=0):
+        """rvb_trace_run_batch: `pairs` = [(mic, source), ...] over the same device-resident directions,
+        traced together.  Returns one Trace per pair (the caller closes them)."""
+        mics = np.ascontiguousarray([_f3(m) for m, _ in pairs], dtype=np.float32)
+        srcs = np.ascontiguousarray([_f3(s_) for _, s_ in pairs], dtype=np.float32)
+        handles = (C.c_void_p * len(pairs))()
+        _check(lib().rvb_trace_run_batch(self._h, len(pairs), _p(mics), _p(srcs), C.c_void_p(device_ptr), int(nrays),
+                                         self.nreflections, int(flags), handles))
+        return [Trace(C.c_void_p(handles[j]), mics[j]) for j in range(len(pairs))]
 
     def getRawDiffuse(self):
         return self.trace.raw_diffuse()

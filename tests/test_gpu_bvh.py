@@ -95,3 +95,34 @@ def test_c4_cathedral_512_rays_x16_hrtf_vs_oracle(orc):
     check_trace_against_oracle(orc, tri, vtx, srf, mic, src, dirs, 16, api.ACCEL_AUTO)
     _render_case(orc, tri, vtx, srf, mic, src, dirs, 16, api.ACCEL_AUTO,
                  hrtf=dict(table=scenes.synthetic_hrtf_table(), facing=(0, 0, -1), up=(0, 1, 0)))
+
+
+@pytest.mark.parametrize("accel,ntri", [(api.ACCEL_BVH, 6000), (api.ACCEL_BRUTE_FORCE, 1500)])
+def test_batched_trace_equals_individual_traces(accel, ntri):
+    """rvb_trace_run_batch (parameter sweeps, cmd/main.cpp:241-297 once per pair): every pair of the batch
+    gives, bit for bit, the trace and the impulse response of the same pair traced alone."""
+    import torch
+    tri, vtx, srf = scenes.pillar_room(ntri, npillars=3)
+    nrefl, nrays = 24, 5000
+    dirs = scenes.sphere_directions(nrays, seed=11)
+    d_dirs = torch.from_numpy(dirs).to("cuda")
+    pairs = [((12.5 - 1.1 * i, 1.4 + 0.2 * i, 8.5 - 0.6 * i), (2.0 + 0.9 * i, 1.6, 2.5 + 0.4 * i)) for i in range(7)]
+    kw = dict(speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], sr=44100.0, ft="linkwitz_riley", lo_cutoff=45.0)
+    rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
+    batch = rt.raytrace_batch(pairs, device_ptr=d_dirs.data_ptr(), nrays=nrays, flags=api.TRACE_DEBUG)
+    assert len(batch) == len(pairs)
+    for (mic, src), tb in zip(pairs, batch):
+        one = rt.raytrace(mic, src, None, device_ptr=d_dirs.data_ptr(), nrays=nrays, flags=api.TRACE_DEBUG)
+        (ha, ca), (hb, cb) = one.debug(), tb.debug()
+        assert np.array_equal(ca, cb) and np.array_equal(ha, hb)
+        assert one.raw_diffuse().tobytes() == tb.raw_diffuse().tobytes()
+        (ia, ka, la), (ib, kb, lb) = one.raw_images(with_keys=True), tb.raw_images(with_keys=True)
+        assert np.array_equal(ka, kb) and np.array_equal(la, lb) and ia.tobytes() == ib.tobytes()
+        sa, sb = one.stats(), tb.stats()
+        for k in ("queries", "tri_tests", "bounces", "emitted"):
+            assert sa[k] == sb[k], k
+        ir_a, ir_b = one.render_ir(**kw), tb.render_ir(**kw)
+        for x, y in zip(ir_a.channels, ir_b.channels):
+            assert x.tobytes() == y.tobytes()
+        tb.close()
+    rt.close()
