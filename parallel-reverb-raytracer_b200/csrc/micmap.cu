@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "micmap.cuh"
 #include "rvb_internal.cuh"
@@ -150,12 +151,18 @@ void micmap_free(MicMapStorage *s)
     s->map = MicMap{};
 }
 
-int micmap_build(const Scene *sc, const float mic[3], MicMapStorage *out)
+// Batched build: pass 1 (count + scan) of every job is enqueued, ONE synchronisation brings the entry
+// totals to the host, then the lists are allocated and filled.  `nqueries` (rays x reflections per job)
+// sizes the grid: building costs ~ entries, a visibility query ~ candidates per cell, so a job with few
+// queries gets a coarser map (16 cells per triangle from 128 queries per triangle upwards, 1 at the
+// other end).
+int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n, size_t nqueries, MicMapStorage *out)
 {
-    *out = MicMapStorage{};
+    for (size_t j = 0; j < n; ++j) out[j] = MicMapStorage{};
     static const int enabled = getenv("RVB_MICMAP") ? atoi(getenv("RVB_MICMAP")) : 1;
-    if (!enabled || sc->accel != RVB_ACCEL_BVH || !(sc->diag > 0.0f)) return RVB_OK;
-    static const double cells_per_tri = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 16.0;
+    if (!enabled || sc->accel != RVB_ACCEL_BVH || !(sc->diag > 0.0f) || n == 0) return RVB_OK;
+    static const double cpt_env = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 0.0;
+    const double cells_per_tri = cpt_env > 0.0 ? cpt_env : std::min(16.0, std::max(1.0, (double)nqueries / (8.0 * sc->T)));
     cudaStream_t st = lib_stream();
     MicMapParams M{};
     M.verts = sc->d_verts; M.T = sc->T;
@@ -164,35 +171,53 @@ int micmap_build(const Scene *sc, const float mic[3], MicMapStorage *out)
     M.delta = 1e-4f * sc->diag + 1e-6f;
     M.r_near = 40.0f * M.delta;
     M.wc = 0.5f * M.r_near;
-    for (int k = 0; k < 3; ++k) M.mic[k] = mic[k];
     M.near_cap = 4096;
     const size_t ncell = (size_t)6 * M.N * M.N;
-    uint32_t *d_cursor = nullptr, *d_block = nullptr, *d_near_count = nullptr;
-    int rc = RVB_OK;
-    auto done = [&](int code) { dev_free(d_cursor); dev_free(d_block); dev_free(d_near_count); if (code) micmap_free(out); return code; };
-    if ((rc = dev_alloc(&out->d_cell_off, ncell + 1)) || (rc = dev_alloc(&d_cursor, ncell)) || (rc = dev_alloc(&d_block, scan_blocks(ncell))) ||
-        (rc = dev_alloc(&d_near_count, 2)) || (rc = dev_alloc(&out->d_near, (size_t)M.near_cap)))
-        return done(rc);
-    RVB_CUDA(cudaMemsetAsync(out->d_cell_off, 0, (ncell + 1) * sizeof(uint32_t), st));
-    RVB_CUDA(cudaMemsetAsync(d_cursor, 0, ncell * sizeof(uint32_t), st));
-    RVB_CUDA(cudaMemsetAsync(d_near_count, 0, 2 * sizeof(uint32_t), st));
     const unsigned grd = (M.T + 3) / 4;   // one warp per triangle, four per CTA
-    note_launch(), micmap_bin_kernel<false><<<grd, 128, 0, st>>>(M, out->d_cell_off, nullptr, nullptr, d_near_count, nullptr);
-    if ((rc = exclusive_scan_u32(out->d_cell_off, out->d_cell_off, ncell, d_block, out->d_cell_off + ncell, st))) return done(rc);
-    uint32_t h[2] = {0, 0};   // total entries, near triangles
-    RVB_CUDA(cudaMemcpyAsync(d_near_count + 1, out->d_cell_off + ncell, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    if ((rc = read_back(h, d_near_count, sizeof h))) return done(rc);
-    const uint32_t n_near = h[0], total = h[1];
-    if (n_near > M.near_cap) return done(RVB_OK), micmap_free(out), RVB_OK;   // microphone inside dense geometry: generic queries
-    if ((rc = dev_alloc(&out->d_cell_ent, (size_t)std::max(1u, total)))) return done(rc);
-    RVB_CUDA(cudaMemsetAsync(d_near_count, 0, sizeof(uint32_t), st));
-    note_launch(), micmap_bin_kernel<true><<<grd, 128, 0, st>>>(M, d_cursor, out->d_cell_off, out->d_cell_ent, d_near_count, out->d_near);
+    std::vector<uint32_t *> cursor(n, nullptr), block(n, nullptr);
+    uint32_t *d_counts = nullptr;          // per job: near triangles, total entries
+    int rc = RVB_OK;
+    auto done = [&](int code) {
+        for (size_t j = 0; j < n; ++j) { dev_free(cursor[j]); dev_free(block[j]); if (code) micmap_free(&out[j]); }
+        dev_free(d_counts);
+        return code;
+    };
+    if ((rc = dev_alloc(&d_counts, 2 * n))) return done(rc);
+    RVB_CUDA(cudaMemsetAsync(d_counts, 0, 2 * n * sizeof(uint32_t), st));
+    for (size_t j = 0; j < n; ++j) {
+        MicMapStorage &o = out[j];
+        if ((rc = dev_alloc(&o.d_cell_off, ncell + 1)) || (rc = dev_alloc(&cursor[j], ncell)) || (rc = dev_alloc(&block[j], scan_blocks(ncell))) ||
+            (rc = dev_alloc(&o.d_near, (size_t)M.near_cap)))
+            return done(rc);
+        RVB_CUDA(cudaMemsetAsync(o.d_cell_off, 0, (ncell + 1) * sizeof(uint32_t), st));
+        RVB_CUDA(cudaMemsetAsync(cursor[j], 0, ncell * sizeof(uint32_t), st));
+        for (int k = 0; k < 3; ++k) M.mic[k] = mics[3 * j + k];
+        note_launch(), micmap_bin_kernel<false><<<grd, 128, 0, st>>>(M, o.d_cell_off, nullptr, nullptr, d_counts + 2 * j, nullptr);
+        if ((rc = exclusive_scan_u32(o.d_cell_off, o.d_cell_off, ncell, block[j], o.d_cell_off + ncell, st))) return done(rc);
+        RVB_CUDA(cudaMemcpyAsync(d_counts + 2 * j + 1, o.d_cell_off + ncell, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    std::vector<uint32_t> h(2 * n, 0u);
+    if ((rc = read_back(h.data(), d_counts, 2 * n * sizeof(uint32_t)))) return done(rc);
+    RVB_CUDA(cudaMemsetAsync(d_counts, 0, 2 * n * sizeof(uint32_t), st));
+    for (size_t j = 0; j < n; ++j) {
+        MicMapStorage &o = out[j];
+        const uint32_t n_near = h[2 * j], total = h[2 * j + 1];
+        if (n_near > M.near_cap) { micmap_free(&o); continue; }   // microphone inside dense geometry: generic queries
+        if ((rc = dev_alloc(&o.d_cell_ent, (size_t)std::max(1u, total)))) return done(rc);
+        for (int k = 0; k < 3; ++k) M.mic[k] = mics[3 * j + k];
+        note_launch(), micmap_bin_kernel<true><<<grd, 128, 0, st>>>(M, cursor[j], o.d_cell_off, o.d_cell_ent, d_counts + 2 * j, o.d_near);
+        o.map.cell_off = o.d_cell_off; o.map.cell_ent = o.d_cell_ent; o.map.near_ent = o.d_near;
+        o.map.n_near = n_near; o.map.N = M.N; o.map.half_n = M.half_n;
+        for (int k = 0; k < 3; ++k) o.map.mic[k] = mics[3 * j + k];
+        o.entries = total;
+    }
     RVB_CUDA(cudaGetLastError());
-    out->map.cell_off = out->d_cell_off; out->map.cell_ent = out->d_cell_ent; out->map.near_ent = out->d_near;
-    out->map.n_near = n_near; out->map.N = M.N; out->map.half_n = M.half_n;
-    for (int k = 0; k < 3; ++k) out->map.mic[k] = mic[k];
-    out->entries = total;
     return done(RVB_OK);
+}
+
+int micmap_build(const Scene *sc, const float mic[3], size_t nqueries, MicMapStorage *out)
+{
+    return micmap_build_batch(sc, mic, 1, nqueries, out);
 }
 
 }  // namespace rvb

@@ -175,7 +175,8 @@ struct MicMapStorage {
     uint32_t *d_cell_off = nullptr, *d_cell_ent = nullptr, *d_near = nullptr;
     uint32_t entries = 0;
 };
-int micmap_build(const Scene *sc, const float mic[3], MicMapStorage *out);
+int micmap_build(const Scene *sc, const float mic[3], size_t nqueries, MicMapStorage *out);
+int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n, size_t nqueries, MicMapStorage *out /* [n] */);
 void micmap_free(MicMapStorage *s);
 
 // ---- stage entry points (defined in the .cu files) ----------------------------------------------

@@ -827,12 +827,15 @@ __device__ __forceinline__ void load_job(TraceJob *dst, const TraceJob *src)
 // BLOCK = 256 for small scenes (several CTAs per SM); when the shared-memory scene leaves room for
 // only one CTA per SM the launcher switches to 1024 (steady phase) / 512 (image phase) threads so
 // that the schedulers still have 8 / 4 warps each.
-template <bool IMAGES, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TraceParams P)
+// BATCH = false: the single job's record is a kernel parameter (constant bank, no registers or shared
+// memory spent on it); BATCH = true: the CTA's job (blockIdx.y) is copied to shared memory.
+template <bool IMAGES, int BLOCK, bool BATCH>
+__global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TraceParams P, const TraceJob J0)
 {
     extern __shared__ float4 s_tri[];
-    __shared__ TraceJob J;
-    load_job(&J, P.jobs + blockIdx.y);
+    __shared__ TraceJob sJ;
+    if (BATCH) load_job(&sJ, P.jobs + blockIdx.y);
+    const TraceJob &J = BATCH ? sJ : J0;
     stage_scene(s_tri, P);
     BruteSmem acc{s_tri, P.T, P.nquads};
     Counters c;
@@ -844,12 +847,13 @@ __global__ void __launch_bounds__(BLOCK) trace_bruteforce_kernel(const TracePara
 
 // One warp per ray (BruteSmemWarp): all lanes run the per-ray code on the same ray; identical values
 // are stored to identical addresses, and only lane 0's bounce count is kept.
-template <bool IMAGES>
-__global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceParams P)
+template <bool IMAGES, bool BATCH>
+__global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceParams P, const TraceJob J0)
 {
     extern __shared__ float4 s_tri[];
-    __shared__ TraceJob J;
-    load_job(&J, P.jobs + blockIdx.y);
+    __shared__ TraceJob sJ;
+    if (BATCH) load_job(&sJ, P.jobs + blockIdx.y);
+    const TraceJob &J = BATCH ? sJ : J0;
     stage_scene(s_tri, P);
     BruteSmemWarp acc{s_tri, P.T, P.nquads};
     Counters c;
@@ -862,12 +866,13 @@ __global__ void __launch_bounds__(256) trace_bruteforce_warp_kernel(const TraceP
     flush_counters(J, c);
 }
 
-template <bool IMAGES, int MINB>
-__global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams P)
+template <bool IMAGES, int MINB, bool BATCH>
+__global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams P, const TraceJob J0)
 {
     extern __shared__ int s_stack[];
-    __shared__ TraceJob J;
-    load_job(&J, P.jobs + blockIdx.y);
+    __shared__ TraceJob sJ;
+    if (BATCH) load_job(&sJ, P.jobs + blockIdx.y);
+    const TraceJob &J = BATCH ? sJ : J0;
     const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, J.micmap, TravStack{s_stack + threadIdx.x}};
     Counters c;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.nrays; i += gridDim.x * blockDim.x) {
@@ -904,7 +909,7 @@ static int occupancy_of(K kernel, int block, size_t smem, int &per_sm)
 }
 
 template <class K>
-static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, cudaStream_t st)
+static int launch_phase(K kernel, const TraceParams &P, const TraceJob &J0, int block, size_t smem, cudaStream_t st)
 {
     int per_sm = 0;
     RVB_TRY(occupancy_of(kernel, block, smem, per_sm));
@@ -913,7 +918,7 @@ static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, 
     const size_t want = ((size_t)P.nrays + block - 1) / block;
     const size_t share = std::max<size_t>(1, ((size_t)per_sm * sm_count() + P.njobs - 1) / P.njobs);
     const size_t grid = std::max<size_t>(1, std::min(want, share));
-    note_launch(), kernel<<<dim3((unsigned)grid, P.njobs), block, smem, st>>>(P);
+    note_launch(), kernel<<<dim3((unsigned)grid, P.njobs), block, smem, st>>>(P, J0);
     RVB_CUDA(cudaGetLastError());
     return RVB_OK;
 }
@@ -926,7 +931,14 @@ static int launch_phase(K kernel, const TraceParams &P, int block, size_t smem, 
 template <bool IMAGES, int BLOCK>
 static int try_block(const TraceParams &P, size_t smem, int &per_sm)
 {
-    return occupancy_of(trace_bruteforce_kernel<IMAGES, BLOCK>, BLOCK, smem, per_sm);
+    if (P.njobs > 1) return occupancy_of(trace_bruteforce_kernel<IMAGES, BLOCK, true>, BLOCK, smem, per_sm);
+    return occupancy_of(trace_bruteforce_kernel<IMAGES, BLOCK, false>, BLOCK, smem, per_sm);
+}
+template <bool IMAGES, int BLOCK>
+static int launch_block(const TraceParams &P, const TraceJob &J0, size_t smem, cudaStream_t st)
+{
+    if (P.njobs > 1) return launch_phase(trace_bruteforce_kernel<IMAGES, BLOCK, true>, P, J0, BLOCK, smem, st);
+    return launch_phase(trace_bruteforce_kernel<IMAGES, BLOCK, false>, P, J0, BLOCK, smem, st);
 }
 // Few rays over many triangles: one warp per ray.  Cost model in units of one pair-test latency:
 // thread-per-ray needs ceil(nrays / resident threads) waves of T tests per query, warp-per-ray
@@ -943,22 +955,22 @@ static bool prefer_warp_per_ray(const TraceParams &P)
 }
 
 template <bool IMAGES>
-static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
+static int launch_bruteforce(const TraceParams &P, const TraceJob &J0, size_t smem, cudaStream_t st)
 {
     if (prefer_warp_per_ray(P)) {
         int per_sm = 0;
-        RVB_TRY(occupancy_of(trace_bruteforce_warp_kernel<IMAGES>, 256, smem, per_sm));
+        auto wk = P.njobs > 1 ? trace_bruteforce_warp_kernel<IMAGES, true> : trace_bruteforce_warp_kernel<IMAGES, false>;
+        RVB_TRY(occupancy_of(wk, 256, smem, per_sm));
         if (per_sm >= 1) {
             const size_t want = ((size_t)P.nrays * 32 + 255) / 256;
             const size_t share = std::max<size_t>(1, ((size_t)per_sm * sm_count() + P.njobs - 1) / P.njobs);
             const size_t grid = std::max<size_t>(1, std::min(want, share));
-            note_launch(), trace_bruteforce_warp_kernel<IMAGES><<<dim3((unsigned)grid, P.njobs), 256, smem, st>>>(P);
+            note_launch(), wk<<<dim3((unsigned)grid, P.njobs), 256, smem, st>>>(P, J0);
             RVB_CUDA(cudaGetLastError());
             return RVB_OK;
         }
     }
     static const int forced = getenv("RVB_BLOCK") ? atoi(getenv("RVB_BLOCK")) : 0;
-    if (forced == 640) return launch_phase(trace_bruteforce_kernel<IMAGES, 640>, P, 640, smem, st);   // experiment: 20 warps at <= 102 registers
     const int sizes[5] = {256, 384, 512, 768, 1024};
     // steady phase (fused two-ray sweep, ~128 registers): 512 threads measured best on C2 and on the
     // 4352-triangle room (profiles/r2_sweep_bruteforce_block.log); image phase: as in round 1
@@ -981,11 +993,11 @@ static int launch_bruteforce(const TraceParams &P, size_t smem, cudaStream_t st)
         if (score > best_score) { best_score = score; best = i; }
     }
     switch (best) {
-    case 0: return launch_phase(trace_bruteforce_kernel<IMAGES, 256>, P, 256, smem, st);
-    case 1: return launch_phase(trace_bruteforce_kernel<IMAGES, 384>, P, 384, smem, st);
-    case 2: return launch_phase(trace_bruteforce_kernel<IMAGES, 512>, P, 512, smem, st);
-    case 3: return launch_phase(trace_bruteforce_kernel<IMAGES, 768>, P, 768, smem, st);
-    default: return launch_phase(trace_bruteforce_kernel<IMAGES, 1024>, P, 1024, smem, st);
+    case 0: return launch_block<IMAGES, 256>(P, J0, smem, st);
+    case 1: return launch_block<IMAGES, 384>(P, J0, smem, st);
+    case 2: return launch_block<IMAGES, 512>(P, J0, smem, st);
+    case 3: return launch_block<IMAGES, 768>(P, J0, smem, st);
+    default: return launch_block<IMAGES, 1024>(P, J0, smem, st);
     }
 }
 
@@ -1018,28 +1030,28 @@ struct WfShared {
     uint32_t ray[128], index[128], queries[128], bounces[128], emitted[128], tri[128];
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const TraceParams P, unsigned int *fetch_all /* [njobs] */)
+template <int MINB, bool BATCH>
+__global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const TraceParams P, const TraceJob J0, unsigned int *fetch_all /* [njobs] */)
 {
     __shared__ WfShared S;
-    __shared__ TraceJob sJ[4];                       // the job each warp currently works for
+    __shared__ TraceJob sJ[4];                       // BATCH: the job each warp currently works for
     extern __shared__ int s_stack[];
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, tid = threadIdx.x, warp = threadIdx.x >> 5;
     const TravStack stack{s_stack + tid};
-    const TraceJob &J = sJ[warp];
+    const TraceJob &J = BATCH ? sJ[warp] : J0;
     // A warp works for ONE job at a time (a plain trace has one job).  With at least as many warps as
     // jobs the warps are dealt round-robin to the jobs, otherwise the jobs to the warps.
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp, nw = gridDim.x * (blockDim.x >> 5);
     const bool many_warps = nw >= P.njobs;
   for (uint32_t job = many_warps ? gw % P.njobs : gw; job < P.njobs; job += many_warps ? P.njobs : nw) {
-    __syncwarp();
-    {
+    if (BATCH) {
+        __syncwarp();
         const uint32_t *src = reinterpret_cast<const uint32_t *>(P.jobs + job);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&sJ[warp]);
         for (uint32_t k = lane; k < sizeof(TraceJob) / 4; k += 32) dst[k] = src[k];
+        __syncwarp();
     }
-    __syncwarp();
     unsigned int *fetch = fetch_all + job;
     const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, J.micmap, stack};
     int sp = 0, node = RVB_SENTINEL;
@@ -1164,7 +1176,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
   }
 }
 
-static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStream_t st)
+static int launch_wavefront(const TraceParams &P_in, const TraceJob &J0, size_t stack_bytes, cudaStream_t st)
 {
     static const int minb_env = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 0;
     static const int service = getenv("RVB_WF_SERVICE") ? atoi(getenv("RVB_WF_SERVICE")) : 24;
@@ -1183,20 +1195,26 @@ static int launch_wavefront(const TraceParams &P_in, size_t stack_bytes, cudaStr
         RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, stack_bytes));
         const size_t want = ((size_t)P.nrays * P.njobs + 127) / 128;
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min(want, (size_t)std::max(per_sm, 1) * sm_count()));
-        note_launch(), kernel<<<grid, 128, stack_bytes, st>>>(P, d_fetch);
+        note_launch(), kernel<<<grid, 128, stack_bytes, st>>>(P, J0, d_fetch);
         RVB_CUDA(cudaGetLastError());
         return RVB_OK;
     };
     int rc;
+    const bool batch = P.njobs > 1;
     switch (minb) {
-    case 4: rc = go(trace_bvh_wavefront_kernel<4>); break;
-    case 5: rc = go(trace_bvh_wavefront_kernel<5>); break;
-    case 7: rc = go(trace_bvh_wavefront_kernel<7>); break;
-    case 8: rc = go(trace_bvh_wavefront_kernel<8>); break;
-    default: rc = go(trace_bvh_wavefront_kernel<6>); break;
+    case 4: rc = batch ? go(trace_bvh_wavefront_kernel<4, true>) : go(trace_bvh_wavefront_kernel<4, false>); break;
+    case 6: rc = batch ? go(trace_bvh_wavefront_kernel<6, true>) : go(trace_bvh_wavefront_kernel<6, false>); break;
+    case 7: rc = batch ? go(trace_bvh_wavefront_kernel<7, true>) : go(trace_bvh_wavefront_kernel<7, false>); break;
+    default: rc = batch ? go(trace_bvh_wavefront_kernel<5, true>) : go(trace_bvh_wavefront_kernel<5, false>); break;
     }
     dev_free(d_fetch);
     return rc;
+}
+
+static int launch_bvh_images(const TraceParams &P, const TraceJob &J0, size_t smem, cudaStream_t st)
+{
+    if (P.njobs > 1) return launch_phase(trace_bvh_kernel<true, 1, true>, P, J0, 128, smem, st);
+    return launch_phase(trace_bvh_kernel<true, 1, false>, P, J0, 128, smem, st);
 }
 
 int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const CandBuffers *cands)
@@ -1260,9 +1278,13 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     // trace: it is part of the measured work, not a cache).
     std::vector<MicMapStorage> mms(njobs);
     std::vector<TraceJob> jobs(njobs);
+    if (!brute && tr->nrays > 0) {
+        std::vector<float> mics(3 * njobs);
+        for (size_t j = 0; j < njobs; ++j) for (int i = 0; i < 3; ++i) mics[3 * j + i] = trs[j]->mic[i];
+        RVB_TRY(micmap_build_batch(sc, mics.data(), njobs, tr->nrays * std::max<size_t>(tr->nrefl, 1), mms.data()));
+    }
     for (size_t j = 0; j < njobs; ++j) {
         Trace *t = trs[j];
-        if (!brute && t->nrays > 0) RVB_TRY(micmap_build(sc, t->mic, &mms[j]));
         TraceJob &J = jobs[j];
         for (int i = 0; i < 3; ++i) { J.mic[i] = t->mic[i]; J.src[i] = t->src[i]; }
         J.ray_offset = t->ray_offset;
@@ -1283,28 +1305,25 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     if (tr->nrays > 0 && tr->nrefl > 0) {
         if (split > 0) {
             P.first = 0; P.last = split;
-            if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
-            else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, smem, st));
+            if (brute) RVB_TRY(launch_bruteforce<true>(P, jobs[0], smem, st));
+            else RVB_TRY(launch_bvh_images(P, jobs[0], smem, st));
             RVB_CUDA(cudaEventRecord(em, st));
             RVB_CUDA(cudaMemcpyAsync(h_mid.data(), d_counters, 6 * njobs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         }
         if (split < tr->nrefl) {
             P.first = split; P.last = (uint32_t)tr->nrefl;
-            if (brute) RVB_TRY(launch_bruteforce<false>(P, smem, st));
-            else if (!wavefront) {
-                // resident CTAs of 128 threads per SM (register cap 65536 / (128 n)); RVB_BVH_MINB overrides
-                static const int minb = getenv("RVB_BVH_MINB") ? atoi(getenv("RVB_BVH_MINB")) : 7;
-                if (minb <= 5) RVB_TRY(launch_phase(trace_bvh_kernel<false, 5>, P, 128, smem, st));
-                else if (minb == 6) RVB_TRY(launch_phase(trace_bvh_kernel<false, 6>, P, 128, smem, st));
-                else RVB_TRY(launch_phase(trace_bvh_kernel<false, 7>, P, 128, smem, st));
+            if (brute) RVB_TRY(launch_bruteforce<false>(P, jobs[0], smem, st));
+            else if (!wavefront) {   // one thread per ray, 6 CTAs of 128 threads per SM (80 registers)
+                if (njobs > 1) RVB_TRY(launch_phase(trace_bvh_kernel<false, 6, true>, P, jobs[0], 128, smem, st));
+                else RVB_TRY(launch_phase(trace_bvh_kernel<false, 6, false>, P, jobs[0], 128, smem, st));
             }
-            else RVB_TRY(launch_wavefront(P, smem, st));
+            else RVB_TRY(launch_wavefront(P, jobs[0], smem, st));
         }
     } else if (tr->nrays > 0 && images) {
         // zero reflections: the reference still computes the direct path for ray 0
         P.first = 0; P.last = 0;
-        if (brute) RVB_TRY(launch_bruteforce<true>(P, smem, st));
-        else RVB_TRY(launch_phase(trace_bvh_kernel<true, 1>, P, 128, smem, st));
+        if (brute) RVB_TRY(launch_bruteforce<true>(P, jobs[0], smem, st));
+        else RVB_TRY(launch_bvh_images(P, jobs[0], smem, st));
     }
     RVB_CUDA(cudaEventRecord(e1, st));
     RVB_CUDA(cudaMemcpyAsync(h_end.data(), d_counters, 6 * njobs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
