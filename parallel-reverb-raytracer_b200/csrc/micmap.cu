@@ -101,14 +101,15 @@ __device__ __forceinline__ bool face_rect(const float (&p)[3][3], int face, cons
 
 // FILL = false: count entries per cell (counts[cell]) and near triangles (near_count)
 // FILL = true : write them (cursor[cell] starts at 0; offsets from the scan)
-// One WARP per triangle, lanes over the cells of its rectangles: the fill's atomics return a value,
-// and a single thread walking its ~30 cells one round trip after the other took 2 ms on the 100k-
-// triangle hall (18x the count pass).
+// One WARP per triangle: lanes 0..5 work out the six faces' rectangles (one face each), then all lanes
+// share the cells of every rectangle -- the fill's atomics return a value, and a single thread walking
+// its ~30 cells one round trip after the other took 2 ms on the 100k-triangle hall.
 template <bool FILL>
 __global__ void __launch_bounds__(128) micmap_bin_kernel(const MicMapParams M, uint32_t *counts_or_cursor, const uint32_t *cell_off,
                                                          uint32_t *cell_ent, uint32_t *near_count, uint32_t *near_ent)
 {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    __shared__ FaceRect s_rect[4][6];
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (i >= M.T) return;   // warp-uniform
     float p[3][3];
 #pragma unroll
@@ -131,14 +132,22 @@ __global__ void __launch_bounds__(128) micmap_bin_kernel(const MicMapParams M, u
         }
         return;
     }
-    for (int f = 0; f < 6; ++f) {
+    bool ok = false;
+    if (lane < 6) {
         FaceRect r;
-        if (!face_rect(p, f, M, r)) continue;   // warp-uniform: every lane computes the same rectangle
+        ok = face_rect(p, (int)lane, M, r);
+        if (ok) s_rect[warp][lane] = r;
+    }
+    const uint32_t valid = __ballot_sync(0xffffffffu, ok);
+    __syncwarp();
+    for (uint32_t f = 0; f < 6; ++f) {
+        if (!((valid >> f) & 1u)) continue;
+        const FaceRect &r = s_rect[warp][f];
         const uint32_t w = r.i1 - r.i0 + 1, n = w * (r.j1 - r.j0 + 1);
         for (uint32_t c = lane; c < n; c += 32u) {
             const uint32_t j = r.j0 + c / w, ii = r.i0 + c % w;
             if (cell_outside(r, ii, j, M.N)) continue;
-            const uint32_t cell = ((uint32_t)f * M.N + j) * M.N + ii;
+            const uint32_t cell = (f * M.N + j) * M.N + ii;
             const uint32_t k = atomicAdd(counts_or_cursor + cell, 1u);
             if (FILL) cell_ent[cell_off[cell] + k] = i;
         }
@@ -154,15 +163,15 @@ void micmap_free(MicMapStorage *s)
 // Batched build: pass 1 (count + scan) of every job is enqueued, ONE synchronisation brings the entry
 // totals to the host, then the lists are allocated and filled.  `nqueries` (rays x reflections per job)
 // sizes the grid: building costs ~ entries, a visibility query ~ candidates per cell, so a job with few
-// queries gets a coarser map (16 cells per triangle from 128 queries per triangle upwards, 1 at the
-// other end).
+// queries gets a coarser map (16 cells per triangle from 32 queries per triangle upwards, 4 at the
+// other end; C5's 16 k rays x 128 per pair: 10).
 int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n, size_t nqueries, MicMapStorage *out)
 {
     for (size_t j = 0; j < n; ++j) out[j] = MicMapStorage{};
     static const int enabled = getenv("RVB_MICMAP") ? atoi(getenv("RVB_MICMAP")) : 1;
     if (!enabled || sc->accel != RVB_ACCEL_BVH || !(sc->diag > 0.0f) || n == 0) return RVB_OK;
     static const double cpt_env = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 0.0;
-    const double cells_per_tri = cpt_env > 0.0 ? cpt_env : std::min(16.0, std::max(1.0, (double)nqueries / (8.0 * sc->T)));
+    const double cells_per_tri = cpt_env > 0.0 ? cpt_env : std::min(16.0, std::max(4.0, (double)nqueries / (2.0 * sc->T)));
     cudaStream_t st = lib_stream();
     MicMapParams M{};
     M.verts = sc->d_verts; M.T = sc->T;

@@ -1279,6 +1279,7 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     std::vector<MicMapStorage> mms(njobs);
     std::vector<TraceJob> jobs(njobs);
     if (!brute && tr->nrays > 0) {
+        StageTimer t_mm("trace.micmap");
         std::vector<float> mics(3 * njobs);
         for (size_t j = 0; j < njobs; ++j) for (int i = 0; i < 3; ++i) mics[3 * j + i] = trs[j]->mic[i];
         RVB_TRY(micmap_build_batch(sc, mics.data(), njobs, tr->nrays * std::max<size_t>(tr->nrefl, 1), mms.data()));
@@ -1304,6 +1305,7 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     RVB_CUDA(cudaEventRecord(em, st));
     if (tr->nrays > 0 && tr->nrefl > 0) {
         if (split > 0) {
+            StageTimer t_im("trace.image_phase");
             P.first = 0; P.last = split;
             if (brute) RVB_TRY(launch_bruteforce<true>(P, jobs[0], smem, st));
             else RVB_TRY(launch_bvh_images(P, jobs[0], smem, st));
@@ -1311,6 +1313,7 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
             RVB_CUDA(cudaMemcpyAsync(h_mid.data(), d_counters, 6 * njobs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         }
         if (split < tr->nrefl) {
+            StageTimer t_st("trace.steady_phase");
             P.first = split; P.last = (uint32_t)tr->nrefl;
             if (brute) RVB_TRY(launch_bruteforce<false>(P, jobs[0], smem, st));
             else if (!wavefront) {   // one thread per ray, 6 CTAs of 128 threads per SM (80 registers)
