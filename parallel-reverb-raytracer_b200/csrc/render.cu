@@ -18,6 +18,7 @@
 
 #include "attenuate.cuh"
 #include "rvb_internal.cuh"
+#include "rvb_sort.cuh"
 
 namespace rvb {
 
@@ -100,7 +101,13 @@ __global__ void times_kernel(const Source S, const ChanSpec C, int *out /* [0] o
 __device__ __forceinline__ uint32_t sample_index(float t, float predelay, bool fix, float sr)
 {
     if (fix) t = t > predelay ? __fsub_rn(t, predelay) : 0.0f;
-    return (uint32_t)roundf(__fmul_rn(t, sr));
+    // round(x), half away from zero (rayverb.cpp:69), without the library call: rint rounds half to even, so it
+    // differs only when the fraction is exactly one half and it went down -- x - r is exact and equals 0.5 then.
+    // (negative x, NaN and infinities convert to the same integers either way)
+    const float x = __fmul_rn(t, sr);
+    float r = rintf(x);
+    if (__fsub_rn(x, r) == 0.5f) r = __fadd_rn(r, 1.0f);
+    return (uint32_t)r;
 }
 
 // Two key formats.  Wide (uint32): key = sample index (sentinel L), value = impulse id; the sort skips
@@ -188,6 +195,73 @@ __global__ void bounds_kernel(const KeyT *keys, uint32_t n, uint32_t nseg, uint3
     }
 }
 
+// ---- the flatten's own sort (rvb_sort.cuh) ----------------------------------------------------------
+// Key = segment id (sample index >> shift), value = impulse id with the sub-bin inside the segment in
+// bits 30-31.  The sample index is a function of the impulse time, so the speaker / pass-through models
+// never store keys: the digit histogram and the first radix pass both evaluate it from the 4-byte time.
+// The HRTF model's time needs the impulse position (kernel.cpp:612-619); there the histogram sweep stores
+// the sample indices and the first pass reads them back.  Skipped impulses (time key -1, kernel.cpp:524)
+// and samples past the end never enter the sort.
+// image sources: time key as for the diffuse slots -- the time, or -1 when all eight volumes are zero (kernel.cpp:524)
+__global__ void image_tkeys_kernel(const float4 *volA, const float4 *volB, const float4 *pt, uint32_t n, float *tkey)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float4 a = volA[j], b = volB[j];
+    const bool any = a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f || b.x != 0.f || b.y != 0.f || b.z != 0.f || b.w != 0.f;
+    tkey[j] = any ? pt[j].w : -1.0f;
+}
+
+enum { FLATTEN_TIME = 0, FLATTEN_TIME_POS = 1, FLATTEN_STORED = 2 };
+template <class KeyT, int MODE>
+struct FlattenIn {
+    const float *tkey, *img_tkey;          // time keys of the diffuse slots / of the image sources
+    const float4 *pt, *img_pt;             // FLATTEN_TIME_POS: (position, time)
+    const uint32_t *stored;                // FLATTEN_STORED: sample index per impulse, 0xffffffff = skipped
+    uint32_t n_diffuse;
+    f3 mic, ear;
+    float predelay, sr;
+    uint32_t L, shift;
+    bool fix;
+    struct RawT { float t; };
+    struct RawTP { float t; float4 p; };
+    typedef typename std::conditional<MODE == FLATTEN_TIME_POS, RawTP, RawT>::type Raw;
+    __device__ __forceinline__ Raw fetch(uint32_t i) const
+    {
+        Raw r{};
+        if constexpr (MODE == FLATTEN_STORED) r.t = __uint_as_float(stored[i]);
+        else {
+            const bool img = i >= n_diffuse;
+            r.t = (img ? img_tkey - n_diffuse : tkey)[i];
+            if constexpr (MODE == FLATTEN_TIME_POS) r.p = (img ? img_pt - n_diffuse : pt)[i];
+        }
+        return r;
+    }
+    __device__ __forceinline__ bool decode(uint32_t i, const Raw &r, KeyT &k, uint32_t &v) const
+    {
+        uint32_t s;
+        if constexpr (MODE == FLATTEN_STORED) s = __float_as_uint(r.t);   // 0xffffffff >= L
+        else {
+            float t = r.t;
+            if (!(t >= 0.0f)) return false;                                                           // Source::time_of
+            if constexpr (MODE == FLATTEN_TIME_POS) t = hrtf_time(r.p.w, mk3(r.p), mic, ear);         // attenuated_time
+            s = sample_index(t, predelay, fix, sr);
+        }
+        if (s >= L) return false;
+        k = (KeyT)(s >> shift);
+        v = i | ((s & ((1u << shift) - 1u)) << 30);   // shift > 0 only when i < 2^30
+        return true;
+    }
+};
+struct StoreSampleIndex {
+    uint32_t *out;
+    uint32_t shift;
+    __device__ __forceinline__ void operator()(uint32_t i, bool ok, uint32_t k, uint32_t v) const
+    {
+        out[i] = ok ? ((k << shift) | (shift ? v >> 30 : 0u)) : 0xffffffffu;
+    }
+};
+
 // One warp per segment: lane l takes entries begin+l, begin+l+32, ... in order (four gathers in
 // flight per lane), then a fixed xor-shuffle tree combines the 32 partial sums of every
 // (sub-bin, channel, band).  hist layout: [channel][band][L].
@@ -272,7 +346,7 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
     for (uint32_t w = warp; w < nseg; w += nwarps) {
         const uint32_t seg = nseg - 1 - w;
         const uint32_t b0 = seg_begin[seg], b1 = seg_end[seg];
-        if (b0 == b1) continue;   // warp-uniform
+        if (b0 >= b1) continue;   // warp-uniform (empty: begin 0xffffffff, end 0)
         float acc[NSUB][MAXC][RVB_NBANDS];
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
@@ -288,9 +362,8 @@ __global__ void __launch_bounds__(256) reduce_kernel(const Source S, const ChanS
                 idx[u] = RVB_NO_IMPULSE; sub[u] = 0;
                 if (j + 32 * u < b1) {
                     idx[u] = vals[j + 32 * u];
-                    if (keys == nullptr) {                     // compact format: sub-bin in the value's top bits
-                        sub[u] = (idx[u] >> 30) & (NSUB - 1);
-                        idx[u] &= RVB_ID_MASK;
+                    if (keys == nullptr) {                     // sub-bin in the value's top bits (ids < 2^30 whenever NSUB > 1)
+                        if (NSUB > 1) { sub[u] = (idx[u] >> 30) & (NSUB - 1); idx[u] &= RVB_ID_MASK; }
                     } else if (NSUB > 1) {
                         const uint32_t k = keys[j + 32 * u];
                         if (k >= L) idx[u] = RVB_NO_IMPULSE;   // skipped impulses share the last segment
@@ -335,7 +408,7 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
     for (uint32_t w = blockIdx.x; w < nseg; w += gridDim.x) {
         const uint32_t seg = nseg - 1 - w;   // from the end of the response (ascending order measured the same)
         const uint32_t b0 = seg_begin[seg], b1 = seg_end[seg];
-        if (b0 == b1) continue;   // block-uniform
+        if (b0 >= b1) continue;   // block-uniform (empty: begin 0xffffffff, end 0)
         const uint32_t chunk = (b1 - b0 + RVB_REDUCE_WARPS - 1) / RVB_REDUCE_WARPS;
         const uint32_t m0 = min(b1, b0 + wid * chunk), m1 = min(b1, m0 + chunk);
         float acc[NSUB][MAXC][RVB_NBANDS];
@@ -353,9 +426,8 @@ __global__ void __launch_bounds__(32 * RVB_REDUCE_WARPS) reduce_cta_kernel(const
                 idx[u] = RVB_NO_IMPULSE; sub[u] = 0;
                 if (j + 32 * u < m1) {
                     idx[u] = vals[j + 32 * u];
-                    if (keys == nullptr) {                     // compact format: sub-bin in the value's top bits
-                        sub[u] = (idx[u] >> 30) & (NSUB - 1);
-                        idx[u] &= RVB_ID_MASK;
+                    if (keys == nullptr) {                     // sub-bin in the value's top bits (ids < 2^30 whenever NSUB > 1)
+                        if (NSUB > 1) { sub[u] = (idx[u] >> 30) & (NSUB - 1); idx[u] &= RVB_ID_MASK; }
                     } else if (NSUB > 1) {
                         const uint32_t k = keys[j + 32 * u];
                         if (k >= L) idx[u] = RVB_NO_IMPULSE;   // skipped impulses share the last segment
@@ -816,6 +888,42 @@ static int times_for_spec(const Source &S_all, const ChanSpec &C, float &mn, flo
     return RVB_OK;
 }
 
+// The flatten's sort (see FlattenIn): on return d_vals[*cur] holds the impulse ids of the valid impulses grouped
+// by segment, segment g occupying [d_begin[g], d_end[g]) (begin >= end: empty).
+#ifndef RVB_SORT_THREADS
+#define RVB_SORT_THREADS 256
+#endif
+template <class KeyT>
+static int flatten_sort_keyed(const Source &S, const ChanSpec &C, float predelay, bool fix, float sr, uint32_t L, uint32_t shift,
+                              const rsort::PassPlan &pl, uint32_t n, uint32_t *const d_vals[2], uint32_t *d_begin, uint32_t *d_end, int *cur,
+                              cudaStream_t st)
+{
+    KeyT *d_keys[2] = {nullptr, nullptr};
+    uint32_t *d_stored = nullptr;
+    if (pl.npasses >= 2) RVB_TRY(dev_alloc(&d_keys[0], (size_t)n));
+    if (pl.npasses >= 3) RVB_TRY(dev_alloc(&d_keys[1], (size_t)n));
+    float *d_img_tkey = nullptr;
+    if (S.n_images) {
+        RVB_TRY(dev_alloc(&d_img_tkey, (size_t)S.n_images));
+        note_launch(), image_tkeys_kernel<<<(S.n_images + 255) / 256, 256, 0, st>>>(S.ivolA, S.ivolB, S.ipt, S.n_images, d_img_tkey);
+    }
+    int rc;
+    if (C.model == 1) {
+        // HRTF: the time depends on the impulse position; evaluate it once (histogram sweep) and keep the sample indices
+        RVB_TRY(dev_alloc(&d_stored, (size_t)n));
+        FlattenIn<KeyT, FLATTEN_TIME_POS> hin{S.tkey, d_img_tkey, S.pt, S.ipt, nullptr, S.n_diffuse, C.mic, C.ear, predelay, sr, L, shift, fix};
+        FlattenIn<KeyT, FLATTEN_STORED> first{nullptr, nullptr, nullptr, nullptr, d_stored, S.n_diffuse, C.mic, C.ear, predelay, sr, L, shift, fix};
+        rc = rsort::sort_pairs<RVB_SORT_THREADS, KeyT>(hin, StoreSampleIndex{d_stored, shift}, first, n, pl, d_keys, d_vals, true, d_begin, d_end, cur,
+                                                       nullptr, st);
+    } else {
+        FlattenIn<KeyT, FLATTEN_TIME> in{S.tkey, d_img_tkey, nullptr, nullptr, nullptr, S.n_diffuse, C.mic, C.ear, predelay, sr, L, shift, fix};
+        rc = rsort::sort_pairs<RVB_SORT_THREADS, KeyT>(in, rsort::NoSink{}, in, n, pl, d_keys, d_vals, true, d_begin, d_end, cur, nullptr, st);
+    }
+    dev_free(d_img_tkey);
+    dev_free(d_keys[0]); dev_free(d_keys[1]); dev_free(d_stored);
+    return rc;
+}
+
 // sort + segmented reduce of one key group into hist rows
 static int histogram_passes(const Source &S, const ChannelSetup &cs, float predelay, bool fix, float sr, const size_t *lengths,
                             float *d_hist)
@@ -828,7 +936,11 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
     if (n == 0) return RVB_OK;
     uint32_t *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr}, *d_begin = nullptr, *d_end = nullptr;
     uint8_t *d_tmp = nullptr;
-    for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_keys[i], n)); RVB_TRY(dev_alloc(&d_vals[i], n)); }
+    static const bool use_cub = getenv("RVB_FLATTEN_SORT") && !strcmp(getenv("RVB_FLATTEN_SORT"), "cub");
+    for (int i = 0; i < 2; ++i) {
+        if (use_cub) RVB_TRY(dev_alloc(&d_keys[i], n));
+        RVB_TRY(dev_alloc(&d_vals[i], n));
+    }
     int last_group = -1;
     uint32_t L = 0, nseg = 0;
     int cur = 0, shift = 0;
@@ -839,6 +951,39 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
         if (cs.model == RVB_MODEL_SPEAKER) {
             for (int c = 1; c < C.nch; ++c)
                 if (lengths[c0 + c] != lengths[c0]) return fail(RVB_ERR_INVALID, "speaker channels must share one length");
+        }
+        if (cs.pass_key_group[p] != last_group && !use_cub) {
+            last_group = cs.pass_key_group[p];
+            L = (uint32_t)lengths[c0];
+            // A segment of the sorted stream holds 2^shift adjacent bins (the reduction has 32 accumulators per lane:
+            // sub-bins x channels x bands), which shortens the keys: take the shift that needs the fewest radix passes,
+            // then the narrowest digits.  The sub-bin rides in bits 30-31 of the value, so ids must stay below 2^30.
+            static const int shift_env = getenv("RVB_FLATTEN_SHIFT") ? atoi(getenv("RVB_FLATTEN_SHIFT")) : -1;
+            int max_shift = C.nch == 1 ? 2 : (C.nch == 2 ? 1 : 0);
+            if (n >= (1u << 30)) max_shift = 0;
+            rsort::PassPlan pl;
+            int key_bits = 0;
+            shift = -1;
+            for (int sft = 0; sft <= max_shift; ++sft) {
+                if (shift_env >= 0 && sft != std::min(shift_env, max_shift)) continue;
+                const uint32_t ns = ((L - 1) >> sft) + 1;
+                int bits = 1;
+                while ((1ull << bits) < (unsigned long long)ns) ++bits;   // segment ids in [0, ns)
+                const rsort::PassPlan cand = rsort::plan_passes(0, bits);
+                if (shift < 0 || cand.npasses < pl.npasses || (cand.npasses == pl.npasses && cand.bits < pl.bits)) {
+                    shift = sft; pl = cand; key_bits = bits;
+                }
+            }
+            nseg = ((L - 1) >> shift) + 1;
+            compact = true;   // (value format: sub-bin in the top bits, no key array for the reduction)
+            dev_free(d_begin); dev_free(d_end);
+            RVB_TRY(dev_alloc(&d_begin, (size_t)nseg)); RVB_TRY(dev_alloc(&d_end, (size_t)nseg));
+            Timer ts(st);
+            RVB_CUDA(cudaMemsetAsync(d_begin, 0xff, (size_t)nseg * sizeof(uint32_t), st));
+            RVB_CUDA(cudaMemsetAsync(d_end, 0, (size_t)nseg * sizeof(uint32_t), st));
+            if (key_bits <= 16 && pl.bits == 8) RVB_TRY(flatten_sort_keyed<uint16_t>(S, C, predelay, fix, sr, L, (uint32_t)shift, pl, n, d_vals, d_begin, d_end, &cur, st));
+            else RVB_TRY(flatten_sort_keyed<uint32_t>(S, C, predelay, fix, sr, L, (uint32_t)shift, pl, n, d_vals, d_begin, d_end, &cur, st));
+            ts.stop_into(&g_stats.sort_ms);
         }
         if (cs.pass_key_group[p] != last_group) {
             last_group = cs.pass_key_group[p];

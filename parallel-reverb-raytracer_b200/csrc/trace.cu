@@ -1181,6 +1181,7 @@ static int launch_wavefront(const TraceParams &P_in, const TraceJob &J0, size_t 
     static const int minb_env = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 0;
     static const int service = getenv("RVB_WF_SERVICE") ? atoi(getenv("RVB_WF_SERVICE")) : 24;
     static const int leaf_min = getenv("RVB_WF_LEAF_MIN") ? atoi(getenv("RVB_WF_LEAF_MIN")) : 8;
+    static const int grid_env = getenv("RVB_WF_GRID") ? atoi(getenv("RVB_WF_GRID")) : 0;
     TraceParams P = P_in;
     P.wf_service = (uint32_t)std::max(1, std::min(32, service));
     P.wf_leaf_min = (uint32_t)std::max(1, std::min(32, leaf_min));
@@ -1194,7 +1195,8 @@ static int launch_wavefront(const TraceParams &P_in, const TraceJob &J0, size_t 
         RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_bytes));
         RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, stack_bytes));
         const size_t want = ((size_t)P.nrays * P.njobs + 127) / 128;
-        const unsigned grid = (unsigned)std::max<size_t>(1, std::min(want, (size_t)std::max(per_sm, 1) * sm_count()));
+        unsigned grid = (unsigned)std::max<size_t>(1, std::min(want, (size_t)std::max(per_sm, 1) * sm_count()));
+        if (grid_env > 0) grid = (unsigned)std::min<size_t>(want, (size_t)grid_env);
         note_launch(), kernel<<<grid, 128, stack_bytes, st>>>(P, J0, d_fetch);
         RVB_CUDA(cudaGetLastError());
         return RVB_OK;

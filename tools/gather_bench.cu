@@ -32,6 +32,15 @@ __global__ void k(const float4 *a, unsigned long long nsec, int per_thread, floa
 int main(int argc, char **argv)
 {
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
+    // optional second argument: cudaLimitMaxL2FetchGranularity (32, 64 or 128 bytes; a hint)
+    size_t gran = 0;
+    cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity);
+    printf("default L2 fetch granularity limit: %zu\n", gran);
+    if (argc > 2) {
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(argv[2]));
+        cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity);
+        printf("set to %s -> %s, now %zu\n", argv[2], cudaGetErrorString(e), gran);
+    }
     const unsigned long long bytes = 4ull << 30, nsec = bytes / 32;
     float4 *a; float *out;
     cudaMalloc(&a, bytes); cudaMemset(a, 0, bytes);
