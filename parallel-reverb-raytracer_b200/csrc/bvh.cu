@@ -12,7 +12,7 @@
 // off by a few 1e-7 * |origin - v0| / sin(grazing angle); a padding proportional to the scene
 // diagonal, which the slab test sees magnified by the same 1/sin factor, keeps every triangle the
 // exact test could accept inside its box.
-#include <cub/cub.cuh>
+#include "rvb_sort.cuh"
 
 #include "rvb_internal.cuh"
 #include "rvb_scan.cuh"
@@ -297,15 +297,12 @@ int scene_build_bvh(Scene *sc)
     float3 inv = make_float3(ext.x > 0 ? 1.0f / ext.x : 0.f, ext.y > 0 ? 1.0f / ext.y : 0.f, ext.z > 0 ? 1.0f / ext.z : 0.f);
     const float diag = std::sqrt(ext.x * ext.x + ext.y * ext.y + ext.z * ext.z);
     const float pad = 2e-5f * diag + 1e-6f;
-    note_launch(), morton_kernel<<<grd, blk, 0, st>>>(d_centroids, T, lo, inv, d_codes[0], d_ids[0]);
-    cub::DoubleBuffer<unsigned long long> kb(d_codes[0], d_codes[1]);
-    cub::DoubleBuffer<uint32_t> vb(d_ids[0], d_ids[1]);
-    size_t bytes = 0;
-    RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)T, 0, 63, st));
-    RVB_TRY(dev_alloc(&d_tmp, bytes));
-    RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)T, 0, 63, st));
-    const unsigned long long *codes = kb.Current();
-    const uint32_t *ids = vb.Current();
+    note_launch(), morton_kernel<<<grd, blk, 0, st>>>(d_centroids, T, lo, inv, d_codes[1], d_ids[1]);
+    int sorted = 1;
+    const int rc_sort = rsort::sort_arrays<unsigned long long>(d_codes, d_ids, T, 0, 63, &sorted, st);   // input in buffer pair 1
+    RVB_TRY(rc_sort);
+    const unsigned long long *codes = d_codes[sorted];
+    const uint32_t *ids = d_ids[sorted];
     note_launch(), hierarchy_kernel<<<grd, blk, 0, st>>>(codes, (int)T, d_children, d_ranges, d_parent_inner, d_parent_leaf);
     RVB_CUDA(cudaMemsetAsync(d_visits, 0, T * sizeof(int), st));
     note_launch(), refit_kernel<<<grd, blk, 0, st>>>(d_tri_boxes, ids, (int)T, d_children, d_parent_inner, d_parent_leaf, d_node_boxes, d_visits);

@@ -9,9 +9,10 @@
 // Here: stable-compact the candidate slots (ray-major), then LSD radix sort on the key columns
 // (column value = entry + 1, 0 = "past the end", so prefixes sort first); stability keeps the
 // lowest ray first within equal keys; then keep the head of every run of equal keys.
-#include <cub/cub.cuh>
-
+// The compactions (rvb_scan.cuh) and the radix sort (rvb_sort.cuh) are the library's own.
 #include "rvb_internal.cuh"
+#include "rvb_scan.cuh"
+#include "rvb_sort.cuh"
 
 namespace rvb {
 
@@ -61,6 +62,11 @@ __global__ void head_flags_packed_kernel(const unsigned long long *keys, uint32_
     if (p < n) head[p] = (p == 0 || keys[p] != keys[p - 1]) ? 1 : 0;
 }
 
+struct HeadSet {
+    const uint8_t *head;
+    __device__ bool operator()(uint32_t p) const { return head[p] != 0; }
+};
+
 __global__ void iota_kernel(uint32_t *a, uint32_t n)
 {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,15 +111,9 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     RVB_TRY(dev_alloc(&d_sel, nflat));
     RVB_TRY(dev_alloc(&d_nsel, 1));
     CandValid pred{cidx, tr->ray_offset};
-    cub::CountingInputIterator<uint32_t> it(0);
-    size_t tmp_bytes = 0;
-    RVB_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, it, d_sel, d_nsel, (int)nflat, pred, st));
-    uint8_t *d_tmp = nullptr;
-    RVB_TRY(dev_alloc(&d_tmp, tmp_bytes));
-    RVB_CUDA(cub::DeviceSelect::If(d_tmp, tmp_bytes, it, d_sel, d_nsel, (int)nflat, pred, st));
+    RVB_TRY(compact_indices(pred, nflat, d_sel, d_nsel, st));
     uint32_t n = 0;
     RVB_TRY(read_back(&n, d_nsel, sizeof n));
-    dev_free(d_tmp);
     if (n == 0) { dev_free(d_sel); dev_free(d_nsel); return RVB_OK; }
 
     uint32_t *d_perm[2] = {nullptr, nullptr}, *d_keys[2] = {nullptr, nullptr};
@@ -130,42 +130,27 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
         // (stable, so the lowest ray still comes first within equal keys)
         unsigned long long *d_k64[2] = {nullptr, nullptr};
         for (int i = 0; i < 2; ++i) RVB_TRY(dev_alloc(&d_k64[i], n));
-        note_launch(), packed_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, n, last_col, (uint32_t)end_bit, d_k64[0], d_perm[0]);
-        cub::DoubleBuffer<unsigned long long> kb(d_k64[0], d_k64[1]);
-        cub::DoubleBuffer<uint32_t> vb(d_perm[0], d_perm[1]);
-        size_t sort_bytes = 0;
-        RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb, vb, (int)n, 0, end_bit * (int)last_col, st));
-        uint8_t *d_sort_tmp = nullptr;
-        RVB_TRY(dev_alloc(&d_sort_tmp, sort_bytes));
-        RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_bytes, kb, vb, (int)n, 0, end_bit * (int)last_col, st));
-        cur = vb.selector;
-        note_launch(), head_flags_packed_kernel<<<grd, blk, 0, st>>>(kb.Current(), n, d_head);
-        dev_free(d_sort_tmp);
+        note_launch(), packed_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, n, last_col, (uint32_t)end_bit, d_k64[1], d_perm[1]);
+        const int rc_sort = rsort::sort_arrays<unsigned long long>(d_k64, d_perm, n, 0, end_bit * (int)last_col, &cur, st);
+        RVB_TRY(rc_sort);
+        note_launch(), head_flags_packed_kernel<<<grd, blk, 0, st>>>(d_k64[cur], n, d_head);
         for (int i = 0; i < 2; ++i) dev_free(d_k64[i]);
     } else {
-        note_launch(), iota_kernel<<<grd, blk, 0, st>>>(d_perm[0], n);
-        size_t sort_bytes = 0;
-        RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, d_keys[0], d_keys[1], d_perm[0], d_perm[1], (int)n, 0, end_bit, st));
-        uint8_t *d_sort_tmp = nullptr;
-        RVB_TRY(dev_alloc(&d_sort_tmp, sort_bytes));
+        cur = 1;
+        note_launch(), iota_kernel<<<grd, blk, 0, st>>>(d_perm[cur], n);
         for (uint32_t j = last_col; j >= 1; --j) {   // LSD over key columns; column 0 is constant
-            note_launch(), col_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, j, d_keys[0]);
-            RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_bytes, d_keys[0], d_keys[1], d_perm[cur], d_perm[cur ^ 1],
-                                                     (int)n, 0, end_bit, st));
-            cur ^= 1;
+            // input in buffer pair 1 (sort_arrays), so move the current permutation there first if needed
+            if (cur != 1) { std::swap(d_perm[0], d_perm[1]); cur = 1; }
+            note_launch(), col_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[1], n, j, d_keys[1]);
+            const int rc_sort = rsort::sort_arrays<uint32_t>(d_keys, d_perm, n, 0, end_bit, &cur, st);
+            RVB_TRY(rc_sort);
         }
-        dev_free(d_sort_tmp);
         note_launch(), head_flags_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, d_perm[cur], n, d_head);
     }
     uint32_t *d_upos = d_keys[0], *d_m = d_nsel;
-    size_t fl_bytes = 0;
-    RVB_CUDA(cub::DeviceSelect::Flagged(nullptr, fl_bytes, it, d_head, d_upos, d_m, (int)n, st));
-    uint8_t *d_fl_tmp = nullptr;
-    RVB_TRY(dev_alloc(&d_fl_tmp, fl_bytes));
-    RVB_CUDA(cub::DeviceSelect::Flagged(d_fl_tmp, fl_bytes, it, d_head, d_upos, d_m, (int)n, st));
+    RVB_TRY(compact_indices(HeadSet{d_head}, n, d_upos, d_m, st));
     uint32_t m = 0;
     RVB_TRY(read_back(&m, d_m, sizeof m));
-    dev_free(d_fl_tmp);
 
     RVB_TRY(dev_alloc(&tr->d_img_volA, m));
     RVB_TRY(dev_alloc(&tr->d_img_volB, m));

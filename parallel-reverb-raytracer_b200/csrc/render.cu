@@ -11,8 +11,6 @@
 // sort-by-sample-index (LSD radix sort of (bin, impulse id) pairs, stable => fixed order inside
 // a bin) followed by a segmented reduction with a fixed lane assignment and a fixed shuffle
 // tree: no float atomics, bit-identical from run to run.
-#include <cub/cub.cuh>
-
 #include <cmath>
 #include <type_traits>
 
@@ -110,90 +108,7 @@ __device__ __forceinline__ uint32_t sample_index(float t, float predelay, bool f
     return (uint32_t)r;
 }
 
-// Two key formats.  Wide (uint32): key = sample index (sentinel L), value = impulse id; the sort skips
-// the low `shift` bits.  Compact (uint16, when there are fewer than 65535 segments and fewer than 2^30
-// impulses): key = segment id = sample index >> shift (sentinel nseg), value = impulse id with the
-// dropped low bits (the sub-bin inside the segment) in bits 30-31 -- a quarter less sort traffic, and
-// the reduction reads 4 bytes per entry instead of 8.
 #define RVB_ID_MASK 0x3fffffffu
-template <bool COMPACT>
-__device__ __forceinline__ void make_key(bool valid, float t, float predelay, bool fix, float sr, uint32_t L, uint32_t shift,
-                                         uint32_t nseg, uint32_t i, uint32_t &k, uint32_t &v)
-{
-    k = COMPACT ? nseg : L;   // sentinel: sorts behind every real bin
-    v = i;
-    if (valid) {
-        const uint32_t s = sample_index(t, predelay, fix, sr);
-        if (s < L) {
-            if (COMPACT) { k = s >> shift; v = i | ((s & ((1u << shift) - 1u)) << 30); }
-            else k = s;
-        }
-    }
-}
-
-template <bool COMPACT>
-__global__ void keys_kernel(const Source S, const ChanSpec C, float predelay, bool fix, float sr, uint32_t L, uint32_t shift,
-                            uint32_t nseg, void *keys_out, uint32_t *vals)
-{
-    using KeyT = typename std::conditional<COMPACT, uint16_t, uint32_t>::type;
-    KeyT *keys = static_cast<KeyT *>(keys_out);
-    const uint32_t n = S.size();
-    // Diffuse slots of the speaker / pass-through models need the 4-byte time only: four slots per
-    // thread, 16-byte loads and stores (the slot count is a multiple of four, rvb_internal.cuh).
-    uint32_t first_scalar = 0;
-    if (C.model != 1 && (S.n_diffuse & 3u) == 0) {
-        first_scalar = S.n_diffuse;
-        const uint32_t nq = S.n_diffuse >> 2;
-        const float4 *t4 = reinterpret_cast<const float4 *>(S.tkey);
-        uint4 *v4 = reinterpret_cast<uint4 *>(vals);
-        for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
-            const float4 t = t4[q];
-            const float tt[4] = {t.x, t.y, t.z, t.w};
-            uint32_t k[4], v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) make_key<COMPACT>(tt[u] >= 0.0f, tt[u], predelay, fix, sr, L, shift, nseg, 4 * q + u, k[u], v[u]);
-            if (COMPACT) reinterpret_cast<ushort4 *>(keys)[q] = make_ushort4((unsigned short)k[0], (unsigned short)k[1], (unsigned short)k[2], (unsigned short)k[3]);
-            else reinterpret_cast<uint4 *>(keys)[q] = make_uint4(k[0], k[1], k[2], k[3]);
-            v4[q] = make_uint4(v[0], v[1], v[2], v[3]);
-        }
-    }
-    for (uint32_t i = first_scalar + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float t = 0.0f;
-        const bool valid = attenuated_time(S, C, i, t);
-        uint32_t k, v;
-        make_key<COMPACT>(valid, t, predelay, fix, sr, L, shift, nseg, i, k, v);
-        keys[i] = (KeyT)k;
-        vals[i] = v;
-    }
-}
-
-// The sort may ignore the low `shift` bits of the sample index (one radix pass fewer): a segment
-// then holds 2^shift adjacent bins, interleaved in impulse order, and the reduction separates them
-// by the key's low bits.  Segment bounds in the sorted key array (four keys per thread, 16-byte loads):
-template <class KeyT>
-__global__ void bounds_kernel(const KeyT *keys, uint32_t n, uint32_t nseg, uint32_t shift, uint32_t *seg_begin, uint32_t *seg_end)
-{
-    const uint32_t nq = (n + 3) >> 2;
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
-        const uint32_t i0 = 4 * q;
-        uint32_t k[6];   // keys i0-1 .. i0+4
-        if (i0 + 4 <= n) {
-            if (sizeof(KeyT) == 4) { const uint4 v = reinterpret_cast<const uint4 *>(keys)[q]; k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w; }
-            else { const ushort4 v = reinterpret_cast<const ushort4 *>(keys)[q]; k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w; }
-        } else for (int u = 0; u < 4; ++u) k[1 + u] = i0 + u < n ? (uint32_t)keys[i0 + u] : 0u;
-        k[0] = i0 ? (uint32_t)keys[i0 - 1] : 0u;
-        k[5] = i0 + 4 < n ? (uint32_t)keys[i0 + 4] : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t i = i0 + u;
-            if (i >= n) break;
-            const uint32_t sg = k[1 + u] >> shift;
-            if (sg >= nseg) continue;   // sentinel-only tail
-            if (i == 0 || (k[u] >> shift) != sg) seg_begin[sg] = i;
-            if (i + 1 == n || (k[2 + u] >> shift) != sg) seg_end[sg] = i + 1;
-        }
-    }
-}
 
 // ---- the flatten's own sort (rvb_sort.cuh) ----------------------------------------------------------
 // Key = segment id (sample index >> shift), value = impulse id with the sub-bin inside the segment in
@@ -934,17 +849,11 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
     for (size_t c = 0; c < cs.nch; ++c) chan_off[c + 1] = chan_off[c] + RVB_NBANDS * lengths[c];
     RVB_CUDA(cudaMemsetAsync(d_hist, 0, chan_off[cs.nch] * sizeof(float), st));
     if (n == 0) return RVB_OK;
-    uint32_t *d_keys[2] = {nullptr, nullptr}, *d_vals[2] = {nullptr, nullptr}, *d_begin = nullptr, *d_end = nullptr;
-    uint8_t *d_tmp = nullptr;
-    static const bool use_cub = getenv("RVB_FLATTEN_SORT") && !strcmp(getenv("RVB_FLATTEN_SORT"), "cub");
-    for (int i = 0; i < 2; ++i) {
-        if (use_cub) RVB_TRY(dev_alloc(&d_keys[i], n));
-        RVB_TRY(dev_alloc(&d_vals[i], n));
-    }
+    uint32_t *d_vals[2] = {nullptr, nullptr}, *d_begin = nullptr, *d_end = nullptr;
+    for (int i = 0; i < 2; ++i) RVB_TRY(dev_alloc(&d_vals[i], n));
     int last_group = -1;
     uint32_t L = 0, nseg = 0;
     int cur = 0, shift = 0;
-    bool compact = false;
     for (size_t p = 0; p < cs.passes.size(); ++p) {
         const ChanSpec &C = cs.passes[p];
         const size_t c0 = cs.pass_first_channel[p];
@@ -952,7 +861,7 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             for (int c = 1; c < C.nch; ++c)
                 if (lengths[c0 + c] != lengths[c0]) return fail(RVB_ERR_INVALID, "speaker channels must share one length");
         }
-        if (cs.pass_key_group[p] != last_group && !use_cub) {
+        if (cs.pass_key_group[p] != last_group) {
             last_group = cs.pass_key_group[p];
             L = (uint32_t)lengths[c0];
             // A segment of the sorted stream holds 2^shift adjacent bins (the reduction has 32 accumulators per lane:
@@ -975,7 +884,6 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
                 }
             }
             nseg = ((L - 1) >> shift) + 1;
-            compact = true;   // (value format: sub-bin in the top bits, no key array for the reduction)
             dev_free(d_begin); dev_free(d_end);
             RVB_TRY(dev_alloc(&d_begin, (size_t)nseg)); RVB_TRY(dev_alloc(&d_end, (size_t)nseg));
             Timer ts(st);
@@ -983,55 +891,6 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             RVB_CUDA(cudaMemsetAsync(d_end, 0, (size_t)nseg * sizeof(uint32_t), st));
             if (key_bits <= 16 && pl.bits == 8) RVB_TRY(flatten_sort_keyed<uint16_t>(S, C, predelay, fix, sr, L, (uint32_t)shift, pl, n, d_vals, d_begin, d_end, &cur, st));
             else RVB_TRY(flatten_sort_keyed<uint32_t>(S, C, predelay, fix, sr, L, (uint32_t)shift, pl, n, d_vals, d_begin, d_end, &cur, st));
-            ts.stop_into(&g_stats.sort_ms);
-        }
-        if (cs.pass_key_group[p] != last_group) {
-            last_group = cs.pass_key_group[p];
-            L = (uint32_t)lengths[c0];
-            int end_bit = 1;
-            while ((1ull << end_bit) <= (unsigned long long)L) ++end_bit;   // keys in [0, L]
-            // drop low key bits from the sort when that saves an 8-bit radix pass (see bounds_kernel)
-            const int max_shift = C.nch == 1 ? 2 : (C.nch == 2 ? 1 : 0);
-            shift = 0;
-            for (int sft = 1; sft <= max_shift; ++sft)
-                if ((end_bit - sft + 7) / 8 < (end_bit + 7) / 8) { shift = sft; break; }
-            nseg = ((L - 1) >> shift) + 1;
-            // compact format (see make_key): 16-bit segment ids, sub-bin in the value's top bits
-            static const bool allow_compact = !(getenv("RVB_WIDE_KEYS") && atoi(getenv("RVB_WIDE_KEYS")) != 0);
-            compact = allow_compact && nseg < 65535u && n < (1u << 30);
-            Timer tk(st);
-            note_launch();
-            if (compact) keys_kernel<true><<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, (uint32_t)shift, nseg, d_keys[0], d_vals[0]);
-            else keys_kernel<false><<<grid_for(n), 256, 0, st>>>(S, C, predelay, fix, sr, L, (uint32_t)shift, nseg, d_keys[0], d_vals[0]);
-            tk.stop_into(&g_stats.keys_ms);
-            Timer ts(st);
-            cub::DoubleBuffer<uint32_t> vb(d_vals[0], d_vals[1]);
-            size_t bytes = 0;
-            if (compact) {
-                int seg_bits = 1;
-                while ((1u << seg_bits) <= nseg) ++seg_bits;   // segment ids in [0, nseg]
-                cub::DoubleBuffer<uint16_t> kb(reinterpret_cast<uint16_t *>(d_keys[0]), reinterpret_cast<uint16_t *>(d_keys[1]));
-                RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, 0, seg_bits, st));
-                dev_free(d_tmp);
-                RVB_TRY(dev_alloc(&d_tmp, bytes));
-                RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, 0, seg_bits, st));
-                cur = kb.selector;
-            } else {
-                cub::DoubleBuffer<uint32_t> kb(d_keys[0], d_keys[1]);
-                RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, shift, end_bit, st));
-                dev_free(d_tmp);
-                RVB_TRY(dev_alloc(&d_tmp, bytes));
-                RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kb, vb, (int)n, shift, end_bit, st));
-                cur = kb.selector;
-            }
-            if (vb.selector != cur) return fail(RVB_ERR_CUDA, "radix sort buffers diverged");
-            dev_free(d_begin); dev_free(d_end);
-            RVB_TRY(dev_alloc(&d_begin, (size_t)nseg)); RVB_TRY(dev_alloc(&d_end, (size_t)nseg));
-            RVB_CUDA(cudaMemsetAsync(d_begin, 0, (size_t)nseg * sizeof(uint32_t), st));
-            RVB_CUDA(cudaMemsetAsync(d_end, 0, (size_t)nseg * sizeof(uint32_t), st));
-            note_launch();
-            if (compact) bounds_kernel<uint16_t><<<grid_for(n), 256, 0, st>>>(reinterpret_cast<const uint16_t *>(d_keys[cur]), n, nseg, 0u, d_begin, d_end);
-            else bounds_kernel<uint32_t><<<grid_for(n), 256, 0, st>>>(d_keys[cur], n, nseg, (uint32_t)shift, d_begin, d_end);
             ts.stop_into(&g_stats.sort_ms);
         }
         Timer tr_(st);
@@ -1043,7 +902,7 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
             for (int c = 0; c < C.nch; ++c) need_pos |= (C.coef[c] != 0.0f);
             note_launch();
             const int nsub = 1 << shift;
-            const uint32_t *rkeys = compact ? nullptr : d_keys[cur];   // compact: the values carry the sub-bin
+            const uint32_t *rkeys = nullptr;   // the values carry the sub-bin (FlattenIn); the sort keeps no key array
             static const int force = getenv("RVB_REDUCE_DENSE") ? atoi(getenv("RVB_REDUCE_DENSE")) : -1;
             const bool dense = force >= 0 ? force != 0 : (size_t)n >= (size_t)256 * nseg;
             if (C.model == 0 && need_pos) launch_reduce<0, true>(nsub, rgrid, dense, st, S, C, rkeys, d_vals[cur], d_begin, d_end, nseg, L, dst, stride);
@@ -1054,8 +913,8 @@ static int histogram_passes(const Source &S, const ChannelSetup &cs, float prede
         RVB_CUDA(cudaGetLastError());
         tr_.stop_into(&g_stats.reduce_ms);
     }
-    for (int i = 0; i < 2; ++i) { dev_free(d_keys[i]); dev_free(d_vals[i]); }
-    dev_free(d_begin); dev_free(d_end); dev_free(d_tmp);
+    for (int i = 0; i < 2; ++i) dev_free(d_vals[i]);
+    dev_free(d_begin); dev_free(d_end);
     return RVB_OK;
 }
 

@@ -99,4 +99,33 @@ static inline int exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, size
     return RVB_OK;
 }
 
+// Stable stream compaction of indices: d_out[k] = the k-th i in [0, n) with pred(i), *d_count = how many.
+template <class Pred>
+static __global__ void compact_flag_kernel(const Pred pred, uint32_t n, uint32_t *flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = pred(i) ? 1u : 0u;
+}
+static __global__ void compact_scatter_kernel(const uint32_t *flags, const uint32_t *pos, uint32_t n, uint32_t *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) out[pos[i]] = i;
+}
+template <class Pred>
+static inline int compact_indices(const Pred &pred, uint32_t n, uint32_t *d_out, uint32_t *d_count, cudaStream_t st)
+{
+    if (n == 0) return exclusive_scan_u32(nullptr, nullptr, 0, nullptr, d_count, st);
+    uint32_t *d_flags = nullptr, *d_pos = nullptr, *d_sums = nullptr;
+    RVB_TRY(dev_alloc(&d_flags, (size_t)n)); RVB_TRY(dev_alloc(&d_pos, (size_t)n)); RVB_TRY(dev_alloc(&d_sums, scan_blocks(n)));
+    const unsigned grd = (n + 255u) / 256u;
+    note_launch(), compact_flag_kernel<<<grd, 256, 0, st>>>(pred, n, d_flags);
+    int rc = exclusive_scan_u32(d_flags, d_pos, n, d_sums, d_count, st);
+    if (rc == RVB_OK) {
+        note_launch(), compact_scatter_kernel<<<grd, 256, 0, st>>>(d_flags, d_pos, n, d_out);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(RVB_ERR_CUDA, "compaction launch failed");
+    }
+    dev_free(d_flags); dev_free(d_pos); dev_free(d_sums);
+    return rc;
+}
+
 }  // namespace rvb

@@ -536,5 +536,20 @@ static inline int sort_pairs(const HIn &hist_in, const Sink &sink, const FIn &fi
     return fail(RVB_ERR_INVALID, "radix sort: unsupported digit width");
 }
 
+// Plain sort of stored pairs by the key bits [begin_bit, begin_bit + nbits).  keys[1] / vals[1] hold the input
+// (vals[1] == nullptr: the values are the indices 0..n-1) and are overwritten; *result says which pair of buffers
+// holds the sorted output.
+template <class KeyT>
+static inline int sort_arrays(KeyT *const keys[2], uint32_t *const vals[2], uint32_t n, int begin_bit, int nbits, int *result, cudaStream_t st)
+{
+    constexpr int THREADS = sizeof(KeyT) == 8 ? 128 : 256;   // 64-bit keys: smaller tiles (static shared memory)
+    *result = 1;
+    if (n == 0) return RVB_OK;
+    PassPlan pl = plan_passes(begin_bit, nbits);
+    if (sizeof(KeyT) == 2 && pl.bits != 8) { pl.bits = 8; pl.npasses = (nbits + 7) / 8; for (int p = 0; p < pl.npasses; ++p) pl.lo_bit[p] = (uint32_t)(begin_bit + 8 * p); }
+    ArrayIn<KeyT> in{keys[1], vals[1]};
+    return sort_pairs<THREADS, KeyT>(in, NoSink{}, in, n, pl, keys, vals, false, nullptr, nullptr, result, nullptr, st);
+}
+
 }  // namespace rsort
 }  // namespace rvb

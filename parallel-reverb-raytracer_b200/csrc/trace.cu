@@ -25,9 +25,9 @@
 #include <cstdlib>
 #include <cstring>
 
-#include <cub/cub.cuh>
 
 #include "rvb_internal.cuh"
+#include "rvb_sort.cuh"
 
 namespace rvb {
 
@@ -885,20 +885,24 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_kernel(const TraceParams 
 // decide the ORDER in which the image phase processes rays: neighbouring lanes then follow the same
 // first reflections, so their image-source validation loops have the same trip counts.  The results
 // do not depend on the order (every ray writes its own slots).
-__global__ void direction_keys_kernel(const float4 *dirs, uint32_t n, uint32_t *keys, uint32_t *ids)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 d = dirs[i];
-    const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-    const float inv = len > 0.f ? 1.0f / len : 0.f;
-    const float z = fminf(fmaxf(d.z * inv * 0.5f + 0.5f, 0.f), 0.999999f);
-    const float az = fminf(fmaxf(atan2f(d.y, d.x) * 0.15915494f + 0.5f, 0.f), 0.999999f);
-    const uint32_t iz = (uint32_t)(z * 256.f), ia = (uint32_t)(az * 256.f);
-    // boustrophedon over the azimuth so that consecutive cells stay adjacent
-    keys[i] = iz * 256u + ((iz & 1u) ? 255u - ia : ia);
-    ids[i] = i;
-}
+// (first-pass functor of the library's radix sort, rvb_sort.cuh: the 16-bit cell keys are never stored)
+struct DirectionCellIn {
+    const float4 *dirs;
+    typedef float4 Raw;
+    __device__ __forceinline__ Raw fetch(uint32_t i) const { return dirs[i]; }
+    __device__ __forceinline__ bool decode(uint32_t i, const Raw &d, uint16_t &k, uint32_t &v) const
+    {
+        const float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        const float inv = len > 0.f ? 1.0f / len : 0.f;
+        const float z = fminf(fmaxf(d.z * inv * 0.5f + 0.5f, 0.f), 0.999999f);
+        const float az = fminf(fmaxf(atan2f(d.y, d.x) * 0.15915494f + 0.5f, 0.f), 0.999999f);
+        const uint32_t iz = (uint32_t)(z * 256.f), ia = (uint32_t)(az * 256.f);
+        // boustrophedon over the azimuth so that consecutive cells stay adjacent
+        k = (uint16_t)(iz * 256u + ((iz & 1u) ? 255u - ia : ia));
+        v = i;
+        return true;
+    }
+};
 
 template <class K>
 static int occupancy_of(K kernel, int block, size_t smem, int &per_sm)
@@ -1257,18 +1261,18 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : (size_t)sc->bvh_stack * RVB_BVH_CTA * sizeof(int);
 
     // processing order of the image phase: rays sorted by direction cell (the jobs share the directions)
-    uint32_t *d_perm_keys[2] = {nullptr, nullptr}, *d_perm_ids[2] = {nullptr, nullptr};
-    uint8_t *d_perm_tmp = nullptr;
+    uint16_t *d_perm_keys[2] = {nullptr, nullptr};
+    uint32_t *d_perm_ids[2] = {nullptr, nullptr};
     if (split > 0 && tr->nrays >= 4096) {
         const uint32_t n = (uint32_t)tr->nrays;
-        for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_perm_keys[i], n)); RVB_TRY(dev_alloc(&d_perm_ids[i], n)); }
-        note_launch(), direction_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_dirs, n, d_perm_keys[0], d_perm_ids[0]);
-        cub::DoubleBuffer<uint32_t> kb(d_perm_keys[0], d_perm_keys[1]), vb(d_perm_ids[0], d_perm_ids[1]);
-        size_t bytes = 0;
-        RVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kb, vb, (int)n, 0, 16, st));
-        RVB_TRY(dev_alloc(&d_perm_tmp, bytes));
-        RVB_CUDA(cub::DeviceRadixSort::SortPairs(d_perm_tmp, bytes, kb, vb, (int)n, 0, 16, st));
-        P.ray_perm = vb.Current();
+        RVB_TRY(dev_alloc(&d_perm_keys[0], n));
+        for (int i = 0; i < 2; ++i) RVB_TRY(dev_alloc(&d_perm_ids[i], n));
+        const DirectionCellIn in{d_dirs};
+        int cur = 0;
+        const int rc_sort = rsort::sort_pairs<256, uint16_t>(in, rsort::NoSink{}, in, n, rsort::plan_passes(0, 16), d_perm_keys, d_perm_ids, true, nullptr,
+                                                             nullptr, &cur, nullptr, st);
+        RVB_TRY(rc_sort);
+        P.ray_perm = d_perm_ids[cur];
     }
     cudaEvent_t e0, e1, em;
     RVB_CUDA(cudaEventCreate(&e0));
@@ -1343,7 +1347,6 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     dev_free(d_jobs);
     for (size_t j = 0; j < njobs; ++j) micmap_free(&mms[j]);
     for (int i = 0; i < 2; ++i) { dev_free(d_perm_keys[i]); dev_free(d_perm_ids[i]); }
-    dev_free(d_perm_tmp);
     for (size_t j = 0; j < njobs; ++j) {
         Trace *t = trs[j];
         const unsigned long long *h = h_end.data() + 6 * j, *hm = h_mid.data() + 6 * j;
