@@ -69,6 +69,12 @@ int rvb_set_stream(void *cuda_stream, int use);
 /* number of kernels this library has launched so far in the process (CUB's sort/select passes
  * are not counted) */
 unsigned long long rvb_launch_count(void);
+/* Device blocks of 1 MiB and more are kept in an exact-size cache when a trace / render frees them, so that
+ * the next trace of the same shape re-uses them (the reference re-creates its cl::Buffers for every group
+ * of rays, rayverb.cpp:560-583).  The cache holds at most RVB_CACHE_LIMIT_MB (environment, default 49152)
+ * of idle blocks per device; this call returns all idle blocks of the calling thread's device to the
+ * driver -- for a process that shares the GPU with another allocator. */
+int rvb_trim_cache(void);
 
 /* ---- scene: Raytracer::Raytracer (rayverb.h:142-148, rayverb.cpp:242-293) -------------------- */
 int rvb_scene_create(const rvb_triangle *triangles, size_t ntriangles,
@@ -83,6 +89,9 @@ int rvb_scene_accel(const rvb_scene *scene, int *accel);
 /* flags */
 #define RVB_TRACE_DEBUG 1u          /* also record per-bounce hit triangle + per-ray reflection count */
 #define RVB_TRACE_NO_IMAGES 2u      /* skip the image-source branch (kernel.cpp:379-457); images = {} */
+/* BVH scenes, testing: bits 8-15 = number of work units a ray's steady-phase reflections are cut into by the
+   wavefront bounce kernel (0: chosen from the ray count; 1: whole rays).  The results do not depend on it. */
+#define RVB_TRACE_UNITS(n) (((unsigned)(n) & 0xffu) << 8)
 /* `ray_offset` is the global index of directions[0] (used when rays are sharded over GPUs: only the
  * shard with ray_offset == 0 emits the direct path, and "lowest ray wins" stays well defined). */
 int rvb_trace_run(rvb_scene *scene, const float mic[3], const float source[3],

@@ -446,24 +446,32 @@ __device__ __forceinline__ M2 m2_mul(const M2 &x, const M2 &y)
 // A thread-block CLUSTER of up to 8 CTAs (1024 threads each) per (channel, band) row.  The
 // recurrence is linear in its (z1, z2) state, so a sweep is split twice:
 //
-//   tiles   16384 samples each, dealt round-robin to the CTAs of the cluster.  Phase 1: every CTA
-//           runs its tiles from a ZERO state and publishes their end states; cluster barrier; every
-//           CTA folds the tile end states with M_T = A^16384 into the true start state of its own
-//           tiles (a few dozen 2x2 steps); phase 2: every CTA re-runs its tiles from those states
-//           and stores the output.  The zero-state work is done twice, but the tiles of a row now
-//           run on up to 8 SMs instead of one after the other on a single SM.
-//   chunks  inside a tile, 1024 chunks of 16 samples, one per thread:
-//     pass 1  every thread runs the reference recurrence over its chunk from a ZERO state and keeps
-//             the end state e_j;
-//     scan    the true start state of chunk j is S_j = M S_{j-1} + e_{j-1}, M = A^16 (A = homogeneous
-//             transition [[-a1, 1], [-a2, 0]], obtained by running the same recurrence on the unit
-//             states).  Three levels: lane 0 of every warp composes its 32 chunks from a zero state,
-//             thread 0 composes the 32 warp totals with M^32, then every thread adds M^lane times its
-//             warp's start state;
-//     pass 2  every thread re-runs the reference recurrence from S_j and stores (float)out.
-// Pass 2 is the reference's own arithmetic; only the start states are associated differently
+//   tiles   16384 samples each, dealt round-robin to the CTAs of the cluster;
+//   chunks  inside a tile, 1024 chunks of 16 samples, one per thread.
+//
+// With A the homogeneous transition [[-a1, 1], [-a2, 0]] (obtained by running the recurrence itself on
+// the unit states), M = A^16 carries a state across a chunk, W = M^32 across a warp's 32 chunks and
+// M_T = W^32 across a tile.  One sweep:
+//
+//   phase A  every thread runs the reference recurrence over its chunk from a ZERO state and keeps the
+//            end state e_j.  The states the chunks WOULD start from if the tile started from zero,
+//            Z_j = sum_{i<j} M^(j-1-i) e_i, come out of two shuffle scans (Kogge-Stone with M^1..M^16
+//            over the lanes of a warp, then with W^1..W^16 over the 32 warp totals); thread j keeps
+//            its part of Z_j in shared memory, the tile's zero-state end goes to global memory;
+//   barrier  (cluster) the tile ends of the whole row are visible; thread 0 of every CTA folds them
+//            with M_T into the true start state T of each of its own tiles (a few dozen 2x2 steps);
+//   phase B  chunk j of a tile starts from S_j = M^j T + Z_j; every thread re-runs the reference
+//            recurrence from S_j and stores (float)out.
+//
+// So every sample is run through the recurrence twice (once for the end states, once for real), the
+// cross-chunk work is 10 shuffle steps instead of serial loops, and the tiles of a row run on up to 8
+// SMs.  Up to RVB_IIR_SLOTS tiles per CTA keep their Z_j between the phases; longer rows go round by
+// round (8 CTAs x 8 slots x 16384 samples = 23 s of audio per round), the fold carrying on.
+// Phase B is the reference's own arithmetic; only the start states are associated differently
 // (double, ~1e-16 relative), so the float outputs equal the serial filter's except for vanishingly
 // rare last-bit rounding flips.  `twopass` = forward sweep then backward sweep (filters.cpp:185-191).
+#define RVB_IIR_SLOTS 8
+
 __device__ __forceinline__ void cluster_sync_all()
 {
     // release/acquire at cluster scope: global writes of the other CTAs of the cluster are visible after it
@@ -483,17 +491,37 @@ __device__ __forceinline__ uint32_t cluster_nctarank()
     return r;
 }
 
+// Inclusive scan over the lanes of a warp of the recurrence I_j = P I_{j-1} + e_j (I_{-1} = 0);
+// pows[k] = P^(2^k).  In: e_j, out: I_j.
+__device__ __forceinline__ void warp_scan_states(const M2 *pows, uint32_t lane, double &a, double &b)
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double pa = __shfl_up_sync(0xffffffffu, a, 1u << k), pb = __shfl_up_sync(0xffffffffu, b, 1u << k);
+        if (lane >= (1u << k)) {
+            const M2 M = pows[k];
+            a += M.a * pa + M.b * pb;
+            b += M.c * pa + M.d * pb;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const uint32_t *row_off, const uint32_t *row_len,
                                                               const RowFilter *filters, int mode /* 1 onepass, 2 twopass */,
                                                               double *tile_ends /* [row][max_tiles][2] */, uint32_t max_tiles)
 {
-    extern __shared__ float tile[];                       // RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1), padded rows
-    __shared__ double e1[RVB_IIR_THREADS], e2[RVB_IIR_THREADS];   // pass-1 end states, then local prefixes
-    __shared__ double w1[RVB_IIR_WARPS], w2[RVB_IIR_WARPS];       // warp totals, then warp start states
+    extern __shared__ __align__(16) unsigned char iir_smem[];
+    float *tile = reinterpret_cast<float *>(iir_smem);                        // RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1), padded rows
+    double *Z1 = reinterpret_cast<double *>(iir_smem + (size_t)RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1) * sizeof(float));
+    double *Z2 = Z1 + RVB_IIR_SLOTS * RVB_IIR_THREADS;                          // [slot][thread]
+    __shared__ double w1[RVB_IIR_WARPS], w2[RVB_IIR_WARPS];       // warp totals (phase A), warp start states (phase B)
+    __shared__ double Y1[RVB_IIR_SLOTS][RVB_IIR_WARPS], Y2[RVB_IIR_SLOTS][RVB_IIR_WARPS];   // zero-start state of every warp of a tile
+    __shared__ double T1[RVB_IIR_SLOTS], T2[RVB_IIR_SLOTS];       // true start state of this CTA's tiles
+    __shared__ double E1[8 * RVB_IIR_SLOTS], E2[8 * RVB_IIR_SLOTS];   // the round's tile ends
     __shared__ M2 pw[32];                                          // M^lane
-    __shared__ M2 MW;                                              // M^32
-    __shared__ M2 MT;                                              // M^1024 = A^RVB_IIR_TILE
-    __shared__ double carry[2];
+    __shared__ M2 pwW[32];                                         // W^lane
+    __shared__ M2 powM[5], powW[5];                                // M^(2^k), W^(2^k)
+    __shared__ M2 MT;                                              // W^32 = A^RVB_IIR_TILE
     const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
     const uint32_t row = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *x = data + row_off[row];
@@ -502,11 +530,12 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
     double *ends = tile_ends + (size_t)row * max_tiles * 2;
     const RowFilter F = filters[row];
     float *mine = tile + tid * (RVB_IIR_CHUNK + 1);
+    const uint32_t round_tiles = csize * RVB_IIR_SLOTS;
     for (int p = 0; p < F.npass; ++p) {
         const BiquadCoef q = F.q[p];
         __syncthreads();
         if (tid < 32) {
-            // M = A^CHUNK from the homogeneous response to the unit states, then M^lane
+            // M = A^CHUNK from the homogeneous response to the unit states, then its powers
             M2 Mc;
             {
                 double c0z1 = 1.0, c0z2 = 0.0, c1z1 = 0.0, c1z2 = 1.0;
@@ -519,36 +548,28 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
             M2 P = M2{1.0, 0.0, 0.0, 1.0};
             for (uint32_t k = 0; k < lane; ++k) P = m2_mul(Mc, P);
             pw[lane] = P;
-            if (lane == 31) {
-                M2 W = m2_mul(Mc, P);      // M^32
-                MW = W;
-                for (int k = 0; k < 5; ++k) W = m2_mul(W, W);   // (M^32)^32 = M^1024
-                MT = W;
-            }
+            if (lane == 31) pwW[1] = m2_mul(Mc, P);                 // W = M^32
+            __syncwarp();
+            const M2 W = pwW[1];
+            __syncwarp();
+            P = M2{1.0, 0.0, 0.0, 1.0};
+            for (uint32_t k = 0; k < lane; ++k) P = m2_mul(W, P);
+            pwW[lane] = P;
+            if (lane == 31) MT = m2_mul(W, P);                      // W^32
+            __syncwarp();
+            if (lane < 5) { powM[lane] = pw[1u << lane]; powW[lane] = pwW[1u << lane]; }
         }
+        __syncthreads();
         for (int dirn = 0; dirn < mode; ++dirn) {
-            // phase 0: zero-state end of every tile of this CTA; phase 1: the real thing
-            double fold_a = 0.0, fold_b = 0.0;   // thread 0: start state of tile fold_pos
-            uint32_t fold_pos = 0;
-            for (int phase = (ntiles > 1 ? 0 : 1); phase < 2; ++phase) {
-                __syncthreads();
-                for (uint32_t t = crank; t < ntiles; t += csize) {
+            double fold_a = 0.0, fold_b = 0.0;   // thread 0: state at the start of the current round, folded onwards
+            uint32_t in_smem = 0xffffffffu;       // the tile whose INPUT samples the shared-memory tile holds
+            for (uint32_t r0 = 0; r0 < ntiles; r0 += round_tiles) {
+                const uint32_t rtiles = min(ntiles - r0, round_tiles);
+                // ---- phase A: zero-state chunk ends, the two scans ------------------------------
+                for (uint32_t slot = 0; slot < RVB_IIR_SLOTS; ++slot) {
+                    const uint32_t t = r0 + slot * csize + crank;
+                    if (t >= ntiles) break;
                     const uint32_t t0 = t * RVB_IIR_TILE;
-                    if (phase == 0 && t + 1 == ntiles) continue;   // nobody needs the end state of the last tile
-                    if (tid == 0) {
-                        if (phase == 0) { carry[0] = 0.0; carry[1] = 0.0; }
-                        else {
-                            // start state of tile t: keep folding the zero-state tile ends (published by the
-                            // whole cluster in phase 0) with M_T from where the previous tile of this CTA stopped
-                            const M2 M = MT;
-                            for (; fold_pos < t; ++fold_pos) {
-                                const double ea = __ldcg(ends + 2 * fold_pos), eb = __ldcg(ends + 2 * fold_pos + 1);
-                                const double na = M.a * fold_a + M.b * fold_b + ea, nb = M.c * fold_a + M.d * fold_b + eb;
-                                fold_a = na; fold_b = nb;
-                            }
-                            carry[0] = fold_a; carry[1] = fold_b;
-                        }
-                    }
                     for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
                         const uint32_t i = t0 + k;
                         float v = 0.0f;   // zero padding past the end never feeds a stored sample
@@ -556,43 +577,70 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                         if (i < n) v = dirn == 0 ? __ldcg(x + i) : __ldcg(x + (n - 1 - i));
                         tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)] = v;
                     }
+                    in_smem = t;
                     __syncthreads();
-                    double z1 = 0.0, z2 = 0.0;
-                    biquad_chunk<false>(q, mine, z1, z2);
-                    e1[tid] = z1; e2[tid] = z2;
-                    __syncwarp();
-                    if (lane == 0) {   // level 1: local prefixes of this warp's chunks, from a zero state
-                        const M2 M = pw[1];
-                        double a = 0.0, b = 0.0;
-                        for (int j = 0; j < 32; ++j) {
-                            const double ea = e1[tid + j], eb = e2[tid + j];
-                            e1[tid + j] = a; e2[tid + j] = b;
-                            const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
-                            a = na; b = nb;
+                    double a = 0.0, b = 0.0;
+                    biquad_chunk<false>(q, mine, a, b);
+                    warp_scan_states(powM, lane, a, b);
+                    {
+                        double za = __shfl_up_sync(0xffffffffu, a, 1), zb = __shfl_up_sync(0xffffffffu, b, 1);
+                        if (lane == 0) { za = 0.0; zb = 0.0; }
+                        Z1[slot * RVB_IIR_THREADS + tid] = za; Z2[slot * RVB_IIR_THREADS + tid] = zb;
+                    }
+                    if (lane == 31) { w1[warp] = a; w2[warp] = b; }
+                    __syncthreads();
+                    if (warp == 0) {
+                        a = w1[lane]; b = w2[lane];
+                        warp_scan_states(powW, lane, a, b);
+                        double ya = __shfl_up_sync(0xffffffffu, a, 1), yb = __shfl_up_sync(0xffffffffu, b, 1);
+                        if (lane == 0) { ya = 0.0; yb = 0.0; }
+                        Y1[slot][lane] = ya; Y2[slot][lane] = yb;
+                        if (lane == 31) { __stcg(ends + 2 * t, a); __stcg(ends + 2 * t + 1, b); }
+                    }
+                    __syncthreads();   // w1 / w2 and (with several slots) the tile are reused
+                }
+                // ---- the tile ends of the whole cluster -> start states of this CTA's tiles ------
+                if (csize > 1) cluster_sync_all(); else __syncthreads();
+                if (tid < rtiles) { E1[tid] = __ldcg(ends + 2 * (r0 + tid)); E2[tid] = __ldcg(ends + 2 * (r0 + tid) + 1); }
+                __syncthreads();
+                if (tid == 0) {
+                    const M2 M = MT;
+                    for (uint32_t k = 0; k < rtiles; ++k) {
+                        if (k % csize == crank) { T1[k / csize] = fold_a; T2[k / csize] = fold_b; }
+                        const double na = M.a * fold_a + M.b * fold_b + E1[k], nb = M.c * fold_a + M.d * fold_b + E2[k];
+                        fold_a = na; fold_b = nb;
+                    }
+                }
+                __syncthreads();
+                // ---- phase B: the real thing -----------------------------------------------------
+                for (uint32_t slot = 0; slot < RVB_IIR_SLOTS; ++slot) {
+                    const uint32_t t = r0 + slot * csize + crank;
+                    if (t >= ntiles) break;
+                    const uint32_t t0 = t * RVB_IIR_TILE;
+                    if (in_smem != t) {
+                        for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
+                            const uint32_t i = t0 + k;
+                            float v = 0.0f;
+                            if (i < n) v = dirn == 0 ? __ldcg(x + i) : __ldcg(x + (n - 1 - i));
+                            tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)] = v;
                         }
-                        w1[warp] = a; w2[warp] = b;
+                    }
+                    if (warp == 0) {   // start state of every warp: W^warp T + Y_warp
+                        const M2 P = pwW[lane];
+                        const double ta = T1[slot], tb = T2[slot];
+                        w1[lane] = P.a * ta + P.b * tb + Y1[slot][lane];
+                        w2[lane] = P.c * ta + P.d * tb + Y2[slot][lane];
                     }
                     __syncthreads();
-                    if (tid == 0) {    // level 2: start state of every warp
-                        const M2 M = MW;
-                        double a = carry[0], b = carry[1];
-                        for (int w = 0; w < RVB_IIR_WARPS; ++w) {
-                            const double ea = w1[w], eb = w2[w];
-                            w1[w] = a; w2[w] = b;
-                            const double na = M.a * a + M.b * b + ea, nb = M.c * a + M.d * b + eb;
-                            a = na; b = nb;
-                        }
-                        if (phase == 0) { __stcg(ends + 2 * t, a); __stcg(ends + 2 * t + 1, b); }
-                    }
-                    __syncthreads();
-                    if (phase == 0) continue;
-                    {                  // level 3: S_j = M^lane * (warp start) + local prefix
+                    double z1, z2;
+                    {                  // S_j = M^lane * (warp start) + Z_j
                         const M2 P = pw[lane];
                         const double a = w1[warp], b = w2[warp];
-                        z1 = P.a * a + P.b * b + e1[tid];
-                        z2 = P.c * a + P.d * b + e2[tid];
+                        z1 = P.a * a + P.b * b + Z1[slot * RVB_IIR_THREADS + tid];
+                        z2 = P.c * a + P.d * b + Z2[slot * RVB_IIR_THREADS + tid];
                     }
                     biquad_chunk<true>(q, mine, z1, z2);
+                    in_smem = 0xffffffffu;
                     __syncthreads();
                     for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
                         const uint32_t i = t0 + k;
@@ -603,10 +651,9 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                     }
                     __syncthreads();
                 }
-                // phase 0 -> 1: the tile ends of the whole cluster must be visible; phase 1 -> next sweep: the
-                // next sweep reads samples the other CTAs stored
-                if (csize > 1) cluster_sync_all(); else __syncthreads();
             }
+            // the next sweep reads samples the other CTAs stored
+            if (csize > 1) cluster_sync_all(); else __syncthreads();
         }
     }
 }
@@ -1057,7 +1104,7 @@ static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nc
     RVB_CUDA(cudaMemcpyAsync(d_f, hf.data(), nrows * sizeof(RowFilter), cudaMemcpyHostToDevice, st));
     RVB_CUDA(cudaMemcpyAsync(d_off, off.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     RVB_CUDA(cudaMemcpyAsync(d_len, len.data(), nrows * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    const size_t iir_smem = (size_t)RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1) * sizeof(float);
+    const size_t iir_smem = (size_t)RVB_IIR_THREADS * (RVB_IIR_CHUNK + 1) * sizeof(float) + (size_t)2 * RVB_IIR_SLOTS * RVB_IIR_THREADS * sizeof(double);
     RVB_CUDA(cudaFuncSetAttribute(iir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iir_smem));
     // cluster size: as many CTAs per row as the longest row has tiles, up to the portable maximum of 8
     size_t max_len = 0;

@@ -72,6 +72,7 @@ __host__ __device__ inline float unordered_key(int i) { i = i ^ ((i >> 31) & 0x7
 // with one stream per thread ran its pairs strictly one after the other because of it).
 int pinned_scratch(void **p, size_t bytes);                       // grown on demand, valid until the next call of this thread
 int read_back(void *dst, const void *d_src, size_t bytes);        // copy + synchronise the library stream of this thread
+int trim_cache();                                                // idle cached blocks of the current device back to the driver
 
 // ---- BVH node (see bvh.cu) ------------------------------------------------------------------
 // 4-wide node in HALF a cache line (64 bytes, two 32-byte loads).  The bounce kernels are bound by the

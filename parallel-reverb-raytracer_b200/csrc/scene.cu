@@ -54,7 +54,14 @@ static std::multimap<size_t, CachedBlock> g_free_blocks[64];
 static std::unordered_map<void *, size_t> g_live_blocks[64];
 static size_t g_cached_bytes[64] = {};
 static const size_t kCacheThreshold = (size_t)1 << 20;
-static const size_t kCacheLimit = (size_t)48 << 30;   // beyond this, idle blocks go back to the driver
+// beyond this many bytes of IDLE blocks (per device), the largest go back to the driver; RVB_CACHE_LIMIT_MB
+// overrides the 48 GiB default (a process that shares the GPU with torch's allocator may want less), and
+// rvb_trim_cache() returns all of them at once
+static size_t cache_limit()
+{
+    static const size_t v = getenv("RVB_CACHE_LIMIT_MB") ? (size_t)strtoull(getenv("RVB_CACHE_LIMIT_MB"), nullptr, 10) << 20 : (size_t)48 << 30;
+    return v;
+}
 
 // Small blocks: a stream-ordered memory pool PER HOST THREAD (and device).  With the device's default
 // pool, a block freed on one thread's stream and re-used on another's makes the driver chain the two
@@ -175,7 +182,7 @@ void free_bytes(void *p)
         cudaEventRecord(ready, st);
         g_free_blocks[dev].emplace(bytes, CachedBlock{p, st, ready});
         g_cached_bytes[dev] += bytes;
-        while (g_cached_bytes[dev] > kCacheLimit && !g_free_blocks[dev].empty()) {
+        while (g_cached_bytes[dev] > cache_limit() && !g_free_blocks[dev].empty()) {
             auto big = std::prev(g_free_blocks[dev].end());
             drop.push_back(big->second.p);
             cudaEventDestroy(big->second.ready);
@@ -187,6 +194,25 @@ void free_bytes(void *p)
         cudaDeviceSynchronize();
         for (void *q : drop) cudaFree(q);
     }
+}
+
+// Give every idle cached block of the current device back to the driver (live blocks are untouched).
+int trim_cache()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::vector<void *> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        for (auto &kv : g_free_blocks[dev]) { drop.push_back(kv.second.p); cudaEventDestroy(kv.second.ready); }
+        g_free_blocks[dev].clear();
+        g_cached_bytes[dev] = 0;
+    }
+    if (!drop.empty()) {
+        RVB_CUDA(cudaDeviceSynchronize());   // their last users may still be running
+        for (void *q : drop) cudaFree(q);
+    }
+    return RVB_OK;
 }
 
 static thread_local void *g_scratch = nullptr;
@@ -356,6 +382,7 @@ int rvb_set_stream(void *cuda_stream, int use)
 }
 
 unsigned long long rvb_launch_count(void) { return g_launches.load(); }
+int rvb_trim_cache(void) { return rvb::trim_cache(); }
 
 int rvb_set_device(int device)
 {

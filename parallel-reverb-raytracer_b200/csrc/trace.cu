@@ -49,6 +49,11 @@ struct TraceParams {
     uint32_t first, last;     // reflections [first, last) handled by this launch
     float air[RVB_NBANDS];
     uint32_t wf_service, wf_leaf_min;          // wavefront kernel: lanes that must wait before `serve` / hold a leaf before the triangle step
+    // wavefront kernel, segmented rays (launch_wavefront): a ray's reflections [first, last) are cut into
+    // wf_nseg work units of wf_seglen reflections; wf_done[ray] = units of that ray completed so far
+    // (RVB_WF_DEAD: the ray left the mesh), wf_done[nrays] = error flag (a unit waited too long)
+    uint32_t wf_nseg, wf_seglen;
+    unsigned int *wf_done;
     const struct TraceJob *jobs;               // [njobs] device array
     uint32_t njobs;
     uint32_t flags;
@@ -1032,9 +1037,35 @@ struct WfShared {
     float volume[RVB_NBANDS][128];
     float distance[128], tmin_nz[128], tmax[128];
     uint32_t ray[128], index[128], queries[128], bounces[128], emitted[128], tri[128];
+    uint32_t end[128];        // the reflection index at which the lane's current work unit ends
 };
 
-template <int MINB, bool BATCH>
+// Segmented rays (SEG).  With fewer than a few waves of rays per launch -- a shard of an 8-GPU run
+// holds 131 k rays on 95 k resident lanes -- whole rays are too coarse a work unit: all rays are equally
+// long (every one of them runs the full reflection count in a closed room), so the lanes finish their
+// first ray together and the remaining 0.4 wave runs on a mostly idle GPU.  A ray's reflections are
+// therefore cut into `wf_nseg` units of `wf_seglen` reflections, queued segment-major (unit u = segment
+// u / nrays of ray u % nrays).  A lane that finishes a unit stores the ray state (the 64-byte record of
+// the image -> steady hand-over: same floats, same bits) and publishes wf_done[ray] with release
+// semantics; the lane that draws the ray's next unit reads it with acquire semantics and, if the
+// predecessor is still running, keeps the unit PENDING while the rest of the warp goes on traversing
+// (it never spins inside a diverged region, and the predecessor was drawn earlier and is being worked
+// on by a resident warp, so the wait ends).  A warp with nothing but pending units sleeps and polls; a
+// poll budget turns a would-be hang into an error the host reports.
+#define RVB_WF_DEAD 0xffffffffu
+#define RVB_WF_POLL_LIMIT (1u << 22)
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int MINB, bool BATCH, bool SEG>
 __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const TraceParams P, const TraceJob J0, unsigned int *fetch_all /* [njobs] */)
 {
     __shared__ WfShared S;
@@ -1060,6 +1091,9 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
     const BvhAccel acc{P.nodes, P.leaf_quads, P.leaf_ids, P.tri, J.micmap, stack};
     int sp = 0, node = RVB_SENTINEL;
     bool has = false, exhausted = false;
+    bool pend = false;                               // SEG: holds a unit whose predecessor has not been published yet
+    uint32_t polls = 0;
+    const uint32_t nunits = SEG ? P.nrays * P.wf_nseg : P.nrays;
     uint32_t ibest = RVB_NONE, nbox = 0, ntri = 0;
     float tbest = RVB_INF;
     f3 pos = mk3(0.f, 0.f, 0.f), dir = pos;
@@ -1088,11 +1122,18 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 for (int b = 0; b < RVB_NBANDS / 2; ++b) { S.volume[2 * b][tid] = R.volume[b].x; S.volume[2 * b + 1][tid] = R.volume[b].y; }
                 S.tmin_nz[tid] = c.tmin_nz; S.tmax[tid] = c.tmax;
                 S.queries[tid] += 1u + c.queries; S.emitted[tid] += c.emitted; S.tri[tid] += (uint32_t)c.tri;
+                S.bounces[tid] += 1u;
                 ++index;
-                more = index != P.last;
+                more = index != (SEG ? S.end[tid] : P.last);
+                if (SEG && !more && index != P.last) {
+                    // end of a unit, not of the ray: hand the ray over to whoever draws its next unit
+                    store_state(J, ray, R, true);
+                    st_release_gpu(P.wf_done + ray, (index - P.first) / P.wf_seglen);
+                }
             } else {
                 S.queries[tid] += 1u;
                 zero_fill(P, J, ray, index);                                    // left the mesh, kernel.cpp:372-375
+                if (SEG) st_release_gpu(P.wf_done + ray, RVB_WF_DEAD);          // its later units are void
             }
             if (more) {
                 S.index[tid] = index;
@@ -1100,13 +1141,13 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 tbest = RVB_INF; ibest = RVB_NONE;
                 sp = 0; stack.push(sp, RVB_SENTINEL); node = 0;
             } else {
-                S.bounces[tid] += index - P.first;
-                if (J.count) J.count[ray] = (P.first ? J.count[ray] : 0u) + (index - P.first);
+                // reflections executed by this ray so far (the image phase, if any, ran [0, first) in full)
+                if (J.count && (index == P.last || ibest == RVB_NONE)) J.count[ray] = index;
                 has = false;
             }
         }
-        // ---- refill: free lanes take the next rays -----------------------------------------------
-        bool want = !has && !exhausted;
+        // ---- refill: free lanes take the next rays (SEG: the next units) ----------------------------
+        bool want = !has && !pend && !exhausted;
         while (true) {
             const unsigned m = __ballot_sync(FULL, want);
             if (!m) break;
@@ -1115,39 +1156,80 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
             if ((int)lane == leader) base = atomicAdd(fetch, (unsigned)__popc(m));
             base = __shfl_sync(FULL, base, leader);
             if (want) {
-                const uint32_t r = base + __popc(m & ((1u << lane) - 1u));
-                if (r >= P.nrays) { want = false; exhausted = true; }
+                const uint32_t u = base + __popc(m & ((1u << lane) - 1u));
+                if (u >= nunits) { want = false; exhausted = true; }
                 else {
-                    bool live = true;
-                    if (P.first == 0) {
-                        pos = mk3(J.src[0], J.src[1], J.src[2]);
-                        dir = mk3(__ldg(P.dirs + r));
-                        S.distance[tid] = 0.0f;
-#pragma unroll
-                        for (int b = 0; b < RVB_NBANDS; ++b) S.volume[b][tid] = 1.0f;
+                    const uint32_t seg = SEG ? u / P.nrays : 0u;
+                    const uint32_t r = u - seg * P.nrays;
+                    if (SEG) S.end[tid] = min(P.last, P.first + (seg + 1u) * P.wf_seglen);
+                    if (seg != 0u) {
+                        // a later unit of ray r: it starts from the state its predecessor publishes
+                        S.ray[tid] = r; S.index[tid] = P.first + seg * P.wf_seglen;
+                        pend = true; want = false;
                     } else {
-                        const float4 *s = J.state + 4 * (size_t)r;
-                        const float4 a = s[0], d = s[1];
-                        live = d.w != 0.0f;   // dead: left the mesh during the image phase (slots already zero-filled)
-                        if (live) {
-                            const float4 va = s[2], vb = s[3];
-                            pos = mk3(a); dir = mk3(d); S.distance[tid] = a.w;
-                            S.volume[0][tid] = va.x; S.volume[1][tid] = va.y; S.volume[2][tid] = va.z; S.volume[3][tid] = va.w;
-                            S.volume[4][tid] = vb.x; S.volume[5][tid] = vb.y; S.volume[6][tid] = vb.z; S.volume[7][tid] = vb.w;
+                        bool live = true;
+                        if (P.first == 0) {
+                            pos = mk3(J.src[0], J.src[1], J.src[2]);
+                            dir = mk3(__ldg(P.dirs + r));
+                            S.distance[tid] = 0.0f;
+#pragma unroll
+                            for (int b = 0; b < RVB_NBANDS; ++b) S.volume[b][tid] = 1.0f;
+                        } else {
+                            const float4 *s = J.state + 4 * (size_t)r;
+                            const float4 a = __ldcg(s), d = __ldcg(s + 1);
+                            live = d.w != 0.0f;   // dead: left the mesh during the image phase (slots already zero-filled)
+                            if (live) {
+                                const float4 va = __ldcg(s + 2), vb = __ldcg(s + 3);
+                                pos = mk3(a); dir = mk3(d); S.distance[tid] = a.w;
+                                S.volume[0][tid] = va.x; S.volume[1][tid] = va.y; S.volume[2][tid] = va.z; S.volume[3][tid] = va.w;
+                                S.volume[4][tid] = vb.x; S.volume[5][tid] = vb.y; S.volume[6][tid] = vb.z; S.volume[7][tid] = vb.w;
+                            } else if (SEG) st_release_gpu(P.wf_done + r, RVB_WF_DEAD);
                         }
+                        if (live) {
+                            S.ray[tid] = r; S.index[tid] = P.first;
+                            sr = BvhAccel::slab_ray(pos, dir);
+                            tbest = RVB_INF; ibest = RVB_NONE;
+                            sp = 0; stack.push(sp, RVB_SENTINEL); node = 0;
+                            has = true; want = false;
+                        }
+                        // dead rays are skipped: keep asking
                     }
-                    if (live) {
-                        S.ray[tid] = r; S.index[tid] = P.first;
-                        sr = BvhAccel::slab_ray(pos, dir);
-                        tbest = RVB_INF; ibest = RVB_NONE;
-                        sp = 0; stack.push(sp, RVB_SENTINEL); node = 0;
-                        has = true; want = false;
-                    }
-                    // dead rays are skipped: keep asking
                 }
             }
         }
-        if (!__any_sync(FULL, has)) break;
+        // ---- SEG: pending units whose predecessor has been published start now ----------------------
+        if (SEG && pend) {
+            const uint32_t r = S.ray[tid];
+            const uint32_t need = (S.index[tid] - P.first) / P.wf_seglen;
+            const uint32_t done = ld_acquire_gpu(P.wf_done + r);
+            if (done >= need) {
+                pend = false;
+                if (done != RVB_WF_DEAD) {
+                    // L2 loads: the record was written by another SM during this launch
+                    const float4 *s = J.state + 4 * (size_t)r;
+                    const float4 a = __ldcg(s), d = __ldcg(s + 1), va = __ldcg(s + 2), vb = __ldcg(s + 3);
+                    pos = mk3(a); dir = mk3(d); S.distance[tid] = a.w;
+                    S.volume[0][tid] = va.x; S.volume[1][tid] = va.y; S.volume[2][tid] = va.z; S.volume[3][tid] = va.w;
+                    S.volume[4][tid] = vb.x; S.volume[5][tid] = vb.y; S.volume[6][tid] = vb.z; S.volume[7][tid] = vb.w;
+                    sr = BvhAccel::slab_ray(pos, dir);
+                    tbest = RVB_INF; ibest = RVB_NONE;
+                    sp = 0; stack.push(sp, RVB_SENTINEL); node = 0;
+                    has = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, has)) {
+            if (!SEG) break;
+            if (__all_sync(FULL, exhausted)) break;   // nothing held, nothing left to draw
+            if (__any_sync(FULL, pend)) {
+                __nanosleep(200);
+                if (++polls > RVB_WF_POLL_LIMIT) {     // never observed; a hang would cost the caller the device
+                    if (lane == 0) atomicExch(P.wf_done + P.nrays, 1u);
+                    break;
+                }
+            }
+            continue;
+        }
 
         // ---- traverse ------------------------------------------------------------------------------
         // Every iteration runs ONE of the two code paths for all lanes that are in that state: the
@@ -1180,39 +1262,69 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
   }
 }
 
-static int launch_wavefront(const TraceParams &P_in, const TraceJob &J0, size_t stack_bytes, cudaStream_t st)
+static int launch_wavefront(const TraceParams &P_in, const TraceJob &J0, size_t stack_bytes, cudaStream_t st, unsigned int **done_out)
 {
+    *done_out = nullptr;
     static const int minb_env = getenv("RVB_WF_MINB") ? atoi(getenv("RVB_WF_MINB")) : 0;
     static const int service = getenv("RVB_WF_SERVICE") ? atoi(getenv("RVB_WF_SERVICE")) : 24;
     static const int leaf_min = getenv("RVB_WF_LEAF_MIN") ? atoi(getenv("RVB_WF_LEAF_MIN")) : 8;
     static const int grid_env = getenv("RVB_WF_GRID") ? atoi(getenv("RVB_WF_GRID")) : 0;
+    static const int nseg_env = getenv("RVB_WF_NSEG") ? atoi(getenv("RVB_WF_NSEG")) : 0;   // 1: whole rays
     TraceParams P = P_in;
     P.wf_service = (uint32_t)std::max(1, std::min(32, service));
     P.wf_leaf_min = (uint32_t)std::max(1, std::min(32, leaf_min));
+    P.wf_nseg = 1; P.wf_seglen = P.last - P.first; P.wf_done = nullptr;
     // 5 CTAs of 128 threads per SM (<= 96 registers): 4 and 6 are 3-5 % slower, 7 (72 registers, spills) 23 %
     const int minb = minb_env ? minb_env : 5;
+    const bool batch = P.njobs > 1;
     unsigned int *d_fetch = nullptr;   // one ray counter per job
+    unsigned int *d_done = nullptr;
     RVB_TRY(dev_alloc(&d_fetch, (size_t)P.njobs));
     RVB_CUDA(cudaMemsetAsync(d_fetch, 0, P.njobs * sizeof(unsigned int), st));
-    auto go = [&](auto kernel) -> int {
+    auto go = [&](auto kernel, auto kernel_seg) -> int {
         int per_sm = 0;
         RVB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_bytes));
         RVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, stack_bytes));
         const size_t want = ((size_t)P.nrays * P.njobs + 127) / 128;
         unsigned grid = (unsigned)std::max<size_t>(1, std::min(want, (size_t)std::max(per_sm, 1) * sm_count()));
         if (grid_env > 0) grid = (unsigned)std::min<size_t>(want, (size_t)grid_env);
-        note_launch(), kernel<<<grid, 128, stack_bytes, st>>>(P, J0, d_fetch);
+        // Segmented rays (see WfShared): only when the rays do not fit the resident lanes at once (otherwise
+        // nothing queues) and a whole-ray tail would matter -- aim at >= 16 units per lane, units of >= 8 reflections.
+        const uint32_t steps = P.last - P.first;
+        const size_t lanes = (size_t)grid * 128;
+        const uint32_t forced = nseg_env > 0 ? (uint32_t)nseg_env : ((P.flags >> 8) & 0xffu);
+        if (!batch && steps >= 2 && J0.state != nullptr && (size_t)P.nrays * 16 < 0xffffffffull && (forced ? forced > 1 : steps >= 16 && P.nrays > lanes)) {
+            uint32_t nseg = forced ? std::min(forced, steps) : (uint32_t)((16 * lanes + P.nrays - 1) / P.nrays);
+            if (!forced) nseg = std::max(1u, std::min(nseg, std::min(16u, steps / 8u)));
+            nseg = std::min(nseg, 16u);
+            if (nseg > 1) {
+                P.wf_seglen = (steps + nseg - 1) / nseg;
+                P.wf_nseg = (steps + P.wf_seglen - 1) / P.wf_seglen;
+            }
+        }
+        if (P.wf_nseg > 1) {
+            RVB_TRY(dev_alloc(&d_done, (size_t)P.nrays + 1));
+            RVB_CUDA(cudaMemsetAsync(d_done, 0, ((size_t)P.nrays + 1) * sizeof(unsigned int), st));
+            P.wf_done = d_done;
+            RVB_CUDA(cudaFuncSetAttribute(kernel_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_bytes));
+            note_launch(), kernel_seg<<<grid, 128, stack_bytes, st>>>(P, J0, d_fetch);
+        } else
+            note_launch(), kernel<<<grid, 128, stack_bytes, st>>>(P, J0, d_fetch);
         RVB_CUDA(cudaGetLastError());
         return RVB_OK;
     };
     int rc;
-    const bool batch = P.njobs > 1;
     switch (minb) {
-    case 4: rc = batch ? go(trace_bvh_wavefront_kernel<4, true>) : go(trace_bvh_wavefront_kernel<4, false>); break;
-    case 6: rc = batch ? go(trace_bvh_wavefront_kernel<6, true>) : go(trace_bvh_wavefront_kernel<6, false>); break;
-    case 7: rc = batch ? go(trace_bvh_wavefront_kernel<7, true>) : go(trace_bvh_wavefront_kernel<7, false>); break;
-    default: rc = batch ? go(trace_bvh_wavefront_kernel<5, true>) : go(trace_bvh_wavefront_kernel<5, false>); break;
+    case 4: rc = batch ? go(trace_bvh_wavefront_kernel<4, true, false>, trace_bvh_wavefront_kernel<4, true, false>)
+                       : go(trace_bvh_wavefront_kernel<4, false, false>, trace_bvh_wavefront_kernel<4, false, true>); break;
+    case 6: rc = batch ? go(trace_bvh_wavefront_kernel<6, true, false>, trace_bvh_wavefront_kernel<6, true, false>)
+                       : go(trace_bvh_wavefront_kernel<6, false, false>, trace_bvh_wavefront_kernel<6, false, true>); break;
+    case 7: rc = batch ? go(trace_bvh_wavefront_kernel<7, true, false>, trace_bvh_wavefront_kernel<7, true, false>)
+                       : go(trace_bvh_wavefront_kernel<7, false, false>, trace_bvh_wavefront_kernel<7, false, true>); break;
+    default: rc = batch ? go(trace_bvh_wavefront_kernel<5, true, false>, trace_bvh_wavefront_kernel<5, true, false>)
+                        : go(trace_bvh_wavefront_kernel<5, false, false>, trace_bvh_wavefront_kernel<5, false, true>); break;
     }
+    *done_out = d_done;   // the caller reads the error flag with its own end-of-trace read-back, then frees it
     dev_free(d_fetch);
     return rc;
 }
@@ -1250,13 +1362,14 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     const bool images = !(tr->flags & RVB_TRACE_NO_IMAGES);
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
     float4 *d_state = nullptr;
+    unsigned int *d_wf_done = nullptr;
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
     // BVH scenes, steady phase: the persistent wavefront kernel (launch_wavefront); RVB_WAVEFRONT=0 selects
     // the one-thread-per-ray kernel for comparison.  Measured on the C3 hall with 64-byte nodes
     // (profiles/r2_bvh_kernels.md): 52.5 ms against 61.5 ms at 1 Mi rays, 14.6 against 16.0 at 262 k,
     // 8.1 against 8.2 at 131 k (the per-GPU share of an 8-GPU run).
     static const bool wavefront = !(getenv("RVB_WAVEFRONT") && *getenv("RVB_WAVEFRONT") == '0');
-    if (split < tr->nrefl && split > 0) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays * njobs));
+    if (split < tr->nrefl && (split > 0 || !brute)) RVB_TRY(dev_alloc(&d_state, 4 * tr->nrays * njobs));
     // brute force: the whole scene; BVH: the traversal stacks (one column of Scene::bvh_stack entries per thread)
     const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : (size_t)sc->bvh_stack * RVB_BVH_CTA * sizeof(int);
 
@@ -1326,7 +1439,7 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
                 if (njobs > 1) RVB_TRY(launch_phase(trace_bvh_kernel<false, 6, true>, P, jobs[0], 128, smem, st));
                 else RVB_TRY(launch_phase(trace_bvh_kernel<false, 6, false>, P, jobs[0], 128, smem, st));
             }
-            else RVB_TRY(launch_wavefront(P, jobs[0], smem, st));
+            else RVB_TRY(launch_wavefront(P, jobs[0], smem, st, &d_wf_done));
         }
     } else if (tr->nrays > 0 && images) {
         // zero reflections: the reference still computes the direct path for ray 0
@@ -1336,7 +1449,10 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     }
     RVB_CUDA(cudaEventRecord(e1, st));
     RVB_CUDA(cudaMemcpyAsync(h_end.data(), d_counters, 6 * njobs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    unsigned int wf_error = 0;   // segmented wavefront kernel: a pending unit ran out of its poll budget
+    if (d_wf_done) RVB_CUDA(cudaMemcpyAsync(&wf_error, d_wf_done + tr->nrays, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_wf_done);
     float ms = 0.f, ms_image = 0.f, ms_steady = 0.f;
     RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     RVB_CUDA(cudaEventElapsedTime(&ms_image, e0, em));
@@ -1361,6 +1477,7 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
         t->stats.queries = h[0]; t->stats.tri_tests = h[1]; t->stats.box_tests = h[2]; t->stats.bounces = h[3];
         t->stats.emitted = h[5];
     }
+    if (wf_error) return fail(RVB_ERR_CUDA, "wavefront kernel: a work unit waited for its predecessor beyond the poll budget");
     return RVB_OK;
 }
 

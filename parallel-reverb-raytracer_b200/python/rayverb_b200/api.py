@@ -19,6 +19,12 @@ LIB_PATH = os.path.join(PKG_ROOT, "librayverb_b200.so")
 
 TRACE_DEBUG = 1
 TRACE_NO_IMAGES = 2
+
+
+def TRACE_UNITS(n):
+    """BVH scenes, testing: cut every ray's steady-phase reflections into n work units (RVB_TRACE_UNITS)."""
+    return (int(n) & 0xff) << 8
+
 ACCEL_AUTO, ACCEL_BRUTE_FORCE, ACCEL_BVH = 0, 1, 2
 MODEL_SPEAKER, MODEL_HRTF = 0, 1
 
@@ -51,7 +57,7 @@ class RenderConfig(C.Structure):
 
 # every symbol include/rayverb_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "rvb_last_error", "rvb_device_count", "rvb_set_device", "rvb_version", "rvb_set_stream", "rvb_launch_count",
+    "rvb_last_error", "rvb_device_count", "rvb_set_device", "rvb_version", "rvb_set_stream", "rvb_launch_count", "rvb_trim_cache",
     "rvb_scene_create", "rvb_scene_destroy", "rvb_scene_accel",
     "rvb_trace_run", "rvb_trace_run_device", "rvb_trace_run_batch", "rvb_trace_destroy", "rvb_trace_diffuse_count", "rvb_trace_copy_diffuse",
     "rvb_trace_image_count", "rvb_trace_copy_images", "rvb_trace_set_images", "rvb_images_merge",
@@ -155,6 +161,11 @@ def set_stream(cuda_stream_ptr):
 
 def launch_count():
     return int(lib().rvb_launch_count())
+
+
+def trim_cache():
+    """rvb_trim_cache: give the idle cached device blocks back to the driver."""
+    _check(lib().rvb_trim_cache())
 
 
 def _filter_id(ft):

@@ -323,6 +323,50 @@ def test_bvh_equals_bruteforce_kernel_4k_triangles():
     assert st_a["queries"] == st_b["queries"]
 
 
+@pytest.mark.parametrize("open_room", [False, True])
+def test_wavefront_work_units_do_not_show(open_room):
+    """The wavefront bounce kernel cuts a ray's steady-phase reflections into work units that different
+    lanes (different SMs) execute one after the other, handing the ray state over through HBM
+    (trace.cu: WfShared / SEG).  The hand-over record holds the same floats the registers held, so the
+    trace must be bit-identical for whole rays (1 unit), for forced cuts -- with 20 000 rays every later
+    unit is drawn while its predecessor still runs, which exercises the pending-unit path on nearly every
+    lane -- and for the cut the launcher chooses itself once the rays exceed the resident lanes.  Open room:
+    rays that leave the mesh void their later units."""
+    tri, vtx = scenes.displaced_box(20.0, 8.0, 14.0, 4400, amp=0.1, fan=0.25, nsurfaces=4)
+    if open_room:
+        tri = tri[len(tri) // 6:]                  # drop most of one wall
+    srf = scenes.hall_surfaces()
+    mic, src = (12, 1.5, 9), (6, 2, 3)
+
+    def run(dirs, nrefl, units, images=True):
+        rt = api.Raytracer(nrefl, tri, vtx, srf, accel=api.ACCEL_BVH)
+        flags = api.TRACE_DEBUG | api.TRACE_UNITS(units) | (0 if images else api.TRACE_NO_IMAGES)
+        tr = rt.raytrace(mic, src, dirs, flags=flags)
+        res = (tr.debug(), tr.raw_diffuse().tobytes(), tr.stats())
+        rt.close()
+        return res
+
+    dirs = scenes.sphere_directions(20000, seed=21)
+    (hit_w, cnt_w), d_w, st_w = run(dirs, 48, 1)
+    if open_room:
+        assert cnt_w.min() < 48 and cnt_w.max() == 48          # some rays escape, some do not
+    for units in (2, 5, 16):
+        (hit, cnt), d, st = run(dirs, 48, units)
+        assert np.array_equal(cnt, cnt_w) and np.array_equal(hit, hit_w), units
+        assert d == d_w, units
+        for k in ("queries", "bounces", "tri_tests", "box_tests"):
+            assert st[k] == st_w[k], (units, k)
+    # no image phase: unit 0 starts from the source, the later ones from hand-over records
+    (hit_a, cnt_a), d_a, _ = run(dirs[:5000], 30, 1, images=False)
+    (hit_b, cnt_b), d_b, _ = run(dirs[:5000], 30, 7, images=False)
+    assert np.array_equal(cnt_a, cnt_b) and np.array_equal(hit_a, hit_b) and d_a == d_b
+    # more rays than resident lanes (148 SMs x 5 CTAs x 128): the launcher's own choice against whole rays
+    dirs = scenes.sphere_directions(150_000, seed=5)
+    (hit_a, cnt_a), d_a, _ = run(dirs, 41, 1)
+    (hit_b, cnt_b), d_b, _ = run(dirs, 41, 0)
+    assert np.array_equal(cnt_a, cnt_b) and np.array_equal(hit_a, hit_b) and d_a == d_b
+
+
 def test_bvh_hall_100k_subsample_vs_oracle(orc):
     """C3 mesh (~100k triangles): a ray subsample against the CPU brute-force oracle."""
     tri, vtx, srf = scenes.concert_hall()
