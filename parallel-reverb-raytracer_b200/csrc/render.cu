@@ -506,6 +506,24 @@ __device__ __forceinline__ void warp_scan_states(const M2 *pows, uint32_t lane, 
     }
 }
 
+// One tile of `tl` samples (a multiple of the chunk length) into the padded shared-memory rows; all 16
+// loads of a thread are issued before the first store (an L2 round trip each: the previous sweep's
+// samples were stored by other CTAs of the cluster).  Samples past the tile or the row read as zero
+// and never feed a stored sample.
+__device__ __forceinline__ void iir_load_tile(float *tile, const float *x, uint32_t n, uint32_t t0, uint32_t tl, int dirn, uint32_t tid)
+{
+    float v[RVB_IIR_CHUNK];
+#pragma unroll
+    for (int j = 0; j < RVB_IIR_CHUNK; ++j) {
+        const uint32_t k = tid + j * RVB_IIR_THREADS, i = t0 + k;
+        v[j] = 0.0f;
+        if (k < tl && i < n) v[j] = dirn == 0 ? __ldcg(x + i) : __ldcg(x + (n - 1 - i));
+    }
+    float *dst = tile + (tid / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (tid % RVB_IIR_CHUNK);
+#pragma unroll
+    for (int j = 0; j < RVB_IIR_CHUNK; ++j) dst[j * (RVB_IIR_THREADS / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1)] = v[j];
+}
+
 __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const uint32_t *row_off, const uint32_t *row_len,
                                                               const RowFilter *filters, int mode /* 1 onepass, 2 twopass */,
                                                               double *tile_ends /* [row][max_tiles][2] */, uint32_t max_tiles)
@@ -526,7 +544,11 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
     const uint32_t row = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *x = data + row_off[row];
     const uint32_t n = row_len[row];
-    const uint32_t ntiles = (n + RVB_IIR_TILE - 1) / RVB_IIR_TILE;
+    // equal tiles, the same number for every CTA of the cluster: tl samples (nch chunks) each
+    const uint32_t per_cta = (n + csize * RVB_IIR_TILE - 1) / (csize * RVB_IIR_TILE);
+    const uint32_t ntiles = csize * per_cta;
+    const uint32_t tl = ntiles ? ((n + ntiles - 1) / ntiles + RVB_IIR_CHUNK - 1) / RVB_IIR_CHUNK * RVB_IIR_CHUNK : 0u;
+    const uint32_t nch = tl / RVB_IIR_CHUNK;   // <= RVB_IIR_THREADS
     double *ends = tile_ends + (size_t)row * max_tiles * 2;
     const RowFilter F = filters[row];
     float *mine = tile + tid * (RVB_IIR_CHUNK + 1);
@@ -555,8 +577,9 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
             P = M2{1.0, 0.0, 0.0, 1.0};
             for (uint32_t k = 0; k < lane; ++k) P = m2_mul(W, P);
             pwW[lane] = P;
-            if (lane == 31) MT = m2_mul(W, P);                      // W^32
+            const M2 W32 = m2_mul(W, P);                            // lane 31: W^32
             __syncwarp();
+            if (lane == 31) MT = nch == RVB_IIR_THREADS ? W32 : m2_mul(pwW[nch >> 5], pw[nch & 31]);   // M^nch: across one tile
             if (lane < 5) { powM[lane] = pw[1u << lane]; powW[lane] = pwW[1u << lane]; }
         }
         __syncthreads();
@@ -569,14 +592,8 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                 for (uint32_t slot = 0; slot < RVB_IIR_SLOTS; ++slot) {
                     const uint32_t t = r0 + slot * csize + crank;
                     if (t >= ntiles) break;
-                    const uint32_t t0 = t * RVB_IIR_TILE;
-                    for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
-                        const uint32_t i = t0 + k;
-                        float v = 0.0f;   // zero padding past the end never feeds a stored sample
-                        // L2 loads: other CTAs of the cluster stored these samples in the previous sweep
-                        if (i < n) v = dirn == 0 ? __ldcg(x + i) : __ldcg(x + (n - 1 - i));
-                        tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)] = v;
-                    }
+                    const uint32_t t0 = t * tl;
+                    iir_load_tile(tile, x, n, t0, tl, dirn, tid);
                     in_smem = t;
                     __syncthreads();
                     double a = 0.0, b = 0.0;
@@ -595,9 +612,16 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                         double ya = __shfl_up_sync(0xffffffffu, a, 1), yb = __shfl_up_sync(0xffffffffu, b, 1);
                         if (lane == 0) { ya = 0.0; yb = 0.0; }
                         Y1[slot][lane] = ya; Y2[slot][lane] = yb;
-                        if (lane == 31) { __stcg(ends + 2 * t, a); __stcg(ends + 2 * t + 1, b); }
+                        if (lane == 31 && nch == RVB_IIR_THREADS) { __stcg(ends + 2 * t, a); __stcg(ends + 2 * t + 1, b); }
                     }
                     __syncthreads();   // w1 / w2 and (with several slots) the tile are reused
+                    if (tid == nch) {
+                        // the tile's zero-start end = the state chunk `nch` would start from
+                        const M2 P = pw[lane];
+                        const double a0 = Y1[slot][warp], b0 = Y2[slot][warp];
+                        __stcg(ends + 2 * t, P.a * a0 + P.b * b0 + Z1[slot * RVB_IIR_THREADS + tid]);
+                        __stcg(ends + 2 * t + 1, P.c * a0 + P.d * b0 + Z2[slot * RVB_IIR_THREADS + tid]);
+                    }
                 }
                 // ---- the tile ends of the whole cluster -> start states of this CTA's tiles ------
                 if (csize > 1) cluster_sync_all(); else __syncthreads();
@@ -613,18 +637,12 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                 }
                 __syncthreads();
                 // ---- phase B: the real thing -----------------------------------------------------
-                for (uint32_t slot = 0; slot < RVB_IIR_SLOTS; ++slot) {
-                    const uint32_t t = r0 + slot * csize + crank;
-                    if (t >= ntiles) break;
-                    const uint32_t t0 = t * RVB_IIR_TILE;
-                    if (in_smem != t) {
-                        for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
-                            const uint32_t i = t0 + k;
-                            float v = 0.0f;
-                            if (i < n) v = dirn == 0 ? __ldcg(x + i) : __ldcg(x + (n - 1 - i));
-                            tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)] = v;
-                        }
-                    }
+                // (last slot first: its samples are still in shared memory from phase A)
+                for (int slot = RVB_IIR_SLOTS - 1; slot >= 0; --slot) {
+                    const uint32_t t = r0 + (uint32_t)slot * csize + crank;
+                    if (t >= ntiles) continue;
+                    const uint32_t t0 = t * tl;
+                    if (in_smem != t) iir_load_tile(tile, x, n, t0, tl, dirn, tid);
                     if (warp == 0) {   // start state of every warp: W^warp T + Y_warp
                         const M2 P = pwW[lane];
                         const double ta = T1[slot], tb = T2[slot];
@@ -642,11 +660,15 @@ __global__ void __launch_bounds__(RVB_IIR_THREADS) iir_kernel(float *data, const
                     biquad_chunk<true>(q, mine, z1, z2);
                     in_smem = 0xffffffffu;
                     __syncthreads();
-                    for (uint32_t k = tid; k < RVB_IIR_TILE; k += RVB_IIR_THREADS) {
-                        const uint32_t i = t0 + k;
-                        if (i < n) {
-                            const float v = tile[(k / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (k % RVB_IIR_CHUNK)];
-                            if (dirn == 0) x[i] = v; else x[n - 1 - i] = v;
+                    {
+                        const float *src = tile + (tid / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1) + (tid % RVB_IIR_CHUNK);
+#pragma unroll
+                        for (int j = 0; j < RVB_IIR_CHUNK; ++j) {
+                            const uint32_t k = tid + j * RVB_IIR_THREADS, i = t0 + k;
+                            if (k < tl && i < n) {
+                                const float v = src[j * (RVB_IIR_THREADS / RVB_IIR_CHUNK) * (RVB_IIR_CHUNK + 1)];
+                                if (dirn == 0) x[i] = v; else x[n - 1 - i] = v;
+                            }
                         }
                     }
                     __syncthreads();
@@ -1109,9 +1131,11 @@ static int filter_device(int ft, float *d_data, const size_t *lengths, size_t nc
     // cluster size: as many CTAs per row as the longest row has tiles, up to the portable maximum of 8
     size_t max_len = 0;
     for (size_t c = 0; c < nch; ++c) max_len = std::max(max_len, lengths[c]);
-    const uint32_t max_tiles = (uint32_t)std::max<size_t>(1, (max_len + RVB_IIR_TILE - 1) / RVB_IIR_TILE);
+    const uint32_t whole_tiles = (uint32_t)std::max<size_t>(1, (max_len + RVB_IIR_TILE - 1) / RVB_IIR_TILE);
     unsigned csize = 1;
-    while (csize < 8 && csize * 2 <= max_tiles) csize *= 2;
+    while (csize < 8 && csize * 2 <= whole_tiles) csize *= 2;
+    // the kernel cuts every row into the same number of (equal) tiles for each CTA of its cluster
+    const uint32_t max_tiles = csize * (uint32_t)std::max<size_t>(1, (max_len + (size_t)csize * RVB_IIR_TILE - 1) / ((size_t)csize * RVB_IIR_TILE));
     double *d_ends = nullptr;
     RVB_TRY(dev_alloc(&d_ends, nrows * (size_t)max_tiles * 2));
     {

@@ -16,14 +16,16 @@ timeout 600 python bench.py --rays 131072 --no-cpu-baseline --no-sub-blocks > $O
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 timeout 600 $CMD > $O/plain_for_ncu.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/launches.csv $CMD > $O/ncu_list.log 2>&1
 CMD4="python bench.py --rays 131072 --steps 1 --warmup 3 --no-cpu-baseline --no-sub-blocks"
-timeout 600 $CMD4 > $O/plain_for_ncu4.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:"trace_bvh|reduce_|onesweep|digit_histogram|iir_kernel" -s 30 -c 12 -o /tmp/prof_c3_kernels -f $CMD4 > $O/ncu_full_c3.log 2>&1
+timeout 600 $CMD4 > $O/plain_for_ncu4.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"wavefront|trace_bvh_kernel|reduce_cta|iir_kernel|FlattenIn" -c 10 -o /tmp/prof_c3_kernels -f $CMD4 > $O/ncu_full_c3.log 2>&1
 CMD2="python bench.py --workload C2_shoebox_12tri_1Mx128_omni --rays 262144 --steps 1 --warmup 3 --no-cpu-baseline"
-timeout 600 $CMD2 > $O/plain_for_ncu2.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:"trace_bruteforce|reduce_cta|iir_kernel|onesweep|digit_histogram" -s 20 -c 8 -o /tmp/prof_c2_kernels -f $CMD2 > $O/ncu_full_c2.log 2>&1
+timeout 600 $CMD2 > $O/plain_for_ncu2.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"trace_bruteforce|reduce_cta|iir_kernel|FlattenIn" -c 10 -o /tmp/prof_c2_kernels -f $CMD2 > $O/ncu_full_c2.log 2>&1
 # the reports stay on the box (gpurun_out/ is capped at 64 MiB): bring back the summaries and the raw metric pages
 for r in c3 c2; do
   python tools/ncu_summary.py /tmp/prof_${r}_kernels.ncu-rep > $O/ncu_${r}_summary.md 2> $O/ncu_${r}_summary.err
   ncu -i /tmp/prof_${r}_kernels.ncu-rep --page raw --csv > $O/ncu_${r}_raw.csv 2>/dev/null
 done
+# per-instruction stall samples of the band filter (source page, SASS)
+ncu -i /tmp/prof_c3_kernels.ncu-rep --page source --csv --kernel-name-base demangled --kernel-name regex:iir_kernel > $O/ncu_iir_source.csv 2>/dev/null
 ls -la $O
 python - <<PY
 import json
