@@ -437,11 +437,13 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
         emit_gbs = nrays * (len(jobs) if scaling == "jobs" else 1) * (nrefl - split) * 52 / (steady_ms * 1e-3) / 1e9 if steady_ms > 0 else 0.0
         traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if brute and world == 1 and os.path.exists(tp):
+        if world == 1 and scaling != "jobs" and os.path.exists(tp):
             # NOT measured in this run: DRAM bytes per ray*bounce of the steady kernel from the committed
             # ncu --set full capture (profiles/ncu_traffic.json), scaled to this run's ray*bounce count
-            traffic = json.load(open(tp))["steady_phase_dram_bytes_per_ray_bounce"] * nrays * (nrefl - split)
-            traffic_note = "profile-derived constant (profiles/ncu_traffic.json) x this run's rays*bounces, not measured live"
+            per_rb = json.load(open(tp)).get("steady_phase_dram_bytes_per_ray_bounce" if brute else "bvh_steady_phase_dram_bytes_per_ray_bounce")
+            if per_rb:
+                traffic = per_rb * nrays * (nrefl - split)
+                traffic_note = "profile-derived constant (profiles/ncu_traffic.json) x this run's rays*bounces, not measured live"
         both_ms = steady_ms + image_ms
         bounces, emitted = per_launch("bounces"), per_launch("emitted")
         block = {
@@ -464,7 +466,7 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
             # the share of them whose impulse the attenuators skip (zero volume, kernel.cpp:524,607)
             "bounces": {"executed": int(bounces), "of": int(nrays * nrefl * max(1, len(jobs) if scaling == "jobs" else 1)),
                         "emitted": int(emitted), "skipped_fraction": (1.0 - emitted / bounces) if bounces > 0 else None},
-            "roofline": {"kernel": ("trace_bruteforce_kernel<false>" if brute else "trace_bvh_kernel<false>")
+            "roofline": {"kernel": ("trace_bruteforce_kernel<false>" if brute else "trace_bvh_wavefront_kernel")
                          + " (steady phase, reflections %d..%d)" % (split, nrefl - 1),
                          "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp32_peak_tf, "traffic": traffic, "traffic_note": traffic_note,
@@ -482,8 +484,9 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
             block["roofline"]["box_tests_per_launch"] = int(steady_boxes)
             block["roofline"]["flop_per_box_test"] = FLOP_PER_BOX
             block["roofline"]["flop_model"] = "tri_tests x 52 + box_tests x 20 (SURVEY 8d); visibility queries go through the microphone map"
-            block["roofline"]["binding_resource"] = ("L1 data pipe: ncu l1tex__data_pipe_lsu_wavefronts 80-90 % of peak on this kernel "
-                                                     "(profiles/r2_bvh_kernels.md) -- divergent node fetches, not FP32 or HBM")
+            block["roofline"]["binding_resource"] = ("L1 data pipe and issue slots: ncu l1tex__data_pipe_lsu_wavefronts 65 % of peak, issue active 59 %, "
+                                                     "17.7 of 32 lanes per instruction on this kernel (profiles/r2_c3_shard_kernels_full.md) -- "
+                                                     "divergent node fetches, not FP32 or HBM")
             block["roofline"]["micmap"] = {"cells_per_face_edge": int(_mean("micmap_cells", tstats)), "entries": int(_mean("micmap_entries", tstats))}
         if sharded_parity is not None:
             block["sharded_parity"] = sharded_parity
