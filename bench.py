@@ -330,9 +330,9 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
             hist, lengths, _ = sharding.sharded_histogram(tr, cfg, rank, world, "cuda", SR, False, timing)
             state["render"].append(api.render_stats())
             if rank == 0:
-                t_host = time.perf_counter()
+                # (the finish follows the last synchronisation point of the step -- the reduce -- so it is not
+                # part of what the shard re-cut can balance: only rank 0's work BEFORE the reduce counts)
                 irs.append(api.render_finish(cfg, hist.data_ptr(), lengths, keep_bands=keep_bands))
-                timing["exclusive_ms"] = timing.get("exclusive_ms", 0.0) + 1e3 * (time.perf_counter() - t_host)
             state["timing"] = timing
         return irs
 
@@ -360,11 +360,11 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
         return ms, api.launch_count() - launches0, d2h
 
     # Warm-up; on a sharded run with several waves of rays per GPU the second warm-up step also MEASURES
-    # the ranks: rank 0 merges the image sources and filters the summed histogram on top of its share of
-    # the rays, so the contiguous ray slices are re-cut once so that every rank finishes at the same time
-    # (sharding.balance_weights).  With ~one wave per GPU the bounce kernels' time is a step function of
-    # the ray count and the linear model behind the re-cut does not hold (C3 at 8 GPUs: 20.5 ms re-cut vs
-    # 19.2 ms equal shards), so small shards stay equal.
+    # the ranks: rank 0 merges the image sources on top of its share of the rays, so the contiguous ray
+    # slices are re-cut once so that every rank reaches the reduce at the same time
+    # (sharding.balance_weights; rank 0's filter + copy-out FOLLOW the reduce and cannot be balanced away:
+    # counting them, as the first version did, took 7.5 k rays off rank 0 at 2 GPUs and made rank 1 the
+    # last to arrive).  Small shards stay equal.
     balance = None
     for w_it in range(max(warmup, 3)):
         step(True)

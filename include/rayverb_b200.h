@@ -92,6 +92,8 @@ int rvb_scene_accel(const rvb_scene *scene, int *accel);
 /* BVH scenes, testing: bits 8-15 = number of work units a ray's steady-phase reflections are cut into by the
    wavefront bounce kernel (0: chosen from the ray count; 1: whole rays).  The results do not depend on it. */
 #define RVB_TRACE_UNITS(n) (((unsigned)(n) & 0xffu) << 8)
+/* testing: de-duplicate the image sources with the radix-sort path even when the few-candidates kernel applies */
+#define RVB_TRACE_SORT_DEDUPE 4u
 /* `ray_offset` is the global index of directions[0] (used when rays are sharded over GPUs: only the
  * shard with ray_offset == 0 emits the direct path, and "lowest ray wins" stays well defined). */
 int rvb_trace_run(rvb_scene *scene, const float mic[3], const float source[3],

@@ -10,6 +10,9 @@
 // (column value = entry + 1, 0 = "past the end", so prefixes sort first); stability keeps the
 // lowest ray first within equal keys; then keep the head of every run of equal keys.
 // The compactions (rvb_scan.cuh) and the radix sort (rvb_sort.cuh) are the library's own.
+#include <cstring>
+#include <vector>
+
 #include "rvb_internal.cuh"
 #include "rvb_scan.cuh"
 #include "rvb_sort.cuh"
@@ -98,6 +101,94 @@ __global__ void gather_unique_kernel(const uint32_t *idx, const uint32_t *sel, c
     for (uint32_t j = 0; j < RVB_NUM_IMAGE_SOURCE; ++j) okeys[u * RVB_NUM_IMAGE_SOURCE + j] = (j <= k0) ? idx[flat - k0 + j] : 0u;
 }
 
+// ---- few candidates: the whole de-duplication in ONE CTA ------------------------------------------
+// A large scene yields few valid image-source candidates (C3's 100k-triangle hall: a few hundred per
+// million rays, a few dozen distinct sequences), and the radix-sort path above then costs ~150 tiny
+// launches (0.43 ms, launch-bound).  Up to RVB_DEDUPE_SMALL candidates are instead ranked by direct
+// comparison in shared memory: candidate p (compacted, ray-major order) is a HEAD if no earlier
+// candidate has the same key -- what the stable sort's "first of a run" selects -- and a head's output
+// position is the number of heads with a lexicographically smaller key (past-the-end columns are 0, so a
+// proper prefix comes before its extensions): the same list in the same order.
+#define RVB_DEDUPE_SMALL 4096u
+#define RVB_DEDUPE_THREADS 1024u
+#define RVB_DEDUPE_COLS (RVB_NUM_IMAGE_SOURCE - 1)   // column 0 is constant
+
+__device__ __forceinline__ int key_cmp_small(const uint32_t *skeys, uint32_t n, uint32_t a, uint32_t b)
+{
+#pragma unroll
+    for (uint32_t j = 0; j < RVB_DEDUPE_COLS; ++j) {
+        const uint32_t ka = skeys[j * n + a], kb = skeys[j * n + b];
+        if (ka != kb) return ka < kb ? -1 : 1;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(RVB_DEDUPE_THREADS) dedupe_small_kernel(const uint32_t *idx, const uint32_t *sel, uint32_t n, const float4 *cvA,
+                                                                          const float4 *cvB, const float4 *cpt, float4 *ovA, float4 *ovB, float4 *opt,
+                                                                          uint32_t *out /* [0] m, [1 + u] key length, [1 + n + 10 u + j] key */)
+{
+    extern __shared__ uint32_t skeys[];                 // [RVB_DEDUPE_COLS][n], then head flags [n]
+    uint32_t *s_head = skeys + (size_t)RVB_DEDUPE_COLS * n;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t p = tid; p < n; p += RVB_DEDUPE_THREADS) {
+        const uint32_t flat = sel[p];
+        for (uint32_t j = 0; j < RVB_DEDUPE_COLS; ++j) skeys[j * n + p] = key_col(idx, flat, j + 1);
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < n; p += RVB_DEDUPE_THREADS) {
+        bool head = true;
+        for (uint32_t q = 0; q < p && head; ++q) head = key_cmp_small(skeys, n, q, p) != 0;
+        s_head[p] = head ? 1u : 0u;
+    }
+    __syncthreads();
+    uint32_t mine = 0;
+    for (uint32_t p = tid; p < n; p += RVB_DEDUPE_THREADS) {
+        if (!s_head[p]) continue;
+        ++mine;
+        uint32_t u = 0;
+        for (uint32_t q = 0; q < n; ++q)
+            if (s_head[q] && key_cmp_small(skeys, n, q, p) < 0) ++u;
+        const uint32_t flat = sel[p], k0 = flat % RVB_NUM_IMAGE_SOURCE;
+        ovA[u] = cvA[flat]; ovB[u] = cvB[flat]; opt[u] = cpt[flat];
+        out[1 + u] = k0 + 1u;
+        for (uint32_t j = 0; j < RVB_NUM_IMAGE_SOURCE; ++j) out[1 + n + u * RVB_NUM_IMAGE_SOURCE + j] = (j <= k0) ? idx[flat - k0 + j] : 0u;
+    }
+    // m = number of heads
+    __shared__ uint32_t s_m;
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    if (mine) atomicAdd(&s_m, mine);
+    __syncthreads();
+    if (tid == 0) out[0] = s_m;
+}
+
+static int dedupe_small(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 *cpt, const uint32_t *cidx, const uint32_t *d_sel, uint32_t n,
+                        cudaStream_t st)
+{
+    // outputs sized for the worst case (every candidate distinct): n <= RVB_DEDUPE_SMALL records
+    RVB_TRY(dev_alloc(&tr->d_img_volA, n));
+    RVB_TRY(dev_alloc(&tr->d_img_volB, n));
+    RVB_TRY(dev_alloc(&tr->d_img_pt, n));
+    uint32_t *d_out = nullptr;
+    const size_t words = 1 + (size_t)n * (1 + RVB_NUM_IMAGE_SOURCE);
+    RVB_TRY(dev_alloc(&d_out, words));
+    const size_t smem = ((size_t)RVB_DEDUPE_COLS + 1) * n * sizeof(uint32_t);
+    RVB_CUDA(cudaFuncSetAttribute(dedupe_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)RVB_DEDUPE_COLS + 1) * RVB_DEDUPE_SMALL * sizeof(uint32_t))));
+    note_launch(), dedupe_small_kernel<<<1, RVB_DEDUPE_THREADS, smem, st>>>(cidx, d_sel, n, cvA, cvB, cpt, tr->d_img_volA, tr->d_img_volB, tr->d_img_pt, d_out);
+    RVB_CUDA(cudaGetLastError());
+    std::vector<uint32_t> h(words);
+    RVB_TRY(read_back(h.data(), d_out, words * sizeof(uint32_t)));
+    dev_free(d_out);
+    const uint32_t m = h[0];
+    tr->img_len.resize(m);
+    tr->img_keys.resize((size_t)m * RVB_NUM_IMAGE_SOURCE);
+    for (uint32_t u = 0; u < m; ++u) tr->img_len[u] = (int32_t)h[1 + u];
+    if (m) memcpy(tr->img_keys.data(), h.data() + 1 + n, (size_t)m * RVB_NUM_IMAGE_SOURCE * sizeof(uint32_t));
+    tr->n_images = m;
+    tr->first_is_direct = (m > 0 && tr->img_len[0] == 1);   // key {0} sorts first when present
+    return RVB_OK;
+}
+
 int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 *cpt, const uint32_t *cidx)
 {
     cudaStream_t st = lib_stream();
@@ -115,6 +206,11 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     uint32_t n = 0;
     RVB_TRY(read_back(&n, d_nsel, sizeof n));
     if (n == 0) { dev_free(d_sel); dev_free(d_nsel); return RVB_OK; }
+    if (n <= RVB_DEDUPE_SMALL && !(tr->flags & RVB_TRACE_SORT_DEDUPE)) {
+        const int rc = dedupe_small(tr, cvA, cvB, cpt, cidx, d_sel, n, st);
+        dev_free(d_sel); dev_free(d_nsel);
+        return rc;
+    }
 
     uint32_t *d_perm[2] = {nullptr, nullptr}, *d_keys[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_perm[i], n)); RVB_TRY(dev_alloc(&d_keys[i], n)); }

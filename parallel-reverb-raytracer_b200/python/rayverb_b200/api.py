@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(PKG_ROOT, "librayverb_b200.so")
 
 TRACE_DEBUG = 1
 TRACE_NO_IMAGES = 2
+TRACE_SORT_DEDUPE = 4
 
 
 def TRACE_UNITS(n):

@@ -367,6 +367,33 @@ def test_wavefront_work_units_do_not_show(open_room):
     assert np.array_equal(cnt_a, cnt_b) and np.array_equal(hit_a, hit_b) and d_a == d_b
 
 
+def test_image_dedupe_few_candidates_kernel_equals_sort_path():
+    """Up to 4096 valid image-source candidates are de-duplicated by one CTA (direct ranking in shared memory,
+    images.cu: dedupe_small_kernel) instead of the radix-sort path.  Same keys, same order, same winners
+    (the lowest ray of every sequence), same impulses: shoebox with many duplicates per sequence, a displaced
+    room with several surfaces, an open room, and the direct path alone (zero reflections)."""
+    cases = []
+    tri, vtx, srf = scenes.shoebox()
+    cases.append((tri, vtx, srf, (7, 2, 4), (2, 1.5, 2), scenes.sphere_directions(400, seed=4), 12, api.ACCEL_BRUTE_FORCE))
+    cases.append((tri[2:], vtx, srf, (7, 2, 4), (2, 1.5, 2), scenes.sphere_directions(380, seed=5), 7, api.ACCEL_BRUTE_FORCE))
+    cases.append((tri, vtx, srf, (7, 2, 4), (2, 1.5, 2), scenes.sphere_directions(64, seed=6), 0, api.ACCEL_BRUTE_FORCE))
+    tri2, vtx2 = scenes.displaced_box(20.0, 8.0, 14.0, 4400, amp=0.1, fan=0.25, nsurfaces=4)
+    cases.append((tri2, vtx2, scenes.hall_surfaces(), (12, 1.5, 9), (6, 2, 3), scenes.sphere_directions(30000, seed=7), 20, api.ACCEL_BVH))
+    for tri, vtx, srf, mic, src, dirs, nrefl, accel in cases:
+        out = []
+        for flags in (0, api.TRACE_SORT_DEDUPE):
+            rt = api.Raytracer(nrefl, tri, vtx, srf, accel=accel)
+            tr = rt.raytrace(mic, src, dirs, flags=flags)
+            img, keys, klen = tr.raw_images(with_keys=True)
+            img_nd = tr.raw_images(remove_direct=True)
+            out.append((img.tobytes(), keys.copy(), klen.copy(), img_nd.tobytes()))
+            rt.close()
+        a, b = out
+        assert len(a[2]) > 0
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert a[0] == b[0] and a[3] == b[3]
+
+
 def test_bvh_hall_100k_subsample_vs_oracle(orc):
     """C3 mesh (~100k triangles): a ray subsample against the CPU brute-force oracle."""
     tri, vtx, srf = scenes.concert_hall()
