@@ -92,6 +92,9 @@ int rvb_scene_accel(const rvb_scene *scene, int *accel);
 /* BVH scenes, testing: bits 8-15 = number of work units a ray's steady-phase reflections are cut into by the
    wavefront bounce kernel (0: chosen from the ray count; 1: whole rays).  The results do not depend on it. */
 #define RVB_TRACE_UNITS(n) (((unsigned)(n) & 0xffu) << 8)
+/* BVH scenes, testing: bits 16-23 = cells per triangle of the microphone visibility map (0: chosen from the query count).
+   The map only pre-selects candidates for the reference's exact test: the results do not depend on it. */
+#define RVB_TRACE_MAP_CELLS(n) (((unsigned)(n) & 0xffu) << 16)
 /* testing: de-duplicate the image sources with the radix-sort path even when the few-candidates kernel applies */
 #define RVB_TRACE_SORT_DEDUPE 4u
 /* `ray_offset` is the global index of directions[0] (used when rays are sharded over GPUs: only the

@@ -165,17 +165,21 @@ void micmap_free(MicMapStorage *s)
 // sizes the grid: building costs ~ entries, a visibility query ~ candidates per cell, so a job with few
 // queries gets a coarser map (16 cells per triangle from 32 queries per triangle upwards, 4 at the
 // other end; C5's 16 k rays x 128 per pair: 10).
-int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n, size_t nqueries, MicMapStorage *out)
+int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n, size_t nqueries, MicMapStorage *out, double forced_cells_per_tri)
 {
     for (size_t j = 0; j < n; ++j) out[j] = MicMapStorage{};
     static const int enabled = getenv("RVB_MICMAP") ? atoi(getenv("RVB_MICMAP")) : 1;
     if (!enabled || sc->accel != RVB_ACCEL_BVH || !(sc->diag > 0.0f) || n == 0) return RVB_OK;
     static const double cpt_env = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 0.0;
-    const double cells_per_tri = cpt_env > 0.0 ? cpt_env : std::min(16.0, std::max(4.0, (double)nqueries / (2.0 * sc->T)));
+    // finer than 16 cells per triangle only pays above ~40 M queries (C3, profiles/r2_micmap_resolution.log: 1 Mi rays x 128,
+    // 48 cells: build +0.7 ms, steady phase -1.9 ms; a 131 k-ray shard: +0.7 / -0.3 ms)
+    const double cap = std::min(48.0, std::max(16.0, 16.0 * (double)nqueries / 40e6));
+    const double cells_per_tri = forced_cells_per_tri > 0.0 ? forced_cells_per_tri : cpt_env > 0.0 ? cpt_env : std::min(cap, std::max(4.0, (double)nqueries / (2.0 * sc->T)));
     cudaStream_t st = lib_stream();
     MicMapParams M{};
     M.verts = sc->d_verts; M.T = sc->T;
-    M.N = (uint32_t)std::min(512.0, std::max(8.0, std::round(std::sqrt(cells_per_tri * sc->T / 6.0))));
+    static const double nmax = getenv("RVB_MICMAP_NMAX") ? atof(getenv("RVB_MICMAP_NMAX")) : 1024.0;
+    M.N = (uint32_t)std::min(nmax, std::max(8.0, std::round(std::sqrt(cells_per_tri * sc->T / 6.0))));
     M.half_n = 0.5f * (float)M.N;
     M.delta = 1e-4f * sc->diag + 1e-6f;
     M.r_near = 40.0f * M.delta;
@@ -226,7 +230,7 @@ int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n
 
 int micmap_build(const Scene *sc, const float mic[3], size_t nqueries, MicMapStorage *out)
 {
-    return micmap_build_batch(sc, mic, 1, nqueries, out);
+    return micmap_build_batch(sc, mic, 1, nqueries, out, 0.0);
 }
 
 }  // namespace rvb

@@ -177,7 +177,8 @@ struct MicMapStorage {
     uint32_t entries = 0;
 };
 int micmap_build(const Scene *sc, const float mic[3], size_t nqueries, MicMapStorage *out);
-int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n, size_t nqueries, MicMapStorage *out /* [n] */);
+int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n, size_t nqueries, MicMapStorage *out /* [n] */,
+                       double forced_cells_per_tri = 0.0 /* RVB_TRACE_MAP_CELLS */);
 void micmap_free(MicMapStorage *s);
 
 // ---- stage entry points (defined in the .cu files) ----------------------------------------------

@@ -1405,7 +1405,7 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
         StageTimer t_mm("trace.micmap");
         std::vector<float> mics(3 * njobs);
         for (size_t j = 0; j < njobs; ++j) for (int i = 0; i < 3; ++i) mics[3 * j + i] = trs[j]->mic[i];
-        RVB_TRY(micmap_build_batch(sc, mics.data(), njobs, tr->nrays * std::max<size_t>(tr->nrefl, 1), mms.data()));
+        RVB_TRY(micmap_build_batch(sc, mics.data(), njobs, tr->nrays * std::max<size_t>(tr->nrefl, 1), mms.data(), (double)((tr->flags >> 16) & 0xffu)));
     }
     for (size_t j = 0; j < njobs; ++j) {
         Trace *t = trs[j];

@@ -26,6 +26,11 @@ def TRACE_UNITS(n):
     """BVH scenes, testing: cut every ray's steady-phase reflections into n work units (RVB_TRACE_UNITS)."""
     return (int(n) & 0xff) << 8
 
+
+def TRACE_MAP_CELLS(n):
+    """BVH scenes, testing: cells per triangle of the microphone visibility map (RVB_TRACE_MAP_CELLS)."""
+    return (int(n) & 0xff) << 16
+
 ACCEL_AUTO, ACCEL_BRUTE_FORCE, ACCEL_BVH = 0, 1, 2
 MODEL_SPEAKER, MODEL_HRTF = 0, 1
 

@@ -394,6 +394,31 @@ def test_image_dedupe_few_candidates_kernel_equals_sort_path():
         assert a[0] == b[0] and a[3] == b[3]
 
 
+def test_visibility_map_resolution_does_not_show():
+    """The microphone visibility map (micmap.cu) pre-selects, per cube-map cell, the triangles that can block
+    the segment hit point -> microphone; the reference's exact test then runs on those candidates.  Its
+    resolution is chosen from the query count (4 ... 48 cells per triangle, up to 1024 x 1024 cells per face at
+    C3's full size), so a 100k-triangle room with free-standing pillars (a third of the hit points do not see
+    the microphone) is traced with the coarsest, the default and the finest map: hits, counts and impulses must
+    be bit-identical (a cell that lost an occluder would turn a zero impulse into a non-zero one)."""
+    tri, vtx, srf = scenes.pillar_room(100_000, npillars=6, pillar_grid=24)
+    dirs = scenes.sphere_directions(100_000, seed=33)
+    out = []
+    for cells in (2, 0, 48):
+        rt = api.Raytracer(48, tri, vtx, srf)
+        tr = rt.raytrace((12.5, 1.4, 8.5), (2.0, 1.6, 2.5), dirs, flags=api.TRACE_DEBUG | api.TRACE_MAP_CELLS(cells))
+        st = tr.stats()
+        out.append((tr.debug(), tr.raw_diffuse().tobytes(), tr.raw_images(with_keys=True), st["micmap_cells"], st["emitted"], st["bounces"]))
+        rt.close()
+    assert out[0][3] < out[1][3] < out[2][3] and out[2][3] > 512       # three different grids, the last beyond 512 cells per edge
+    skipped = 1.0 - out[0][4] / out[0][5]
+    assert 0.05 < skipped < 0.95, skipped                               # occlusion really happens in this scene
+    for o in out[1:]:
+        assert np.array_equal(o[0][0], out[0][0][0]) and np.array_equal(o[0][1], out[0][0][1])
+        assert o[1] == out[0][1] and o[4] == out[0][4]
+        assert o[2][0].tobytes() == out[0][2][0].tobytes() and np.array_equal(o[2][1], out[0][2][1])
+
+
 def test_bvh_hall_100k_subsample_vs_oracle(orc):
     """C3 mesh (~100k triangles): a ray subsample against the CPU brute-force oracle."""
     tri, vtx, srf = scenes.concert_hall()
