@@ -32,7 +32,13 @@ struct MicMapParams {
 
 // cell rectangle of a triangle on one cube face + the projected (clipped) polygon and the margin it was
 // grown by, for the per-cell test
-struct FaceRect { uint32_t i0, i1, j0, j1; int np; float pu[4], pv[4], margin; };
+struct FaceRect {
+    uint32_t i0, i1, j0, j1;
+    int np; float pu[4], pv[4], margin;
+    // per-edge constants of the separating-edge test, worked out once per rectangle (prepare_edges)
+    int ne;                       // -1: reject nothing (degenerate polygon)
+    float nu[4], nv[4], thr[4];   // outward normal of edge k -> k+1 and the distance beyond which a cell is outside
+};
 
 __device__ __forceinline__ void grow_uv(float W, float U, float V, float delta, float &ulo, float &uhi, float &vlo, float &vhi, FaceRect &r)
 {
@@ -49,24 +55,36 @@ __device__ __forceinline__ void grow_uv(float W, float U, float V, float delta, 
 
 // Is cell (i, j) certainly outside the projected polygon grown by its margin?  (Separating-edge test
 // against the cell corner that lies deepest inside; a degenerate, edge-on polygon rejects nothing.)
-__device__ __forceinline__ bool cell_outside(const FaceRect &r, uint32_t i, uint32_t j, uint32_t N)
+// prepare_edges: the part that does not depend on the cell.
+__device__ __forceinline__ void prepare_edges(FaceRect &r)
 {
-    if (r.np < 3) return false;
-    const float h = 2.0f / (float)N;
-    const float cu0 = -1.0f + (float)i * h, cu1 = cu0 + h, cv0 = -1.0f + (float)j * h, cv1 = cv0 + h;
+    r.ne = -1;
+    if (r.np < 3) return;
     float area = 0.0f;
     for (int k = 0; k < r.np; ++k) { const int k1 = (k + 1) % r.np; area += r.pu[k] * r.pv[k1] - r.pu[k1] * r.pv[k]; }
-    if (fabsf(area) < 1e-12f) return false;
+    if (fabsf(area) < 1e-12f) return;
     const float sgn = area > 0.0f ? 1.0f : -1.0f;
+    r.ne = r.np;
     for (int k = 0; k < r.np; ++k) {
         const int k1 = (k + 1) % r.np;
         const float du = r.pu[k1] - r.pu[k], dv = r.pv[k1] - r.pv[k];
         const float nu = sgn * dv, nv = -sgn * du;               // outward normal of edge k -> k1
         const float len = sqrtf(nu * nu + nv * nv);
-        if (len == 0.0f) continue;
+        r.nu[k] = nu; r.nv[k] = nv;
+        // (the cell bounds are recomputed from the index, hence the 2e-5 on top of the map's own 1e-5 slack);
+        // a zero-length edge excludes nothing
+        r.thr[k] = len == 0.0f ? 3e38f : (r.margin + 3e-5f) * len * 1.0001f + 1e-7f;
+    }
+}
+__device__ __forceinline__ bool cell_outside(const FaceRect &r, uint32_t i, uint32_t j, uint32_t N)
+{
+    if (r.ne < 0) return false;
+    const float h = 2.0f / (float)N;
+    const float cu0 = -1.0f + (float)i * h, cu1 = cu0 + h, cv0 = -1.0f + (float)j * h, cv1 = cv0 + h;
+    for (int k = 0; k < r.ne; ++k) {
+        const float nu = r.nu[k], nv = r.nv[k];
         const float cu = nu > 0.0f ? cu0 : cu1, cv = nv > 0.0f ? cv0 : cv1;
-        // (the cell bounds above are recomputed from the index, hence the 2e-5 on top of the map's own 1e-5 slack)
-        if (nu * (cu - r.pu[k]) + nv * (cv - r.pv[k]) > (r.margin + 3e-5f) * len * 1.0001f + 1e-7f) return true;
+        if (nu * (cu - r.pu[k]) + nv * (cv - r.pv[k]) > r.thr[k]) return true;
     }
     return false;
 }
@@ -136,7 +154,7 @@ __global__ void __launch_bounds__(128) micmap_bin_kernel(const MicMapParams M, u
     if (lane < 6) {
         FaceRect r;
         ok = face_rect(p, (int)lane, M, r);
-        if (ok) s_rect[warp][lane] = r;
+        if (ok) { prepare_edges(r); s_rect[warp][lane] = r; }
     }
     const uint32_t valid = __ballot_sync(0xffffffffu, ok);
     __syncwarp();

@@ -11,9 +11,11 @@ timeout 600 python bench.py --impl reference > $O/default_reference_cpu.json 2> 
 for wl in C1_vault_3754tri_1024x64 C5_hall_64pairs_16kx128; do
   timeout 600 python bench.py --workload $wl --steps 3 --no-cpu-baseline > $O/${wl}_1gpu.json 2> $O/${wl}_1gpu.err
 done
+# C4's mesh and output model on one GPU at a reduced ray count (the full 4 Mi x 256 is the 8-GPU configuration)
+timeout 900 python bench.py --workload C4_cathedral_1Mtri_4Mx256_hrtf --rays 262144 --steps 2 --no-cpu-baseline > $O/C4_cathedral_262kx256_1gpu.json 2> $O/C4_cathedral_262kx256_1gpu.err
 # the shard-sized problem of the 8-GPU run (131072 rays) on one GPU: where a shard's time goes
 timeout 600 python bench.py --rays 131072 --no-cpu-baseline --no-sub-blocks > $O/C3_shard131k_1gpu.json 2> $O/C3_shard131k_1gpu.err
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sub-blocks"
 timeout 600 $CMD > $O/plain_for_ncu.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/launches.csv $CMD > $O/ncu_list.log 2>&1
 CMD4="python bench.py --rays 131072 --steps 1 --warmup 3 --no-cpu-baseline --no-sub-blocks"
 timeout 600 $CMD4 > $O/plain_for_ncu4.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"wavefront|trace_bvh_kernel|reduce_cta|iir_kernel|FlattenIn" -c 10 -o /tmp/prof_c3_kernels -f $CMD4 > $O/ncu_full_c3.log 2>&1
