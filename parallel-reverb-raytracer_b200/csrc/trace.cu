@@ -918,7 +918,7 @@ static int occupancy_of(K kernel, int block, size_t smem, int &per_sm)
 }
 
 template <class K>
-static int launch_phase(K kernel, const TraceParams &P, const TraceJob &J0, int block, size_t smem, cudaStream_t st)
+static int launch_phase(K kernel, const TraceParams &P, const TraceJob &J0, int block, size_t smem, cudaStream_t st, bool full_grid = false)
 {
     int per_sm = 0;
     RVB_TRY(occupancy_of(kernel, block, smem, per_sm));
@@ -926,7 +926,9 @@ static int launch_phase(K kernel, const TraceParams &P, const TraceJob &J0, int 
     // grid.y = job; the resident CTAs are shared out among the jobs
     const size_t want = ((size_t)P.nrays + block - 1) / block;
     const size_t share = std::max<size_t>(1, ((size_t)per_sm * sm_count() + P.njobs - 1) / P.njobs);
-    const size_t grid = std::max<size_t>(1, std::min(want, share));
+    // full_grid: one CTA per `block` rays, handed out by the hardware as SMs free up, instead of a resident
+    // grid striding over the rays -- for kernels without per-CTA set-up whose rays differ a lot in cost
+    const size_t grid = std::max<size_t>(1, full_grid ? want : std::min(want, share));
     note_launch(), kernel<<<dim3((unsigned)grid, P.njobs), block, smem, st>>>(P, J0);
     RVB_CUDA(cudaGetLastError());
     return RVB_OK;
@@ -946,6 +948,8 @@ static int try_block(const TraceParams &P, size_t smem, int &per_sm)
 template <bool IMAGES, int BLOCK>
 static int launch_block(const TraceParams &P, const TraceJob &J0, size_t smem, cudaStream_t st)
 {
+    // (one CTA per BLOCK rays instead of a resident grid, as in launch_bvh_images, changes nothing for the
+    // shoebox's image phase: 1.70 ms either way)
     if (P.njobs > 1) return launch_phase(trace_bruteforce_kernel<IMAGES, BLOCK, true>, P, J0, BLOCK, smem, st);
     return launch_phase(trace_bruteforce_kernel<IMAGES, BLOCK, false>, P, J0, BLOCK, smem, st);
 }
@@ -1334,9 +1338,13 @@ static int launch_bvh_images(const TraceParams &P, const TraceJob &J0, size_t sm
     // registers capped at 128 for 4 CTAs per SM instead of 3 (136 registers uncapped, RVB_IMG_MINB=1): 5.25 -> 4.76 ms
     // on C3's 1 Mi rays, 1.24 -> 1.20 ms on a 131 k-ray shard
     static const int minb = getenv("RVB_IMG_MINB") ? atoi(getenv("RVB_IMG_MINB")) : 4;
-    if (P.njobs > 1) return launch_phase(trace_bvh_kernel<true, 1, true>, P, J0, 128, smem, st);
-    if (minb == 4) return launch_phase(trace_bvh_kernel<true, 4, false>, P, J0, 128, smem, st);
-    return launch_phase(trace_bvh_kernel<true, 1, false>, P, J0, 128, smem, st);
+    // The image phase's rays differ widely in cost (how many image sources survive validation), so its CTAs are
+    // dispatched one per 128 rays rather than striding (C3: 4.79 -> 4.32 ms for map + image phase; RVB_IMG_STRIDE=1
+    // restores the resident grid)
+    static const bool full = !(getenv("RVB_IMG_STRIDE") && *getenv("RVB_IMG_STRIDE") == '1');
+    if (P.njobs > 1) return launch_phase(trace_bvh_kernel<true, 1, true>, P, J0, 128, smem, st, full);
+    if (minb == 4) return launch_phase(trace_bvh_kernel<true, 4, false>, P, J0, 128, smem, st, full);
+    return launch_phase(trace_bvh_kernel<true, 1, false>, P, J0, 128, smem, st, full);
 }
 
 int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const CandBuffers *cands)
