@@ -170,6 +170,7 @@ static int dedupe_small(Trace *tr, const float4 *cvA, const float4 *cvB, const f
     RVB_TRY(dev_alloc(&tr->d_img_volB, n));
     RVB_TRY(dev_alloc(&tr->d_img_pt, n));
     uint32_t *d_out = nullptr;
+    const auto cleanup = on_scope_exit([&] { dev_free(d_out); });
     const size_t words = 1 + (size_t)n * (1 + RVB_NUM_IMAGE_SOURCE);
     RVB_TRY(dev_alloc(&d_out, words));
     const size_t smem = ((size_t)RVB_DEDUPE_COLS + 1) * n * sizeof(uint32_t);
@@ -178,7 +179,6 @@ static int dedupe_small(Trace *tr, const float4 *cvA, const float4 *cvB, const f
     RVB_CUDA(cudaGetLastError());
     std::vector<uint32_t> h(words);
     RVB_TRY(read_back(h.data(), d_out, words * sizeof(uint32_t)));
-    dev_free(d_out);
     const uint32_t m = h[0];
     tr->img_len.resize(m);
     tr->img_keys.resize((size_t)m * RVB_NUM_IMAGE_SOURCE);
@@ -199,38 +199,42 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     const uint32_t nflat = (uint32_t)nflat64;
 
     uint32_t *d_sel = nullptr, *d_nsel = nullptr;
+    uint32_t *d_perm[2] = {nullptr, nullptr}, *d_keys[2] = {nullptr, nullptr};
+    unsigned long long *d_k64[2] = {nullptr, nullptr};
+    uint8_t *d_head = nullptr;
+    uint32_t *d_okeys = nullptr;
+    int32_t *d_olen = nullptr;
+    const auto cleanup = on_scope_exit([&] {
+        dev_free(d_okeys); dev_free(d_olen); dev_free(d_head);
+        for (int i = 0; i < 2; ++i) { dev_free(d_perm[i]); dev_free(d_keys[i]); dev_free(d_k64[i]); }
+        dev_free(d_sel); dev_free(d_nsel);
+    });
     RVB_TRY(dev_alloc(&d_sel, nflat));
     RVB_TRY(dev_alloc(&d_nsel, 1));
     CandValid pred{cidx, tr->ray_offset};
     RVB_TRY(compact_indices(pred, nflat, d_sel, d_nsel, st));
     uint32_t n = 0;
     RVB_TRY(read_back(&n, d_nsel, sizeof n));
-    if (n == 0) { dev_free(d_sel); dev_free(d_nsel); return RVB_OK; }
+    if (n == 0) return RVB_OK;
     if (n <= RVB_DEDUPE_SMALL && !(tr->flags & RVB_TRACE_SORT_DEDUPE)) {
-        const int rc = dedupe_small(tr, cvA, cvB, cpt, cidx, d_sel, n, st);
-        dev_free(d_sel); dev_free(d_nsel);
-        return rc;
+        return dedupe_small(tr, cvA, cvB, cpt, cidx, d_sel, n, st);
     }
 
-    uint32_t *d_perm[2] = {nullptr, nullptr}, *d_keys[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) { RVB_TRY(dev_alloc(&d_perm[i], n)); RVB_TRY(dev_alloc(&d_keys[i], n)); }
     const unsigned blk = 256, grd = (n + blk - 1) / blk;
     int end_bit = 1;
     while ((1ull << end_bit) < (unsigned long long)tr->scene->T + 2ull) ++end_bit;
     int cur = 0;
     const uint32_t last_col = (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl);
-    uint8_t *d_head = nullptr;
     RVB_TRY(dev_alloc(&d_head, n));
     if ((uint32_t)end_bit * last_col <= 64u) {
         // small scenes: every key fits one 64-bit word -> ONE radix sort instead of one per column
         // (stable, so the lowest ray still comes first within equal keys)
-        unsigned long long *d_k64[2] = {nullptr, nullptr};
         for (int i = 0; i < 2; ++i) RVB_TRY(dev_alloc(&d_k64[i], n));
         note_launch(), packed_keys_kernel<<<grd, blk, 0, st>>>(cidx, d_sel, n, last_col, (uint32_t)end_bit, d_k64[1], d_perm[1]);
         const int rc_sort = rsort::sort_arrays<unsigned long long>(d_k64, d_perm, n, 0, end_bit * (int)last_col, &cur, st);
         RVB_TRY(rc_sort);
         note_launch(), head_flags_packed_kernel<<<grd, blk, 0, st>>>(d_k64[cur], n, d_head);
-        for (int i = 0; i < 2; ++i) dev_free(d_k64[i]);
     } else {
         cur = 1;
         note_launch(), iota_kernel<<<grd, blk, 0, st>>>(d_perm[cur], n);
@@ -251,8 +255,6 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     RVB_TRY(dev_alloc(&tr->d_img_volA, m));
     RVB_TRY(dev_alloc(&tr->d_img_volB, m));
     RVB_TRY(dev_alloc(&tr->d_img_pt, m));
-    uint32_t *d_okeys = nullptr;
-    int32_t *d_olen = nullptr;
     RVB_TRY(dev_alloc(&d_okeys, (size_t)m * RVB_NUM_IMAGE_SOURCE));
     RVB_TRY(dev_alloc(&d_olen, m));
     note_launch(), gather_unique_kernel<<<(m + blk - 1) / blk, blk, 0, st>>>(cidx, d_sel, d_perm[cur], d_upos, m, cvA, cvB, cpt, tr->d_img_volA,
@@ -264,9 +266,6 @@ int images_dedupe(Trace *tr, const float4 *cvA, const float4 *cvB, const float4 
     RVB_TRY(read_back(tr->img_len.data(), d_olen, m * sizeof(int32_t)));
     tr->n_images = m;
     tr->first_is_direct = (m > 0 && tr->img_len[0] == 1);   // key {0} sorts first when present
-    dev_free(d_okeys); dev_free(d_olen); dev_free(d_head);
-    for (int i = 0; i < 2; ++i) { dev_free(d_perm[i]); dev_free(d_keys[i]); }
-    dev_free(d_sel); dev_free(d_nsel);
     return RVB_OK;
 }
 

@@ -12,6 +12,7 @@
 // a bin) followed by a segmented reduction with a fixed lane assignment and a fixed shuffle
 // tree: no float atomics, bit-identical from run to run.
 #include <cmath>
+#include <memory>
 #include <type_traits>
 
 #include "attenuate.cuh"
@@ -1356,7 +1357,7 @@ int rvb_render_ir(rvb_trace *tr, const rvb_render_config *cfg, rvb_ir **out)
         RVB_TRY(make_channels(tr->mic, cfg, cs));
     }
     g_stats.n_impulses = (uint64_t)S.n_diffuse + S.n_images;
-    StageTimer *t_t = new StageTimer("render.times");
+    std::unique_ptr<StageTimer> t_t(new StageTimer("render.times"));
     // per-channel time extrema -> predelay (min over all channels) and flatten lengths
     std::vector<float> mn(cs.nch), mx(cs.nch);
     int last_group = -1;
@@ -1373,7 +1374,7 @@ int rvb_render_ir(rvb_trace *tr, const rvb_render_config *cfg, rvb_ir **out)
     std::vector<size_t> lengths(cs.nch);
     size_t total = 0;
     for (size_t c = 0; c < cs.nch; ++c) { lengths[c] = flatten_length(mx[c], predelay, fix, cfg->sample_rate); total += RVB_NBANDS * lengths[c]; }
-    delete t_t;
+    t_t.reset();
     float *d_hist = nullptr;
     RVB_TRY(dev_alloc(&d_hist, total));
     int rc;

@@ -62,6 +62,19 @@ inline void dev_free(T *&p)
     p = nullptr;
 }
 
+// Runs `f` when the enclosing scope ends -- on every early return of RVB_TRY / RVB_CUDA too: the
+// temporary device blocks and events of a call are released on its error paths as well.
+template <class F>
+struct ScopeExit {
+    F f;
+    explicit ScopeExit(F g) : f(g) {}
+    ~ScopeExit() { f(); }
+    ScopeExit(const ScopeExit &) = delete;
+    ScopeExit &operator=(const ScopeExit &) = delete;
+};
+template <class F>
+inline ScopeExit<F> on_scope_exit(F f) { return ScopeExit<F>(f); }
+
 // order-preserving float <-> int keys for atomicMin / atomicMax on floats
 __host__ __device__ inline int ordered_key(float f) { int i; memcpy(&i, &f, 4); return i ^ ((i >> 31) & 0x7fffffff); }
 __host__ __device__ inline float unordered_key(int i) { i = i ^ ((i >> 31) & 0x7fffffff); float f; memcpy(&f, &i, 4); return f; }

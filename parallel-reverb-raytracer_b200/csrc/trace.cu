@@ -1,14 +1,16 @@
 // The bounce kernels: B200-native replacement of `kernel raytrace` (rayverb/kernel.cpp:304-503).
 //
-// One thread per ray (one WARP per ray when there are few rays and many triangles), persistent
-// grid-stride over rays, in two kernels:
+// Two kernels per trace:
 //
 //   image phase    reflections 0..8: the part of the reference loop that carries the image-source
 //                  branch (kernel.cpp:379-457: mirrored triangles, validation queries, add_image).
-//                  Heavy, divergent, 7 % of the reflections.
-//   steady phase   reflections 9..: nearest hit -> visibility -> emit -> reflect, one inlined copy
-//                  of each query loop so the hot code stays instruction-cache resident and the
-//                  lanes of a warp stay in lock step.
+//                  Heavy, divergent, 7 % of the reflections.  One thread per ray.
+//   steady phase   reflections 9..: nearest hit -> visibility -> emit -> reflect.  Brute-force scenes:
+//                  one thread per ray (one WARP per ray when there are few rays and many triangles),
+//                  persistent grid-stride over rays, one inlined copy of each query loop so the hot code
+//                  stays instruction-cache resident and the lanes of a warp stay in lock step.  BVH
+//                  scenes: persistent warps whose lanes are independent state machines drawing work
+//                  units -- pieces of rays -- from a queue (trace_bvh_wavefront_kernel below).
 //
 // The ray state (position, direction, path length, 8-band volume) passes between them through a
 // 64-byte record per ray.  The scene is staged once per CTA in shared memory in pair-interleaved
@@ -1283,6 +1285,7 @@ static int launch_wavefront(const TraceParams &P_in, const TraceJob &J0, size_t 
     const bool batch = P.njobs > 1;
     unsigned int *d_fetch = nullptr;   // one ray counter per job
     unsigned int *d_done = nullptr;
+    const auto cleanup = on_scope_exit([&] { dev_free(d_fetch); dev_free(d_done); });   // d_done: unless handed to the caller
     RVB_TRY(dev_alloc(&d_fetch, (size_t)P.njobs));
     RVB_CUDA(cudaMemsetAsync(d_fetch, 0, P.njobs * sizeof(unsigned int), st));
     auto go = [&](auto kernel, auto kernel_seg) -> int {
@@ -1328,8 +1331,7 @@ static int launch_wavefront(const TraceParams &P_in, const TraceJob &J0, size_t 
     default: rc = batch ? go(trace_bvh_wavefront_kernel<5, true, false>, trace_bvh_wavefront_kernel<5, true, false>)
                         : go(trace_bvh_wavefront_kernel<5, false, false>, trace_bvh_wavefront_kernel<5, false, true>); break;
     }
-    *done_out = d_done;   // the caller reads the error flag with its own end-of-trace read-back, then frees it
-    dev_free(d_fetch);
+    if (rc == RVB_OK) { *done_out = d_done; d_done = nullptr; }   // the caller reads the error flag with its end-of-trace read-back, then frees it
     return rc;
 }
 
@@ -1363,6 +1365,22 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     for (int b = 0; b < RVB_NBANDS; ++b) P.air[b] = (float)air[b];
     P.flags = tr->flags;
     unsigned long long *d_counters = nullptr;   // six per job; [4] holds the two ordered time keys
+    float4 *d_state = nullptr;
+    unsigned int *d_wf_done = nullptr;
+    TraceJob *d_jobs = nullptr;
+    uint16_t *d_perm_keys[2] = {nullptr, nullptr};
+    uint32_t *d_perm_ids[2] = {nullptr, nullptr};
+    cudaEvent_t e0 = nullptr, e1 = nullptr, em = nullptr;
+    std::vector<MicMapStorage> mms(njobs);
+    // everything this call allocates is temporary: released on every way out
+    const auto cleanup = on_scope_exit([&] {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        if (em) cudaEventDestroy(em);
+        dev_free(d_counters); dev_free(d_state); dev_free(d_jobs); dev_free(d_wf_done);
+        for (size_t j = 0; j < njobs; ++j) micmap_free(&mms[j]);
+        for (int i = 0; i < 2; ++i) { dev_free(d_perm_keys[i]); dev_free(d_perm_ids[i]); }
+    });
     RVB_TRY(dev_alloc(&d_counters, 6 * njobs));
     {
         std::vector<unsigned long long> init(6 * njobs, 0ull);
@@ -1373,8 +1391,6 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
 
     const bool images = !(tr->flags & RVB_TRACE_NO_IMAGES);
     const uint32_t split = images ? (uint32_t)std::min<size_t>(RVB_NUM_IMAGE_SOURCE - 1, tr->nrefl) : 0u;
-    float4 *d_state = nullptr;
-    unsigned int *d_wf_done = nullptr;
     const bool brute = sc->accel == RVB_ACCEL_BRUTE_FORCE;
     // BVH scenes, steady phase: the persistent wavefront kernel (launch_wavefront); RVB_WAVEFRONT=0 selects
     // the one-thread-per-ray kernel for comparison.  Measured on the C3 hall with 64-byte nodes
@@ -1386,8 +1402,6 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     const size_t smem = brute ? (size_t)9 * sc->nquads * sizeof(float4) : (size_t)sc->bvh_stack * RVB_BVH_CTA * sizeof(int);
 
     // processing order of the image phase: rays sorted by direction cell (the jobs share the directions)
-    uint16_t *d_perm_keys[2] = {nullptr, nullptr};
-    uint32_t *d_perm_ids[2] = {nullptr, nullptr};
     if (split > 0 && tr->nrays >= 4096) {
         const uint32_t n = (uint32_t)tr->nrays;
         RVB_TRY(dev_alloc(&d_perm_keys[0], n));
@@ -1399,7 +1413,6 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
         RVB_TRY(rc_sort);
         P.ray_perm = d_perm_ids[cur];
     }
-    cudaEvent_t e0, e1, em;
     RVB_CUDA(cudaEventCreate(&e0));
     RVB_CUDA(cudaEventCreate(&e1));
     RVB_CUDA(cudaEventCreate(&em));
@@ -1407,7 +1420,6 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     RVB_CUDA(cudaEventRecord(e0, st));
     // The job records.  BVH scenes: the visibility map around every job's microphone (rebuilt for every
     // trace: it is part of the measured work, not a cache).
-    std::vector<MicMapStorage> mms(njobs);
     std::vector<TraceJob> jobs(njobs);
     if (!brute && tr->nrays > 0) {
         StageTimer t_mm("trace.micmap");
@@ -1428,7 +1440,6 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
         J.time_ext = reinterpret_cast<int *>(d_counters + 6 * j + 4);
         t->stats.micmap_cells = mms[j].map.N; t->stats.micmap_entries = mms[j].entries;
     }
-    TraceJob *d_jobs = nullptr;
     RVB_TRY(dev_alloc(&d_jobs, njobs));
     RVB_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), njobs * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
     RVB_CUDA(cudaStreamSynchronize(st));
@@ -1464,17 +1475,10 @@ int trace_launch(Trace *const *trs, size_t njobs, const float4 *d_dirs, const Ca
     unsigned int wf_error = 0;   // segmented wavefront kernel: a pending unit ran out of its poll budget
     if (d_wf_done) RVB_CUDA(cudaMemcpyAsync(&wf_error, d_wf_done + tr->nrays, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     RVB_CUDA(cudaStreamSynchronize(st));
-    dev_free(d_wf_done);
     float ms = 0.f, ms_image = 0.f, ms_steady = 0.f;
     RVB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     RVB_CUDA(cudaEventElapsedTime(&ms_image, e0, em));
     RVB_CUDA(cudaEventElapsedTime(&ms_steady, em, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(em);
-    dev_free(d_counters);
-    dev_free(d_state);
-    dev_free(d_jobs);
-    for (size_t j = 0; j < njobs; ++j) micmap_free(&mms[j]);
-    for (int i = 0; i < 2; ++i) { dev_free(d_perm_keys[i]); dev_free(d_perm_ids[i]); }
     for (size_t j = 0; j < njobs; ++j) {
         Trace *t = trs[j];
         const unsigned long long *h = h_end.data() + 6 * j, *hm = h_mid.data() + 6 * j;

@@ -30,8 +30,8 @@ def rel_l2(a, b):
 
 def assert_filter_close(got, want, what):
     """The chunk-parallel IIR runs the reference's own double recurrence inside every 16-sample
-    chunk; the chunk start states come from a three-level scan with powers of the state-transition
-    matrix, which is associated differently from the serial filter (double precision, but with
+    chunk; the chunk start states come from shuffle scans (lanes, warps) and a fold over the tiles with
+    powers of the state-transition matrix, which is associated differently from the serial filter (double precision, but with
     cancellation between large terms for the low bands' near-unit poles).  A start state that is off
     by ~1e-13 relative occasionally flips the float rounding of one output sample, and that one-ulp
     difference feeds the later sweeps of a two-pass / Linkwitz-Riley chain.  Bar: every sample
