@@ -66,8 +66,8 @@ int rvb_version(void);
  * of the library's own; use = 0 switches back.  The reference has one in-order queue per object
  * (rayverb.cpp:190-191). */
 int rvb_set_stream(void *cuda_stream, int use);
-/* number of kernels this library has launched so far in the process (CUB's sort/select passes
- * are not counted) */
+/* number of kernels this library has launched so far in the process (every kernel it launches is its own:
+ * there are no library sort / select passes) */
 unsigned long long rvb_launch_count(void);
 /* Device blocks of 1 MiB and more are kept in an exact-size cache when a trace / render frees them, so that
  * the next trace of the same shape re-uses them (the reference re-creates its cl::Buffers for every group
