@@ -123,6 +123,38 @@ def test_c3_hall_100k_triangles_1m_rays_properties():
                     speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], ft="linkwitz_riley", lo_cutoff=45.0)
 
 
+def test_c3_full_size_histogram_does_not_depend_on_work_units_or_map_resolution():
+    """C3 at full size (1 Mi rays x 128 on ~100k triangles): the wavefront kernel cuts the rays into work units
+    and the visibility map takes its finest resolution (48 cells per triangle, 894 x 894 cells per face) only
+    at this size.  Neither is allowed to show: whole rays with the 16-cell map, the launcher's own choices, and
+    16 units with a 4-cell map must give bit-identical histograms (every impulse in the same bin with the same
+    bits -- the flatten is deterministic)."""
+    api.set_device(0)
+    tri, vtx, srf = scenes.concert_hall()
+    nrays, nrefl = 1 << 20, 128
+    d_dirs = torch.from_numpy(scenes.sphere_directions(nrays, seed=2015)).cuda()
+    cfg, keep = api.make_render_config(sr=SR, speakers=[((-1, 0, -1), 0.5), ((1, 0, -1), 0.5)], ft="linkwitz_riley", lo_cutoff=45.0)
+    rt = api.Raytracer(nrefl, tri, vtx, srf)
+    ref, ref_stats = None, None
+    for flags in (api.TRACE_UNITS(1) | api.TRACE_MAP_CELLS(16), 0, api.TRACE_UNITS(16) | api.TRACE_MAP_CELLS(4)):
+        tr = rt.raytrace((24, 1.5, 18), (20, 2.0, 4), None, device_ptr=d_dirs.data_ptr(), nrays=nrays, flags=flags)
+        st = tr.stats()
+        mn, mx = tr.render_times(cfg)
+        predelay = sharding._fold_predelay([float(v) for v in mn])
+        lengths = [sharding.flatten_length(float(m), predelay, False, SR) for m in mx]
+        hist = _histogram(tr, cfg, predelay, lengths)
+        key = (st["bounces"], st["emitted"], st["queries"], tuple(lengths))
+        if ref is None:
+            ref, ref_stats = hist.clone(), key
+            assert st["micmap_cells"] <= 520
+        else:
+            assert key == ref_stats
+            assert torch.equal(ref.view(torch.int32), hist.view(torch.int32))
+            if flags == 0:
+                assert st["micmap_cells"] > 800          # the finest map really was used
+    rt.close()
+
+
 def test_full_size_run_contains_the_oracle_subsample(orc):
     """Rays [0, 256) of the 1 Mi-ray C2 run: hit sequences, positions and times equal the oracle's
     bit for bit.  (The run is traced with TRACE_DEBUG on a 64 k-ray prefix to bound the copy-out;
