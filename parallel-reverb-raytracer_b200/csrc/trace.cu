@@ -475,6 +475,73 @@ struct BvhAccel {
         c.queries++; c.tri += ntri;
         return blocked;
     }
+
+    // The same query for a whole warp at once (wavefront kernel).  In the per-lane form above the lanes of
+    // a warp hold 1..12 candidates each and wait for the longest list: 7.1 of 25 serving lanes were active in
+    // that loop, which -- two dependent load latencies per iteration -- was 16 % of the kernel's stall samples
+    // (ncu source page, profiles/r2_wavefront_source_hotspots.md).  Here the (query, candidate pair) items of all
+    // serving lanes are numbered through (inclusive scan of the item counts) and dealt to ALL 32 lanes, which
+    // fetch their item's query from its owner by shuffle: ceil(items / 32) iterations instead of the longest
+    // list's.  The test itself is the one above on the same operands, the answer an OR -- so the same bits.
+    // q: this lane has a query; e0 / ne: its cell's entry range (micmap_lookup); returns blocked for q lanes.
+    __device__ __forceinline__ void micmap_lookup(f3 begin, uint32_t &e0, uint32_t &ne) const
+    {
+        const f3 w = mk3(begin.x - mm.mic[0], begin.y - mm.mic[1], begin.z - mm.mic[2]);
+        const uint32_t cell = micmap_cell(w, mm.half_n, mm.N);
+        e0 = __ldg(mm.cell_off + cell);
+        ne = __ldg(mm.cell_off + cell + 1) - e0;
+    }
+    __device__ __forceinline__ bool warp_occluded_to_mic(bool q, f3 begin, f3 dir, float mag, uint32_t e0, uint32_t ne,
+                                                         uint32_t *s_inc /* [32], this warp's */, uint32_t *s_blk /* this warp's */) const
+    {
+        const unsigned FULL = 0xffffffffu;
+        const uint32_t lane = threadIdx.x & 31u;
+        const uint32_t ntri = ne + mm.n_near;
+        const uint32_t items = q ? (ntri + 1u) >> 1 : 0u;
+        uint32_t inc = items;
+#pragma unroll
+        for (uint32_t o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
+        s_inc[lane] = inc;
+        if (lane == 0) *s_blk = 0u;
+        __syncwarp();
+        for (uint32_t base = 0; base < total; base += 32u) {
+            const uint32_t item = base + lane;
+            const bool act = item < total;
+            // owner: the first lane whose inclusive count exceeds the item number (it has items, by construction)
+            uint32_t lo = 0;
+            if (act) {
+#pragma unroll
+                for (uint32_t step = 16; step; step >>= 1)
+                    if (s_inc[lo + step - 1] <= item) lo += step;
+            }
+            const uint32_t oe0 = __shfl_sync(FULL, e0, lo), one = __shfl_sync(FULL, ne, lo);
+            const f3 ob = mk3(__shfl_sync(FULL, begin.x, lo), __shfl_sync(FULL, begin.y, lo), __shfl_sync(FULL, begin.z, lo));
+            const f3 od = mk3(__shfl_sync(FULL, dir.x, lo), __shfl_sync(FULL, dir.y, lo), __shfl_sync(FULL, dir.z, lo));
+            const float omag = __shfl_sync(FULL, mag, lo);
+            if (act) {
+                const uint32_t ontri = one + mm.n_near;
+                const uint32_t k0 = 2u * (item - (lo ? s_inc[lo - 1] : 0u));
+                const uint32_t ka = k0, kb = min(k0 + 1, ontri - 1);
+                const uint32_t ia = ka < one ? __ldg(mm.cell_ent + oe0 + ka) : __ldg(mm.near_ent + (ka - one));
+                const uint32_t ib = kb < one ? __ldg(mm.cell_ent + oe0 + kb) : __ldg(mm.near_ent + (kb - one));
+                const float4 *pa = tri + 3 * (size_t)ia, *pb = tri + 3 * (size_t)ib;
+                const float4 Aa = __ldg(pa), Ba = __ldg(pa + 1), Ab = __ldg(pb), Bb = __ldg(pb + 1);
+                const float Ca = __ldg(reinterpret_cast<const float *>(pa + 2)), Cb = __ldg(reinterpret_cast<const float *>(pb + 2));
+                bool oka, okb;
+                const float ta = mt_intersect_pred(mk3(Aa.x, Aa.y, Aa.z), mk3(Aa.w, Ba.x, Ba.y), mk3(Ba.z, Ba.w, Ca), ob, od, oka);
+                const float tb = mt_intersect_pred(mk3(Ab.x, Ab.y, Ab.z), mk3(Ab.w, Bb.x, Bb.y), mk3(Bb.z, Bb.w, Cb), ob, od, okb);
+                if ((oka && ta > RVB_EPSILON && ta <= omag) | (okb && tb > RVB_EPSILON && tb <= omag)) atomicOr(s_blk, 1u << lo);
+            }
+        }
+        __syncwarp();
+        const bool blocked = ((*s_blk >> lane) & 1u) != 0u;
+        __syncwarp();   // the scratch is reused by the next call
+        return blocked;
+    }
 };
 
 // kernel.cpp:195-214: pow(M_E, distance * AIR) * 1, with M_E narrowed to float, for two bands at
@@ -505,7 +572,9 @@ __device__ __noinline__ float pow_e_slow(float x) { return powf(RVB_M_E_F, x); }
 // All eight bands, as four pairs.  The exponents distance * AIR are <= 0 (distance >= 0, every
 // AIR < 0, rayverb.cpp:632-641) and AIR[7] is the most negative, so one test on band 7 covers the
 // fast path's range for all of them; NaN, negative distances and exponents below -83 (result <
-// 2^-120) take the library powf.
+// 2^-120) take the library powf -- band pair by band pair: after ~1400 m of path (the last of 128
+// reflections in a large hall) band 7 leaves the fast path's range, and sending every band of such a
+// lane through powf made its whole warp wait (2 % of the wavefront kernel's stall samples).
 __device__ __forceinline__ void air_attenuation(float distance, const float *air, float2 *att)
 {
     const float worst = __fmul_rn(__fmul_rn(distance, air[RVB_NBANDS - 1]), 1.4426950216293335f);
@@ -514,8 +583,11 @@ __device__ __forceinline__ void air_attenuation(float distance, const float *air
         for (int b = 0; b < RVB_NBANDS / 2; ++b) att[b] = pow_e_pair(__fmul2_rn(bcast2(distance), make_float2(air[2 * b], air[2 * b + 1])));
     } else {
 #pragma unroll
-        for (int b = 0; b < RVB_NBANDS / 2; ++b)
-            att[b] = make_float2(pow_e_slow(__fmul_rn(distance, air[2 * b])), pow_e_slow(__fmul_rn(distance, air[2 * b + 1])));
+        for (int b = 0; b < RVB_NBANDS / 2; ++b) {
+            const float w = __fmul_rn(__fmul_rn(distance, air[2 * b + 1]), 1.4426950216293335f);   // the pair's more negative exponent
+            if (w > -120.0f && distance >= 0.0f) att[b] = pow_e_pair(__fmul2_rn(bcast2(distance), make_float2(air[2 * b], air[2 * b + 1])));
+            else att[b] = make_float2(pow_e_slow(__fmul_rn(distance, air[2 * b])), pow_e_slow(__fmul_rn(distance, air[2 * b + 1])));
+        }
     }
 }
 
@@ -569,9 +641,13 @@ struct RayState {
 // kernel.cpp:459-501: everything a reflection does after the nearest hit is known
 // `next`: with a fused accelerator (Accel::kFused) and next->want, the visibility sweep also answers
 // the nearest-hit query of the reflected ray (see BruteSmem::visible_and_next).
+// `pre`: the visibility of the hit point was already worked out by the caller (BvhAccel::warp_occluded_to_mic);
+// ntri = the candidates that query tested, for the counters.
+struct PreVisibility { bool visible; uint32_t ntri; };
 template <class Accel>
 __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceParams &P, const TraceJob &J, f3 mic, uint32_t ray, uint32_t index,
-                                                  float tclosest, uint32_t prim, RayState &R, Counters &c, NextHit *next = nullptr)
+                                                  float tclosest, uint32_t prim, RayState &R, Counters &c, NextHit *next = nullptr,
+                                                  const PreVisibility *pre = nullptr)
 {
     const f3 X = madd(R.pos, R.dir, tclosest);                               // :459
     const float newDist = __fadd_rn(R.distance, tclosest);
@@ -593,7 +669,8 @@ __device__ __forceinline__ void shade_and_reflect(const Accel &acc, const TraceP
             const float mag = length(btp);
             vis = !acc.visible_and_next(X, normalize(btp), mag, newDir, *next, c);
         } else vis = point_visible(acc, X, mic, c);
-    } else vis = point_visible(acc, X, mic, c);                              // :463
+    } else if (pre) { vis = pre->visible; c.queries++; c.tri += pre->ntri; }
+    else vis = point_visible(acc, X, mic, c);                                // :463
     const float DIST = vis ? __fadd_rn(newDist, length(mic - X)) : 0.0f;     // :471
     const float DIFF = fabsf(dot(normal, R.dir));                            // :478
     float2 out[RVB_NBANDS / 2];
@@ -1044,6 +1121,7 @@ struct WfShared {
     float distance[128], tmin_nz[128], tmax[128];
     uint32_t ray[128], index[128], queries[128], bounces[128], emitted[128], tri[128];
     uint32_t end[128];        // the reflection index at which the lane's current work unit ends
+    uint32_t vis_inc[4][32], vis_blk[4];   // scratch of the warp-wide visibility query (BvhAccel::warp_occluded_to_mic)
 };
 
 // Segmented rays (SEG).  With fewer than a few waves of rays per launch -- a shard of an 8-GPU run
@@ -1110,6 +1188,26 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
 
     while (true) {
         // ---- serve: completed queries -------------------------------------------------------
+        // their visibility queries first, all lanes of the warp sharing the candidate tests
+        PreVisibility pv{false, 0u};
+        bool have_pv = false;
+        if (acc.mm.N != 0u && __any_sync(FULL, has && node == RVB_SENTINEL)) {   // warp-uniform
+            const bool q = has && node == RVB_SENTINEL && ibest != RVB_NONE;
+            f3 X = pos, vdir = dir;
+            float mag = 0.0f;
+            uint32_t e0 = 0, ne = 0;
+            if (q) {
+                const f3 mic = mk3(J.mic[0], J.mic[1], J.mic[2]);
+                X = madd(pos, dir, tbest);                       // the hit point, as shade_and_reflect computes it
+                const f3 btp = mic - X;                          // point_visible's operands
+                mag = length(btp);
+                vdir = normalize(btp);
+                acc.micmap_lookup(X, e0, ne);
+            }
+            const bool blocked = acc.warp_occluded_to_mic(q, X, vdir, mag, e0, ne, S.vis_inc[warp], &S.vis_blk[warp]);
+            pv.visible = !blocked; pv.ntri = ne + acc.mm.n_near;
+            have_pv = q;
+        }
         if (has && node == RVB_SENTINEL) {
             const uint32_t ray = S.ray[tid];
             uint32_t index = S.index[tid];
@@ -1122,7 +1220,7 @@ __global__ void __launch_bounds__(128, MINB) trace_bvh_wavefront_kernel(const Tr
                 for (int b = 0; b < RVB_NBANDS / 2; ++b) R.volume[b] = make_float2(S.volume[2 * b][tid], S.volume[2 * b + 1][tid]);
                 Counters c;
                 c.tmin_nz = S.tmin_nz[tid]; c.tmax = S.tmax[tid];
-                shade_and_reflect(acc, P, J, mic, ray, index, tbest, ibest, R, c);
+                shade_and_reflect(acc, P, J, mic, ray, index, tbest, ibest, R, c, nullptr, have_pv ? &pv : nullptr);
                 pos = R.pos; dir = R.dir; S.distance[tid] = R.distance;
 #pragma unroll
                 for (int b = 0; b < RVB_NBANDS / 2; ++b) { S.volume[2 * b][tid] = R.volume[b].x; S.volume[2 * b + 1][tid] = R.volume[b].y; }
