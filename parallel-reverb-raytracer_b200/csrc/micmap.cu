@@ -189,9 +189,10 @@ int micmap_build_batch(const Scene *sc, const float *mics /* [n][3] */, size_t n
     static const int enabled = getenv("RVB_MICMAP") ? atoi(getenv("RVB_MICMAP")) : 1;
     if (!enabled || sc->accel != RVB_ACCEL_BVH || !(sc->diag > 0.0f) || n == 0) return RVB_OK;
     static const double cpt_env = getenv("RVB_MICMAP_CPT") ? atof(getenv("RVB_MICMAP_CPT")) : 0.0;
-    // finer than 16 cells per triangle only pays above ~40 M queries (C3, profiles/r2_micmap_resolution.log: 1 Mi rays x 128,
-    // 48 cells: build +0.7 ms, steady phase -1.9 ms; a 131 k-ray shard: +0.7 / -0.3 ms)
-    const double cap = std::min(48.0, std::max(16.0, 16.0 * (double)nqueries / 40e6));
+    // finer than 16 cells per triangle only pays above ~40 M queries, and little since the wavefront kernel shares
+    // the candidate tests of a serve round among its lanes (C3, profiles/r2_micmap_resolution.log: 1 Mi rays x 128,
+    // trace 50.75 / 50.63 / 50.55 / 50.72 ms at 16 / 24 / 32 / 48 cells; a 131 k-ray shard: 7.46 / 7.41 / 7.43 at 10 / 16 / 24)
+    const double cap = std::min(32.0, std::max(16.0, 16.0 * (double)nqueries / 40e6));
     const double cells_per_tri = forced_cells_per_tri > 0.0 ? forced_cells_per_tri : cpt_env > 0.0 ? cpt_env : std::min(cap, std::max(4.0, (double)nqueries / (2.0 * sc->T)));
     cudaStream_t st = lib_stream();
     MicMapParams M{};
