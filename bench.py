@@ -484,8 +484,8 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
             block["roofline"]["box_tests_per_launch"] = int(steady_boxes)
             block["roofline"]["flop_per_box_test"] = FLOP_PER_BOX
             block["roofline"]["flop_model"] = "tri_tests x 52 + box_tests x 20 (SURVEY 8d); visibility queries go through the microphone map"
-            block["roofline"]["binding_resource"] = ("L1 data pipe and issue slots: ncu l1tex__data_pipe_lsu_wavefronts 65 % of peak, issue active 59 %, "
-                                                     "17.7 of 32 lanes per instruction on this kernel (profiles/r2_c3_shard_kernels_full.md) -- "
+            block["roofline"]["binding_resource"] = ("L1 data pipe and issue slots: ncu l1tex__data_pipe_lsu_wavefronts 70 % of peak, issue active 58 %, "
+                                                     "20.1 of 32 lanes per instruction on this kernel (profiles/r2_c3_shard_kernels_full.md) -- "
                                                      "divergent node fetches, not FP32 or HBM")
             block["roofline"]["micmap"] = {"cells_per_face_edge": int(_mean("micmap_cells", tstats)), "entries": int(_mean("micmap_entries", tstats))}
         if sharded_parity is not None:
