@@ -488,6 +488,10 @@ def measure(wl_name, wl, args, env, steps, warmup, parity=False):
                                                      "20.1 of 32 lanes per instruction on this kernel (profiles/r2_c3_shard_kernels_full.md) -- "
                                                      "divergent node fetches, not FP32 or HBM")
             block["roofline"]["micmap"] = {"cells_per_face_edge": int(_mean("micmap_cells", tstats)), "entries": int(_mean("micmap_entries", tstats))}
+            try:   # what ncu measured on the binding resource (committed capture, not this run)
+                block["roofline"]["ncu_utilisation"] = json.load(open(tp)).get("bvh_ncu_utilisation")
+            except (OSError, ValueError):
+                pass
         if sharded_parity is not None:
             block["sharded_parity"] = sharded_parity
     if pool is not None:
